@@ -1,0 +1,173 @@
+// fovgs_api.cu — the extern "C" surface declared in include/fovgs.h (argument checking, workspace carving,
+// launch orchestration).  No torch types, no allocation, no hidden state.
+#include <stdio.h>
+#include <string.h>
+#include "fovgs_internal.cuh"
+
+using namespace fovgs;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s", where, cudaGetErrorString(e));
+    return FOVGS_ERR_CUDA;
+}
+
+extern "C" {
+
+const char* fovgs_last_error(void) { return g_err; }
+int fovgs_version(void) { return FOVGS_VERSION; }
+
+size_t fovgs_workspace_bytes(int32_t P, int32_t W, int32_t H, int64_t max_instances, int32_t foveated, int32_t ps1_mode) {
+    if (P < 0 || W <= 0 || H <= 0 || max_instances < 0) return 0;
+    const Mode mode = foveated ? MODE_FOV : (ps1_mode == FOVGS_PS1_SUM ? MODE_SUM : MODE_OBB);
+    return carve_workspace(nullptr, P, W, H, max_instances, mode).total_bytes;
+}
+
+static int check_cam(const fovgs_camera& c) {
+    if (c.image_width <= 0 || c.image_height <= 0) return fail(FOVGS_ERR_INVALID_ARG, "image size must be positive%s");
+    if (!c.bg || !c.viewmatrix || !c.projmatrix || !c.campos)
+        return fail(FOVGS_ERR_INVALID_ARG, "camera pointers (bg, viewmatrix, projmatrix, campos) must be non-null%s");
+    return 0;
+}
+
+int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
+    if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_cam(a->cam)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = a->cam.image_width, H = a->cam.image_height;
+    if (a->P < 0) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3)%s");
+    if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
+    if (a->P == 0) return 0;  // reference: outputs stay at their initial value (rasterize_points.cu:103)
+    if (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->shs_dcs || !a->highest_levels || !a->gaze)
+        return fail(FOVGS_ERR_INVALID_ARG, "null input pointer (means3D/opacities/scales/rotations/shs_dcs/highest_levels/gaze)%s");
+    if (a->M_rest > 0 && !a->shs_rest) return fail(FOVGS_ERR_INVALID_ARG, "shs_rest is null but M_rest > 0%s");
+    if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
+    Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, MODE_FOV);
+    if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->M_rest, MODE_FOV, a->gaze, a->alpha, (uint32_t)a->max_instances, st);
+    if (e != cudaSuccess) return fail_cuda(e, "setup");
+    FrameInputs in{};
+    in.P = a->P; in.M = a->M_rest;
+    in.means3D = a->means3D; in.opacities = a->opacities; in.scales = a->scales; in.rotations = a->rotations;
+    in.shs = a->M_rest > 0 ? a->shs_rest : nullptr; in.shs_dcs = a->shs_dcs; in.highest_levels = a->highest_levels;
+    in.radii = a->radii; in.out_color = a->out_color;
+    in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    e = launch_forward(ws, in, W, H, MODE_FOV, a->cam.debug != 0, st);
+    if (e != cudaSuccess) return fail_cuda(e, "forward_fov");
+    return 0;
+}
+
+int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
+    if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_cam(a->cam)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = a->cam.image_width, H = a->cam.image_height;
+    if (a->mode != FOVGS_PS1_OBB && a->mode != FOVGS_PS1_SUM) return fail(FOVGS_ERR_INVALID_ARG, "bad ps1 mode%s");
+    const Mode mode = a->mode == FOVGS_PS1_SUM ? MODE_SUM : MODE_OBB;
+    if (a->P < 0) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3)%s");
+    if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
+    if (a->P == 0) return 0;
+    if (!a->means3D || !a->opacities) return fail(FOVGS_ERR_INVALID_ARG, "null input pointer (means3D/opacities)%s");
+    if (!a->cov3D_precomp && (!a->scales || !a->rotations))
+        return fail(FOVGS_ERR_INVALID_ARG, "provide either scales+rotations or cov3D_precomp%s");
+    if (!a->colors_precomp && !(a->shs && a->M > 0))
+        return fail(FOVGS_ERR_INVALID_ARG, "provide either shs (M>0) or colors_precomp%s");
+    if (mode == MODE_SUM && (!a->gaussians_count || !a->contributions))
+        return fail(FOVGS_ERR_INVALID_ARG, "SUM mode needs gaussians_count and contributions%s");
+    if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
+    Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, mode);
+    if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->colors_precomp ? 0 : a->M, mode, nullptr, 0.0f, (uint32_t)a->max_instances, st);
+    if (e != cudaSuccess) return fail_cuda(e, "setup");
+    FrameInputs in{};
+    in.P = a->P; in.M = a->M;
+    in.means3D = a->means3D; in.opacities = a->opacities; in.scales = a->scales; in.rotations = a->rotations;
+    in.cov3D_precomp = a->cov3D_precomp; in.shs = a->colors_precomp ? nullptr : a->shs; in.colors_precomp = a->colors_precomp;
+    in.radii = a->radii; in.gaussians_count = a->gaussians_count; in.contributions = a->contributions;
+    in.out_color = a->out_color; in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    e = launch_forward(ws, in, W, H, mode, a->cam.debug != 0, st);
+    if (e != cudaSuccess) return fail_cuda(e, "forward_ps1");
+    return 0;
+}
+
+int fovgs_backward_ps1(const fovgs_ps1_bwd_args* a, void* stream) {
+    if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_cam(a->cam)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->P == 0) return 0;
+    if (!a->means3D || !a->radii || !a->dL_dout_color || !a->workspace)
+        return fail(FOVGS_ERR_INVALID_ARG, "null input pointer (means3D/radii/dL_dout_color/workspace)%s");
+    if (!a->dL_dmeans2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolors || !a->dL_dmeans3D || !a->dL_dcov3D)
+        return fail(FOVGS_ERR_INVALID_ARG, "null gradient output pointer%s");
+    if (a->shs && !a->dL_dsh) return fail(FOVGS_ERR_INVALID_ARG, "dL_dsh is null%s");
+    if (a->scales && (!a->rotations || !a->dL_dscales || !a->dL_drotations))
+        return fail(FOVGS_ERR_INVALID_ARG, "scale/rotation gradient outputs are null%s");
+    const int W = a->cam.image_width, H = a->cam.image_height;
+    Workspace ws = carve_workspace(const_cast<void*>(a->workspace), a->P, W, H, a->max_instances, MODE_SUM);
+    if (a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
+    fovgs_ps1_bwd_args b = *a;
+    if (b.colors_precomp) b.shs = nullptr;
+    cudaError_t e = launch_backward(ws, b, st);
+    if (e != cudaSuccess) return fail_cuda(e, "backward_ps1");
+    return 0;
+}
+
+int fovgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                       void* stream) {
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present)))
+        return fail(FOVGS_ERR_INVALID_ARG, "mark_visible: null pointer%s");
+    if (P == 0) return 0;
+    cudaError_t e = launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "mark_visible");
+    return 0;
+}
+
+int fovgs_read_stats_async(const void* workspace, fovgs_frame_stats* stats_host, void* stream) {
+    if (!workspace || !stats_host) return fail(FOVGS_ERR_INVALID_ARG, "read_stats: null pointer%s");
+    cudaError_t e = cudaMemcpyAsync(stats_host, workspace, sizeof(fovgs_frame_stats), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "read_stats");
+    return 0;
+}
+
+int fovgs_fov_tile_tables(const void* workspace, int32_t W, int32_t H, float* tile_level, float* tile_min, float* grad_x,
+                          float* grad_y, uint8_t* blending, void* stream) {
+    if (!workspace) return fail(FOVGS_ERR_INVALID_ARG, "tile_tables: null workspace%s");
+    Workspace ws = carve_workspace(const_cast<void*>(workspace), 0, W, H, 0, MODE_FOV);
+    const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (tile_level && e == cudaSuccess) e = cudaMemcpyAsync(tile_level, ws.tile_level, T * 4, cudaMemcpyDeviceToDevice, st);
+    if (tile_min && e == cudaSuccess) e = cudaMemcpyAsync(tile_min, ws.tile_min, T * 4, cudaMemcpyDeviceToDevice, st);
+    if (grad_x && e == cudaSuccess) e = cudaMemcpyAsync(grad_x, ws.tile_gx, T * 4, cudaMemcpyDeviceToDevice, st);
+    if (grad_y && e == cudaSuccess) e = cudaMemcpyAsync(grad_y, ws.tile_gy, T * 4, cudaMemcpyDeviceToDevice, st);
+    if (blending && e == cudaSuccess) e = cudaMemcpyAsync(blending, ws.tile_blend, T, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail_cuda(e, "tile_tables");
+    return 0;
+}
+
+int fovgs_ps1_geometry(const void* workspace, int32_t P, int32_t W, int32_t H, int32_t ps1_mode, float* means2D, float* depths,
+                       float* conic, float* cov3D, float* rgb, void* stream) {
+    if (!workspace) return fail(FOVGS_ERR_INVALID_ARG, "geometry: null workspace%s");
+    const Mode mode = ps1_mode == FOVGS_PS1_SUM ? MODE_SUM : MODE_OBB;
+    // tile tables and per-Gaussian arrays do not depend on the instance capacity
+    Workspace ws = carve_workspace(const_cast<void*>(workspace), P, W, H, 0, mode);
+    cudaError_t e = launch_export_geometry(ws, P, mode, means2D, depths, conic, cov3D, rgb, nullptr, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "geometry");
+    return 0;
+}
+
+int fovgs_fov_geometry(const void* workspace, int32_t P, int32_t W, int32_t H, float* means2D, float* depths, float* conic,
+                       float* level_colors, void* stream) {
+    if (!workspace) return fail(FOVGS_ERR_INVALID_ARG, "geometry: null workspace%s");
+    Workspace ws = carve_workspace(const_cast<void*>(workspace), P, W, H, 0, MODE_FOV);
+    cudaError_t e = launch_export_geometry(ws, P, MODE_FOV, means2D, depths, conic, nullptr, nullptr, level_colors, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "geometry");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// fovgs_backward.cu — gradient of the PS=1 training rasterizer (diff_gaussian_rasterization_pcheck_obb_sum).
+//
+//   k_bwd_render      <- SUM/cuda_rasterizer/backward.cu:399-557  (renderCUDA, back-to-front re-traversal)
+//   k_bwd_preprocess  <- SUM/cuda_rasterizer/backward.cu:144-274 (computeCov2DCUDA) + :346-396 (preprocessCUDA)
+//                        + :20-139 (SH backward) + :278-343 (cov3D backward), fused into one per-Gaussian pass.
+//
+// B200 design: the reference issues 9 global atomicAdds per (pixel, Gaussian) hit.  Here the 9 partial
+// derivatives are first reduced across the warp with shuffles, accumulated per batch entry in shared memory
+// (one shared atomic per warp and value) and flushed with ONE global atomic per (tile, Gaussian, value).
+#include "fovgs_internal.cuh"
+
+namespace fovgs {
+
+__device__ constexpr float BSH_C0 = 0.28209479177387814f;
+__device__ constexpr float BSH_C1 = 0.4886025119029199f;
+__device__ constexpr float BSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                        -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float BSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                        0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                        -0.5900435899266435f};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* __restrict__ dL_dpixels,
+                                                    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
+                                                    float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors) {
+    __shared__ float4 sA[256];
+    __shared__ float4 sB[256];
+    __shared__ float sCb[256];
+    __shared__ int sId[256];
+    __shared__ float acc[9][256];
+    const FrameHeader* __restrict__ hdr = ws.hdr;
+    const int W = hdr->cam.W, H = hdr->cam.H, gx = hdr->cam.grid_x;
+    const int tile = blockIdx.x;
+    const int tx = tile % gx, ty = tile / gx;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int pxi = tx * TILE + (tid & 15), pyi = ty * TILE + (tid >> 4);
+    const bool inside = pxi < W && pyi < H;
+    const uint32_t pix_id = (uint32_t)W * pyi + pxi;
+    const float pixx = (float)pxi, pixy = (float)pyi;
+    const uint32_t cap = hdr->cap;
+    const uint32_t rbeg = min(ws.tile_offset[tile], cap), rend = min(ws.tile_offset[tile + 1], cap);
+    const int total = (int)(rend - rbeg);
+    if (total == 0) return;
+    const int rounds = (total + 255) / 256;
+    const size_t HW = (size_t)H * W;
+
+    const float T_final = inside ? ws.final_T[pix_id] : 0.0f;
+    float T = T_final;
+    uint32_t contributor = (uint32_t)total;
+    const int last_contributor = inside ? (int)ws.n_contrib[pix_id] : 0;
+    float accum_rec[3] = {0.f, 0.f, 0.f};
+    float dL_dpixel[3] = {0.f, 0.f, 0.f};
+    if (inside) {
+        dL_dpixel[0] = dL_dpixels[pix_id];
+        dL_dpixel[1] = dL_dpixels[HW + pix_id];
+        dL_dpixel[2] = dL_dpixels[2 * HW + pix_id];
+    }
+    float last_alpha = 0.0f;
+    float last_color[3] = {0.f, 0.f, 0.f};
+    const float ddelx_dx = 0.5 * W;
+    const float ddely_dy = 0.5 * H;
+    const float bg_dot_dpixel = hdr->bg[0] * dL_dpixel[0] + hdr->bg[1] * dL_dpixel[1] + hdr->bg[2] * dL_dpixel[2];
+
+    int toDo = total;
+    for (int i = 0; i < rounds; i++, toDo -= 256) {
+        __syncthreads();
+        const int progress = i * 256 + tid;
+        if (progress < total) {
+            const uint32_t id = ws.point_list[rend - progress - 1];
+            const float4* rec = ws.rec + (size_t)REC_PS1 * id;
+            sId[tid] = (int)id;
+            sA[tid] = rec[0];
+            sB[tid] = rec[1];
+            sCb[tid] = rec[2].x;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) acc[k][tid] = 0.0f;
+        __syncthreads();
+        const int lim = min(256, toDo);
+        for (int j = 0; j < lim; j++) {
+            float g[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) g[k] = 0.0f;
+            bool hit = false;
+            if (inside) {
+                contributor--;
+                if ((int)contributor < last_contributor) {
+                    const float4 a = sA[j];
+                    const float4 b = sB[j];
+                    const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
+                    const float power = gauss_power(a.z, a.w, b.x, dx, dy);
+                    if (!(power > 0.0f || power < -4.5f)) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, FM(b.y, G));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            hit = true;
+                            T = T / (1.f - alpha);
+                            const float dchannel_dcolor = alpha * T;
+                            float dL_dalpha = 0.0f;
+                            const float col[3] = {b.z, b.w, sCb[j]};
+#pragma unroll
+                            for (int ch = 0; ch < 3; ch++) {
+                                const float c = col[ch];
+                                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                                last_color[ch] = c;
+                                const float dL_dchannel = dL_dpixel[ch];
+                                dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
+                                g[ch] = dchannel_dcolor * dL_dchannel;
+                            }
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                            const float dL_dG = b.y * dL_dalpha;
+                            const float gdx = G * dx;
+                            const float gdy = G * dy;
+                            const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                            const float dG_ddely = -gdy * b.x - gdx * a.w;
+                            g[3] = dL_dG * dG_ddelx * ddelx_dx;
+                            g[4] = dL_dG * dG_ddely * ddely_dy;
+                            g[5] = -0.5f * gdx * dx * dL_dG;
+                            g[6] = -0.5f * gdx * dy * dL_dG;
+                            g[7] = -0.5f * gdy * dy * dL_dG;
+                            g[8] = G * dL_dalpha;
+                        }
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const float v = warp_sum(g[k]);
+                    if (lane == 0) atomicAdd(&acc[k][j], v);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < lim) {
+            const int id = sId[tid];
+            float v[9];
+            bool nz = false;
+#pragma unroll
+            for (int k = 0; k < 9; k++) { v[k] = acc[k][tid]; nz = nz || (v[k] != 0.0f); }
+            if (nz) {
+                atomicAdd(&dL_dcolors[3 * (size_t)id + 0], v[0]);
+                atomicAdd(&dL_dcolors[3 * (size_t)id + 1], v[1]);
+                atomicAdd(&dL_dcolors[3 * (size_t)id + 2], v[2]);
+                atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], v[3]);
+                atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], v[4]);
+                atomicAdd(&dL_dconic[4 * (size_t)id + 0], v[5]);
+                atomicAdd(&dL_dconic[4 * (size_t)id + 1], v[6]);
+                atomicAdd(&dL_dconic[4 * (size_t)id + 3], v[7]);
+                atomicAdd(&dL_dopacity[id], v[8]);
+            }
+        }
+    }
+}
+
+// normalisation backward (SUM/auxiliary.h dnormvdv, float3)
+__device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
+    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    float3 r;
+    r.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+    r.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+    r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_bwd_preprocess(Workspace ws, fovgs_ps1_bwd_args a) {
+    __shared__ CamParams cam;
+    {
+        const int n = (int)(sizeof(CamParams) / 4);
+        const uint32_t* src = (const uint32_t*)&ws.hdr->cam;
+        uint32_t* dst = (uint32_t*)&cam;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P || !(a.radii[idx] > 0)) return;
+    const float* v = cam.view;
+    const float* proj = cam.proj;
+    const float3 mean = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+
+    // ---------------- computeCov2DCUDA (backward.cu:144-274) ----------------
+    const float* cov3D = a.cov3D_precomp ? a.cov3D_precomp + 6 * (size_t)idx : ws.cov3D + 6 * (size_t)idx;
+    const float3 dL_dconic = make_float3(a.dL_dconic[4 * (size_t)idx], a.dL_dconic[4 * (size_t)idx + 1], a.dL_dconic[4 * (size_t)idx + 3]);
+    float3 t;
+    t.x = v[0] * mean.x + v[4] * mean.y + v[8] * mean.z + v[12];
+    t.y = v[1] * mean.x + v[5] * mean.y + v[9] * mean.z + v[13];
+    t.z = v[2] * mean.x + v[6] * mean.y + v[10] * mean.z + v[14];
+    const float limx = 1.3f * cam.tanfovx, limy = 1.3f * cam.tanfovy;
+    const float txtz = t.x / t.z, tytz = t.y / t.z;
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+    const float h_x = cam.focal_x, h_y = cam.focal_y;
+    const float J00 = h_x / t.z, J02 = -(h_x * t.x) / (t.z * t.z);
+    const float J11 = h_y / t.z, J12 = -(h_y * t.y) / (t.z * t.z);
+    // T[a][b] in glm (column a, row b); only columns 0 and 1 are non-zero
+    const float T00 = v[0] * J00 + v[2] * J02, T01 = v[4] * J00 + v[6] * J02, T02 = v[8] * J00 + v[10] * J02;
+    const float T10 = v[1] * J11 + v[2] * J12, T11 = v[5] * J11 + v[6] * J12, T12 = v[9] * J11 + v[10] * J12;
+    const float V00 = cov3D[0], V01 = cov3D[1], V02 = cov3D[2], V11 = cov3D[3], V12 = cov3D[4], V22 = cov3D[5];
+    // rows of T applied to Vrk
+    const float TV0_0 = T00 * V00 + T01 * V01 + T02 * V02;
+    const float TV0_1 = T00 * V01 + T01 * V11 + T02 * V12;
+    const float TV0_2 = T00 * V02 + T01 * V12 + T02 * V22;
+    const float TV1_0 = T10 * V00 + T11 * V01 + T12 * V02;
+    const float TV1_1 = T10 * V01 + T11 * V11 + T12 * V12;
+    const float TV1_2 = T10 * V02 + T11 * V12 + T12 * V22;
+    const float ca = (TV0_0 * T00 + TV0_1 * T01 + TV0_2 * T02) + 0.3f;
+    const float cb = (TV0_0 * T10 + TV0_1 * T11 + TV0_2 * T12);
+    const float cc = (TV1_0 * T10 + TV1_1 * T11 + TV1_2 * T12) + 0.3f;
+    const float denom = ca * cc - cb * cb;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    float dcov[6] = {0, 0, 0, 0, 0, 0};
+    if (denom2inv != 0) {
+        dL_da = denom2inv * (-cc * cc * dL_dconic.x + 2 * cb * cc * dL_dconic.y + (denom - ca * cc) * dL_dconic.z);
+        dL_dc = denom2inv * (-ca * ca * dL_dconic.z + 2 * ca * cb * dL_dconic.y + (denom - ca * cc) * dL_dconic.x);
+        dL_db = denom2inv * 2 * (cb * cc * dL_dconic.x - (denom + 2 * cb * cb) * dL_dconic.y + ca * cb * dL_dconic.z);
+        dcov[0] = (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
+        dcov[3] = (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
+        dcov[5] = (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
+        dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+        dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+        dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+    const float dL_dT00 = 2 * TV0_0 * dL_da + TV1_0 * dL_db;
+    const float dL_dT01 = 2 * TV0_1 * dL_da + TV1_1 * dL_db;
+    const float dL_dT02 = 2 * TV0_2 * dL_da + TV1_2 * dL_db;
+    const float dL_dT10 = 2 * TV1_0 * dL_dc + TV0_0 * dL_db;
+    const float dL_dT11 = 2 * TV1_1 * dL_dc + TV0_1 * dL_db;
+    const float dL_dT12 = 2 * TV1_2 * dL_dc + TV0_2 * dL_db;
+    const float dL_dJ00 = v[0] * dL_dT00 + v[4] * dL_dT01 + v[8] * dL_dT02;
+    const float dL_dJ02 = v[2] * dL_dT00 + v[6] * dL_dT01 + v[10] * dL_dT02;
+    const float dL_dJ11 = v[1] * dL_dT10 + v[5] * dL_dT11 + v[9] * dL_dT12;
+    const float dL_dJ12 = v[2] * dL_dT10 + v[6] * dL_dT11 + v[10] * dL_dT12;
+    const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+    const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+    float3 dmean;   // transformVec4x3Transpose
+    dmean.x = v[0] * dL_dtx + v[1] * dL_dty + v[2] * dL_dtz;
+    dmean.y = v[4] * dL_dtx + v[5] * dL_dty + v[6] * dL_dtz;
+    dmean.z = v[8] * dL_dtx + v[9] * dL_dty + v[10] * dL_dtz;
+
+    // ---------------- preprocessCUDA backward (backward.cu:346-396) ----------------
+    {
+        const float m_hw = proj[3] * mean.x + proj[7] * mean.y + proj[11] * mean.z + proj[15];
+        const float m_w = 1.0f / (m_hw + 0.0000001f);
+        const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+        const float g2x = a.dL_dmeans2D[3 * (size_t)idx], g2y = a.dL_dmeans2D[3 * (size_t)idx + 1];
+        dmean.x += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
+        dmean.y += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
+        dmean.z += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+    }
+
+    // ---------------- SH backward (backward.cu:20-139) ----------------
+    if (a.shs != nullptr) {
+        const int M = a.M, deg = cam.sh_degree;
+        const float3 dir_orig = make_float3(mean.x - cam.campos[0], mean.y - cam.campos[1], mean.z - cam.campos[2]);
+        const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+        const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+        const float* sh = a.shs + (size_t)3 * M * idx;
+        float* dsh = a.dL_dsh + (size_t)3 * M * idx;
+        const uchar4 cl = reinterpret_cast<const uchar4*>(ws.clamped)[idx];
+        float dRGB[3] = {a.dL_dcolors[3 * (size_t)idx], a.dL_dcolors[3 * (size_t)idx + 1], a.dL_dcolors[3 * (size_t)idx + 2]};
+        dRGB[0] *= cl.x ? 0.f : 1.f;
+        dRGB[1] *= cl.y ? 0.f : 1.f;
+        dRGB[2] *= cl.z ? 0.f : 1.f;
+        float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
+        auto S = [&](int k, int ch) { return sh[3 * k + ch]; };
+        auto W3 = [&](int k, float w) {
+            dsh[3 * k + 0] = w * dRGB[0];
+            dsh[3 * k + 1] = w * dRGB[1];
+            dsh[3 * k + 2] = w * dRGB[2];
+        };
+        W3(0, BSH_C0);
+        if (deg > 0) {
+            W3(1, -BSH_C1 * y);
+            W3(2, BSH_C1 * z);
+            W3(3, -BSH_C1 * x);
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                dRGBdx[ch] = -BSH_C1 * S(3, ch);
+                dRGBdy[ch] = -BSH_C1 * S(1, ch);
+                dRGBdz[ch] = BSH_C1 * S(2, ch);
+            }
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                W3(4, BSH_C2[0] * xy);
+                W3(5, BSH_C2[1] * yz);
+                W3(6, BSH_C2[2] * (2.f * zz - xx - yy));
+                W3(7, BSH_C2[3] * xz);
+                W3(8, BSH_C2[4] * (xx - yy));
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    dRGBdx[ch] += BSH_C2[0] * y * S(4, ch) + BSH_C2[2] * 2.f * -x * S(6, ch) + BSH_C2[3] * z * S(7, ch) + BSH_C2[4] * 2.f * x * S(8, ch);
+                    dRGBdy[ch] += BSH_C2[0] * x * S(4, ch) + BSH_C2[1] * z * S(5, ch) + BSH_C2[2] * 2.f * -y * S(6, ch) + BSH_C2[4] * 2.f * -y * S(8, ch);
+                    dRGBdz[ch] += BSH_C2[1] * y * S(5, ch) + BSH_C2[2] * 2.f * 2.f * z * S(6, ch) + BSH_C2[3] * x * S(7, ch);
+                }
+                if (deg > 2) {
+                    W3(9, BSH_C3[0] * y * (3.f * xx - yy));
+                    W3(10, BSH_C3[1] * xy * z);
+                    W3(11, BSH_C3[2] * y * (4.f * zz - xx - yy));
+                    W3(12, BSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                    W3(13, BSH_C3[4] * x * (4.f * zz - xx - yy));
+                    W3(14, BSH_C3[5] * z * (xx - yy));
+                    W3(15, BSH_C3[6] * x * (xx - 3.f * yy));
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        dRGBdx[ch] += (BSH_C3[0] * S(9, ch) * 3.f * 2.f * xy + BSH_C3[1] * S(10, ch) * yz + BSH_C3[2] * S(11, ch) * -2.f * xy +
+                                       BSH_C3[3] * S(12, ch) * -3.f * 2.f * xz + BSH_C3[4] * S(13, ch) * (-3.f * xx + 4.f * zz - yy) +
+                                       BSH_C3[5] * S(14, ch) * 2.f * xz + BSH_C3[6] * S(15, ch) * 3.f * (xx - yy));
+                        dRGBdy[ch] += (BSH_C3[0] * S(9, ch) * 3.f * (xx - yy) + BSH_C3[1] * S(10, ch) * xz +
+                                       BSH_C3[2] * S(11, ch) * (-3.f * yy + 4.f * zz - xx) + BSH_C3[3] * S(12, ch) * -3.f * 2.f * yz +
+                                       BSH_C3[4] * S(13, ch) * -2.f * xy + BSH_C3[5] * S(14, ch) * -2.f * yz +
+                                       BSH_C3[6] * S(15, ch) * -3.f * 2.f * xy);
+                        dRGBdz[ch] += (BSH_C3[1] * S(10, ch) * xy + BSH_C3[2] * S(11, ch) * 4.f * 2.f * yz +
+                                       BSH_C3[3] * S(12, ch) * 3.f * (2.f * zz - xx - yy) + BSH_C3[4] * S(13, ch) * 4.f * 2.f * xz +
+                                       BSH_C3[5] * S(14, ch) * (xx - yy));
+                    }
+                }
+            }
+        }
+        const float3 dL_ddir = make_float3(dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
+                                           dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
+                                           dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]);
+        const float3 dm = dnormvdv3(dir_orig, dL_ddir);
+        dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
+    }
+    a.dL_dmeans3D[3 * (size_t)idx + 0] = dmean.x;
+    a.dL_dmeans3D[3 * (size_t)idx + 1] = dmean.y;
+    a.dL_dmeans3D[3 * (size_t)idx + 2] = dmean.z;
+
+    // ---------------- cov3D -> scale / rotation (backward.cu:278-343) ----------------
+    if (a.scales != nullptr) {
+        const float mod = cam.scale_modifier;
+        const float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        // R in math (row,col) convention == glm R[col][row]
+        float Rm[3][3];
+        Rm[0][0] = 1.f - 2.f * (y * y + z * z); Rm[1][0] = 2.f * (x * y - r * z); Rm[2][0] = 2.f * (x * z + r * y);
+        Rm[0][1] = 2.f * (x * y + r * z); Rm[1][1] = 1.f - 2.f * (x * x + z * z); Rm[2][1] = 2.f * (y * z - r * x);
+        Rm[0][2] = 2.f * (x * z - r * y); Rm[1][2] = 2.f * (y * z + r * x); Rm[2][2] = 1.f - 2.f * (x * x + y * y);
+        const float s[3] = {mod * a.scales[3 * (size_t)idx], mod * a.scales[3 * (size_t)idx + 1], mod * a.scales[3 * (size_t)idx + 2]};
+        float Mm[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Mm[i][j] = s[i] * Rm[i][j];
+        float D[3][3];
+        D[0][0] = dcov[0]; D[0][1] = 0.5f * dcov[1]; D[0][2] = 0.5f * dcov[2];
+        D[1][0] = 0.5f * dcov[1]; D[1][1] = dcov[3]; D[1][2] = 0.5f * dcov[4];
+        D[2][0] = 0.5f * dcov[2]; D[2][1] = 0.5f * dcov[4]; D[2][2] = dcov[5];
+        float dM[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) dM[i][j] = 2.0f * Mm[i][0] * D[0][j] + 2.0f * Mm[i][1] * D[1][j] + 2.0f * Mm[i][2] * D[2][j];
+        float ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) ds[i] = Rm[i][0] * dM[i][0] + Rm[i][1] * dM[i][1] + Rm[i][2] * dM[i][2];
+        // the reference multiplies by scale_modifier implicitly? No: dL_dscale is w.r.t. the raw scale entry times
+        // nothing else (backward.cu:321-324 writes dot(Rt[i], dL_dMt[i])), keep as is.
+        a.dL_dscales[3 * (size_t)idx + 0] = ds[0];
+        a.dL_dscales[3 * (size_t)idx + 1] = ds[1];
+        a.dL_dscales[3 * (size_t)idx + 2] = ds[2];
+        float E[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) E[i][j] = dM[i][j] * s[i];
+        float4 dq;
+        dq.x = 2 * z * (E[0][1] - E[1][0]) + 2 * y * (E[2][0] - E[0][2]) + 2 * x * (E[1][2] - E[2][1]);
+        dq.y = 2 * y * (E[1][0] + E[0][1]) + 2 * z * (E[2][0] + E[0][2]) + 2 * r * (E[1][2] - E[2][1]) - 4 * x * (E[2][2] + E[1][1]);
+        dq.z = 2 * x * (E[1][0] + E[0][1]) + 2 * r * (E[2][0] - E[0][2]) + 2 * z * (E[1][2] + E[2][1]) - 4 * y * (E[2][2] + E[0][0]);
+        dq.w = 2 * r * (E[0][1] - E[1][0]) + 2 * x * (E[2][0] + E[0][2]) + 2 * y * (E[1][2] + E[2][1]) - 4 * z * (E[1][1] + E[0][0]);
+        *reinterpret_cast<float4*>(a.dL_drotations + 4 * (size_t)idx) = dq;
+    }
+}
+
+cudaError_t launch_backward(const Workspace& ws, const fovgs_ps1_bwd_args& a, cudaStream_t st) {
+    const int W = a.cam.image_width, H = a.cam.image_height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const int T = gx * gy;
+    k_bwd_render<<<T, 256, 0, st>>>(ws, a.dL_dout_color, a.dL_dmeans2D, a.dL_dconic, a.dL_dopacity, a.dL_dcolors);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (a.cam.debug) { e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e; }
+    k_bwd_preprocess<<<(a.P + 255) / 256, 256, 0, st>>>(ws, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (a.cam.debug) e = cudaStreamSynchronize(st);
+    return e;
+}
+
+}  // namespace fovgs

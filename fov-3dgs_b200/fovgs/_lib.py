@@ -1,0 +1,176 @@
+"""ctypes binding of libfovgs.so (the C-ABI declared in include/fovgs.h).
+
+The library is hand-written CUDA for sm_100a; there is NO fallback: if the shared object is missing or a
+call fails, a RuntimeError is raised (the reference raises RuntimeError from AT_ERROR / CHECK_CUDA the same way,
+FOV/rasterize_points.cu:64-66, FOV/cuda_rasterizer/auxiliary.h:298-305).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfovgs.so")
+
+FOVGS_PS1_OBB = 0
+FOVGS_PS1_SUM = 1
+
+_f = C.c_void_p  # all device pointers travel as void*
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("image_height", C.c_int32),
+        ("image_width", C.c_int32),
+        ("tanfovx", C.c_float),
+        ("tanfovy", C.c_float),
+        ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32),
+        ("prefiltered", C.c_int32),
+        ("debug", C.c_int32),
+        ("bg", _f),
+        ("viewmatrix", _f),
+        ("projmatrix", _f),
+        ("campos", _f),
+    ]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [
+        ("num_rendered", C.c_uint32),
+        ("overflow", C.c_uint32),
+        ("num_visible", C.c_uint32),
+        ("num_blend_tiles", C.c_uint32),
+        ("max_tile_instances", C.c_uint32),
+        ("reserved", C.c_uint32 * 11),
+    ]
+
+
+class FovFwdArgs(C.Structure):
+    _fields_ = [
+        ("cam", Camera),
+        ("P", C.c_int32),
+        ("M_rest", C.c_int32),
+        ("means3D", _f),
+        ("opacities", _f),
+        ("scales", _f),
+        ("rotations", _f),
+        ("shs_rest", _f),
+        ("shs_dcs", _f),
+        ("highest_levels", _f),
+        ("gaze", _f),
+        ("alpha", C.c_float),
+        ("blending", C.c_int32),
+        ("out_color", _f),
+        ("radii", _f),
+        ("workspace", _f),
+        ("workspace_bytes", C.c_size_t),
+        ("max_instances", C.c_int64),
+        ("out_point_list", _f),
+        ("out_ranges", _f),
+    ]
+
+
+class Ps1FwdArgs(C.Structure):
+    _fields_ = [
+        ("cam", Camera),
+        ("mode", C.c_int32),
+        ("P", C.c_int32),
+        ("M", C.c_int32),
+        ("means3D", _f),
+        ("opacities", _f),
+        ("scales", _f),
+        ("rotations", _f),
+        ("cov3D_precomp", _f),
+        ("shs", _f),
+        ("colors_precomp", _f),
+        ("out_color", _f),
+        ("radii", _f),
+        ("gaussians_count", _f),
+        ("contributions", _f),
+        ("workspace", _f),
+        ("workspace_bytes", C.c_size_t),
+        ("max_instances", C.c_int64),
+        ("out_point_list", _f),
+        ("out_ranges", _f),
+    ]
+
+
+class Ps1BwdArgs(C.Structure):
+    _fields_ = [
+        ("cam", Camera),
+        ("P", C.c_int32),
+        ("M", C.c_int32),
+        ("means3D", _f),
+        ("scales", _f),
+        ("rotations", _f),
+        ("cov3D_precomp", _f),
+        ("shs", _f),
+        ("colors_precomp", _f),
+        ("radii", _f),
+        ("dL_dout_color", _f),
+        ("workspace", _f),
+        ("workspace_bytes", C.c_size_t),
+        ("max_instances", C.c_int64),
+        ("dL_dmeans2D", _f),
+        ("dL_dconic", _f),
+        ("dL_dopacity", _f),
+        ("dL_dcolors", _f),
+        ("dL_dmeans3D", _f),
+        ("dL_dcov3D", _f),
+        ("dL_dsh", _f),
+        ("dL_dscales", _f),
+        ("dL_drotations", _f),
+    ]
+
+
+# every symbol include/fovgs.h declares (tests/test_abi.py checks this list against the header)
+EXPORTS = (
+    "fovgs_workspace_bytes",
+    "fovgs_forward_fov",
+    "fovgs_forward_ps1",
+    "fovgs_backward_ps1",
+    "fovgs_mark_visible",
+    "fovgs_read_stats_async",
+    "fovgs_fov_tile_tables",
+    "fovgs_ps1_geometry",
+    "fovgs_fov_geometry",
+    "fovgs_last_error",
+    "fovgs_version",
+)
+
+_lib = None
+
+
+def lib():
+    """Load libfovgs.so once.  Raises RuntimeError when it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libfovgs.so not found at {LIB_PATH}: build it with `make -C fov-3dgs_b200` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU/PyTorch fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.fovgs_last_error.restype = C.c_char_p
+    L.fovgs_version.restype = C.c_int
+    L.fovgs_workspace_bytes.restype = C.c_size_t
+    L.fovgs_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+    L.fovgs_forward_fov.argtypes = [C.POINTER(FovFwdArgs), C.c_void_p]
+    L.fovgs_forward_ps1.argtypes = [C.POINTER(Ps1FwdArgs), C.c_void_p]
+    L.fovgs_backward_ps1.argtypes = [C.POINTER(Ps1BwdArgs), C.c_void_p]
+    L.fovgs_mark_visible.argtypes = [C.c_int32, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_read_stats_async.argtypes = [_f, _f, C.c_void_p]
+    L.fovgs_fov_tile_tables.argtypes = [_f, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_ps1_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_fov_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, C.c_void_p]
+    for fn in ("fovgs_forward_fov", "fovgs_forward_ps1", "fovgs_backward_ps1", "fovgs_mark_visible",
+               "fovgs_read_stats_async", "fovgs_fov_tile_tables", "fovgs_ps1_geometry", "fovgs_fov_geometry"):
+        getattr(L, fn).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().fovgs_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")

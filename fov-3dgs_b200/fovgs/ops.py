@@ -1,0 +1,410 @@
+"""Torch-facing operators on top of the C-ABI: tensor checks, output/workspace allocation (torch's caching
+allocator owns all memory, like the reference's resizeFunctional callbacks, FOV/rasterize_points.cu:27-33) and
+the overflow protocol.  These replace the reference's C++ glue functions:
+
+  forward_fov   <- RasterizeGaussiansCUDA          FOV/rasterize_points.cu:35-152
+  forward_ps1   <- RasterizeGaussiansCUDA          OBB|SUM/rasterize_points.cu:35-135
+  backward_ps1  <- RasterizeGaussiansBackwardCUDA  SUM/rasterize_points.cu:137-216
+  mark_visible  <- markVisible                     FOV/rasterize_points.cu:236-253
+
+Host synchronisation: the reference blocks four times per frame (2x .item(), 2x cudaMemcpy).  Here nothing in
+the kernel pipeline synchronises; the only host wait is ONE read of the 64-byte frame statistics after all
+launches are queued (to detect instance-capacity overflow and to return `num_rendered`).  Set
+FOVGS_DEFERRED_CHECK=1 to skip even that (the previous frame's statistics are then checked at the next call).
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import Camera, FovFwdArgs, FrameStats, Ps1BwdArgs, Ps1FwdArgs, check, lib
+
+MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
+_DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _prep(t, name, device, dtype=torch.float32, optional=False):
+    """Contiguous fp32 CUDA view of an input (reference: `.contiguous().data<float>()`); empty -> None (Q13)."""
+    if t is None or (isinstance(t, torch.Tensor) and t.numel() == 0):
+        if optional:
+            return None
+        raise RuntimeError(f"{name} must be a non-empty tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _camera(rs, device, keep):
+    bg = _prep(rs.bg, "bg", device)
+    view = _prep(rs.viewmatrix, "viewmatrix", device)
+    proj = _prep(rs.projmatrix, "projmatrix", device)
+    campos = _prep(rs.campos, "campos", device)
+    keep += [bg, view, proj, campos]
+    cam = Camera()
+    cam.image_height = int(rs.image_height)
+    cam.image_width = int(rs.image_width)
+    cam.tanfovx = float(rs.tanfovx)
+    cam.tanfovy = float(rs.tanfovy)
+    cam.scale_modifier = float(rs.scale_modifier)
+    cam.sh_degree = int(rs.sh_degree)
+    cam.prefiltered = int(bool(rs.prefiltered))
+    cam.debug = int(bool(rs.debug))
+    cam.bg = bg.data_ptr()
+    cam.viewmatrix = view.data_ptr()
+    cam.projmatrix = proj.data_ptr()
+    cam.campos = campos.data_ptr()
+    return cam
+
+
+class _Pool:
+    """Reusable workspaces for the inference paths, one per (device, mode, P, W, H)."""
+
+    def __init__(self):
+        self.items = {}
+
+    def get(self, device, mode, P, W, H, min_cap=0):
+        key = (device.index, mode, P, W, H)
+        it = self.items.get(key)
+        if it is None or it["cap"] < min_cap:
+            cap = max(min_cap, _initial_capacity(P))
+            it = _new_workspace(device, mode, P, W, H, cap)
+            self.items[key] = it
+        return it
+
+    def clear(self):
+        self.items.clear()
+
+
+def _initial_capacity(P):
+    env = os.environ.get("FOVGS_INSTANCE_CAPACITY")
+    if env:
+        return int(env)
+    return int(min(max(1 << 20, 8 * P), 0xFFFFFFF0))
+
+
+def _new_workspace(device, mode, P, W, H, cap):
+    nbytes = lib().fovgs_workspace_bytes(P, W, H, cap, 1 if mode == MODE_FOV else 0, 1 if mode == MODE_SUM else 0)
+    if nbytes == 0:
+        raise RuntimeError("fovgs_workspace_bytes rejected the frame configuration")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    stats = torch.zeros(16, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(16, dtype=torch.int32)
+    return {"ws": ws, "cap": cap, "bytes": nbytes, "stats": stats, "pending": False}
+
+
+_pool = _Pool()
+
+
+def _read_stats(item, stream):
+    check(lib().fovgs_read_stats_async(item["ws"].data_ptr(), item["stats"].data_ptr(), stream), "fovgs_read_stats_async")
+
+
+def _stats_dict(item):
+    s = item["stats"]
+    return {
+        "num_rendered": int(s[0]) & 0xFFFFFFFF,
+        "overflow": int(s[1]),
+        "num_visible": int(s[2]) & 0xFFFFFFFF,
+        "num_blend_tiles": int(s[3]) & 0xFFFFFFFF,
+        "max_tile_instances": int(s[4]) & 0xFFFFFFFF,
+    }
+
+
+last_stats = {}
+
+
+def _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace):
+    """Runs `launch(item)`; on instance overflow grows the workspace and re-runs (no silent truncation)."""
+    global last_stats
+    stream = torch.cuda.current_stream(device).cuda_stream
+    min_cap = 0
+    while True:
+        if fresh_workspace:
+            cap = max(min_cap, _train_capacity_hint.get((device.index, P, W, H), _initial_capacity(P)))
+            item = _new_workspace(device, mode, P, W, H, cap)
+        else:
+            item = _pool.get(device, mode, P, W, H, min_cap)
+            if _DEFERRED and item["pending"]:
+                # previous frame's statistics have long landed in pinned memory
+                st = _stats_dict(item)
+                if st["overflow"]:
+                    raise RuntimeError("fovgs: the previous frame overflowed its instance capacity "
+                                       f"({st['num_rendered']} > {item['cap']}); re-run without FOVGS_DEFERRED_CHECK")
+        launch(item, stream)
+        _read_stats(item, stream)
+        if _DEFERRED and not fresh_workspace:
+            item["pending"] = True
+            return item, None
+        torch.cuda.current_stream(device).synchronize()
+        st = _stats_dict(item)
+        last_stats = st
+        if not st["overflow"]:
+            if fresh_workspace:
+                _train_capacity_hint[(device.index, P, W, H)] = max(1 << 20, int(st["num_rendered"] * 1.25) + 1024)
+            return item, st
+        min_cap = int(st["num_rendered"] * 1.25) + 1024
+
+
+_train_capacity_hint = {}
+
+
+def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highest_levels, gazeArray, alpha, blending,
+                raster_settings, want_lists=False):
+    """Foveated forward.  Returns (num_rendered, color[3,H,W], radii[P]) (+ point_list, ranges when want_lists)."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    device = means3D.device
+    rs = raster_settings
+    H, W = int(rs.image_height), int(rs.image_width)
+    P = means3D.size(0)
+    if P == 0:
+        z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
+        return 0, z, torch.zeros((0,), dtype=torch.int32, device=device)
+    keep = []
+    means3D = _prep(means3D, "means3D", device)
+    opacities = _prep(opacities, "opacities", device)
+    if opacities.numel() != P * 4:
+        raise RuntimeError("opacities must have dimensions (num_points, 4) for the foveated rasterizer")
+    scales = _prep(scales, "scales", device)
+    rotations = _prep(rotations, "rotations", device)
+    shs_rest = _prep(shs_rest, "shs_rest", device, optional=True)
+    shs_dcs = _prep(shs_dcs, "shs_dcs", device)
+    highest_levels = _prep(highest_levels, "highest_levels", device)
+    if shs_dcs.numel() != P * 12 or highest_levels.numel() != P:
+        raise RuntimeError("shs_dcs must be (P,4,3) and highest_levels (P,1)")
+    gaze = gazeArray
+    if not isinstance(gaze, torch.Tensor):
+        gaze = torch.tensor([float(gaze[0]), float(gaze[1])], dtype=torch.float32)
+    if not gaze.is_cuda:
+        gaze = gaze.to(device, non_blocking=True)
+    gaze = _prep(gaze, "gazeArray", device)
+    M_rest = 0 if shs_rest is None else int(shs_rest.size(1))
+    cam = _camera(rs, device, keep)
+    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    lists = {}
+
+    def launch(item, stream):
+        a = FovFwdArgs()
+        a.cam = cam
+        a.P = P
+        a.M_rest = M_rest
+        a.means3D = means3D.data_ptr()
+        a.opacities = opacities.data_ptr()
+        a.scales = scales.data_ptr()
+        a.rotations = rotations.data_ptr()
+        a.shs_rest = _ptr(shs_rest)
+        a.shs_dcs = shs_dcs.data_ptr()
+        a.highest_levels = highest_levels.data_ptr()
+        a.gaze = gaze.data_ptr()
+        a.alpha = float(alpha) if alpha is not None else 0.0
+        a.blending = int(bool(blending))
+        a.out_color = color.data_ptr()
+        a.radii = radii.data_ptr()
+        a.workspace = item["ws"].data_ptr()
+        a.workspace_bytes = item["bytes"]
+        a.max_instances = item["cap"]
+        if want_lists:
+            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
+            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
+            a.out_point_list = lists["point_list"].data_ptr()
+            a.out_ranges = lists["ranges"].data_ptr()
+        check(lib().fovgs_forward_fov(C.byref(a), stream), "fovgs_forward_fov")
+
+    item, st = _run_with_capacity(launch, device, MODE_FOV, P, W, H, fresh_workspace=False)
+    n = st["num_rendered"] if st is not None else -1
+    if want_lists:
+        return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item
+    return n, color, radii
+
+
+def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs, colors_precomp, raster_settings,
+                want_lists=False):
+    """PS=1 forward (mode = MODE_OBB | MODE_SUM).
+    Returns (num_rendered, color, radii, workspace_item[, gaussians_count, contributions][, point_list, ranges])."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    device = means3D.device
+    rs = raster_settings
+    H, W = int(rs.image_height), int(rs.image_width)
+    P = means3D.size(0)
+    sum_mode = mode == MODE_SUM
+    if P == 0:
+        z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
+        r = torch.zeros((0,), dtype=torch.int32, device=device)
+        out = [0, z, r, None]
+        if sum_mode:
+            out += [torch.zeros((0,), dtype=torch.int32, device=device), torch.zeros((0,), dtype=torch.float32, device=device)]
+        return tuple(out)
+    keep = []
+    means3D = _prep(means3D, "means3D", device)
+    opacities = _prep(opacities, "opacities", device)
+    scales = _prep(scales, "scales", device, optional=True)
+    rotations = _prep(rotations, "rotations", device, optional=True)
+    cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device, optional=True)
+    shs = _prep(shs, "shs", device, optional=True)
+    colors_precomp = _prep(colors_precomp, "colors_precomp", device, optional=True)
+    M = 0 if shs is None else int(shs.size(1))
+    cam = _camera(rs, device, keep)
+    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    gcount = contrib = None
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    lists = {}
+    extra = {}
+
+    def launch(item, stream):
+        a = Ps1FwdArgs()
+        a.cam = cam
+        a.mode = _lib.FOVGS_PS1_SUM if sum_mode else _lib.FOVGS_PS1_OBB
+        a.P = P
+        a.M = M
+        a.means3D = means3D.data_ptr()
+        a.opacities = opacities.data_ptr()
+        a.scales = _ptr(scales)
+        a.rotations = _ptr(rotations)
+        a.cov3D_precomp = _ptr(cov3D_precomp)
+        a.shs = _ptr(shs)
+        a.colors_precomp = _ptr(colors_precomp)
+        a.out_color = color.data_ptr()
+        a.radii = radii.data_ptr()
+        if sum_mode:
+            extra["gcount"] = torch.zeros((P,), dtype=torch.int32, device=device)
+            extra["contrib"] = torch.zeros((P,), dtype=torch.float32, device=device)
+            a.gaussians_count = extra["gcount"].data_ptr()
+            a.contributions = extra["contrib"].data_ptr()
+        a.workspace = item["ws"].data_ptr()
+        a.workspace_bytes = item["bytes"]
+        a.max_instances = item["cap"]
+        if want_lists:
+            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
+            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
+            a.out_point_list = lists["point_list"].data_ptr()
+            a.out_ranges = lists["ranges"].data_ptr()
+        check(lib().fovgs_forward_ps1(C.byref(a), stream), "fovgs_forward_ps1")
+
+    item, st = _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace=sum_mode)
+    n = st["num_rendered"] if st is not None else -1
+    out = [n, color, radii, item]
+    if sum_mode:
+        out += [extra["gcount"], extra["contrib"]]
+    if want_lists:
+        out += [lists["point_list"][: max(n, 0)], lists["ranges"]]
+    return tuple(out)
+
+
+def backward_ps1(workspace_item, means3D, radii, scales, rotations, cov3D_precomp, shs, colors_precomp, raster_settings,
+                 grad_out_color):
+    """Gradient of the SUM forward.  Returns the reference's 8-tuple
+    (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
+    device = means3D.device
+    rs = raster_settings
+    P = means3D.size(0)
+    keep = []
+    means3D = _prep(means3D, "means3D", device)
+    scales = _prep(scales, "scales", device, optional=True)
+    rotations = _prep(rotations, "rotations", device, optional=True)
+    cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device, optional=True)
+    shs = _prep(shs, "shs", device, optional=True)
+    colors_precomp = _prep(colors_precomp, "colors_precomp", device, optional=True)
+    M = 0 if shs is None else int(shs.size(1))
+    opts = dict(dtype=torch.float32, device=device)
+    dL_dmeans3D = torch.zeros((P, 3), **opts)
+    dL_dmeans2D = torch.zeros((P, 3), **opts)
+    dL_dcolors = torch.zeros((P, 3), **opts)
+    dL_dconic = torch.zeros((P, 2, 2), **opts)
+    dL_dopacity = torch.zeros((P, 1), **opts)
+    dL_dcov3D = torch.zeros((P, 6), **opts)
+    dL_dsh = torch.zeros((P, M, 3), **opts)
+    dL_dscales = torch.zeros((P, 3), **opts)
+    dL_drotations = torch.zeros((P, 4), **opts)
+    if P != 0:
+        if workspace_item is None:
+            raise RuntimeError("backward_ps1 needs the workspace of the matching forward call")
+        g = _prep(grad_out_color, "grad_out_color", device)
+        a = Ps1BwdArgs()
+        a.cam = _camera(rs, device, keep)
+        a.P = P
+        a.M = M
+        a.means3D = means3D.data_ptr()
+        a.scales = _ptr(scales)
+        a.rotations = _ptr(rotations)
+        a.cov3D_precomp = _ptr(cov3D_precomp)
+        a.shs = _ptr(shs)
+        a.colors_precomp = _ptr(colors_precomp)
+        a.radii = radii.contiguous().data_ptr()
+        a.dL_dout_color = g.data_ptr()
+        a.workspace = workspace_item["ws"].data_ptr()
+        a.workspace_bytes = workspace_item["bytes"]
+        a.max_instances = workspace_item["cap"]
+        a.dL_dmeans2D = dL_dmeans2D.data_ptr()
+        a.dL_dconic = dL_dconic.data_ptr()
+        a.dL_dopacity = dL_dopacity.data_ptr()
+        a.dL_dcolors = dL_dcolors.data_ptr()
+        a.dL_dmeans3D = dL_dmeans3D.data_ptr()
+        a.dL_dcov3D = dL_dcov3D.data_ptr()
+        a.dL_dsh = _ptr(dL_dsh)
+        a.dL_dscales = dL_dscales.data_ptr()
+        a.dL_drotations = dL_drotations.data_ptr()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib().fovgs_backward_ps1(C.byref(a), stream), "fovgs_backward_ps1")
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def mark_visible(positions, viewmatrix, projmatrix):
+    device = positions.device
+    P = positions.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=device)
+    if P != 0:
+        pos = _prep(positions, "positions", device)
+        view = _prep(viewmatrix, "viewmatrix", device)
+        proj = _prep(projmatrix, "projmatrix", device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib().fovgs_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(), present.data_ptr(), stream),
+              "fovgs_mark_visible")
+    return present
+
+
+def fov_tile_tables(item, W, H):
+    """Parity helper: (tile_level, tile_min, grad_x, grad_y, blending) of the last FOV frame in `item`."""
+    device = item["ws"].device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    f = lambda: torch.empty((T,), dtype=torch.float32, device=device)
+    lvl, mn, gx, gy = f(), f(), f(), f()
+    bl = torch.empty((T,), dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    check(lib().fovgs_fov_tile_tables(item["ws"].data_ptr(), W, H, lvl.data_ptr(), mn.data_ptr(), gx.data_ptr(),
+                                      gy.data_ptr(), bl.data_ptr(), stream), "fovgs_fov_tile_tables")
+    return lvl, mn, gx, gy, bl
+
+
+def geometry(item, mode, P, W, H):
+    """Parity helper: dense per-Gaussian projection results of the last frame (valid where radii > 0)."""
+    device = item["ws"].device
+    opts = dict(dtype=torch.float32, device=device)
+    means2D = torch.zeros((P, 2), **opts)
+    depths = torch.zeros((P,), **opts)
+    conic = torch.zeros((P, 3), **opts)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if mode == MODE_FOV:
+        lc = torch.zeros((P, 4, 3), **opts)
+        check(lib().fovgs_fov_geometry(item["ws"].data_ptr(), P, W, H, means2D.data_ptr(), depths.data_ptr(),
+                                       conic.data_ptr(), lc.data_ptr(), stream), "fovgs_fov_geometry")
+        return {"means2D": means2D, "depths": depths, "conic": conic, "level_colors": lc}
+    cov3D = torch.zeros((P, 6), **opts)
+    rgb = torch.zeros((P, 3), **opts)
+    check(lib().fovgs_ps1_geometry(item["ws"].data_ptr(), P, W, H, 1 if mode == MODE_SUM else 0, means2D.data_ptr(),
+                                   depths.data_ptr(), conic.data_ptr(), cov3D.data_ptr() if mode == MODE_SUM else None,
+                                   rgb.data_ptr(), stream), "fovgs_ps1_geometry")
+    return {"means2D": means2D, "depths": depths, "conic": conic, "cov3D": cov3D, "rgb": rgb}
