@@ -930,6 +930,18 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
     return ws;
 }
 
+// ---- optional stage timing (bench.py roofline): CUDA events between the stages of a frame ----
+StageProfile g_prof;
+static inline void prof_mark(int i, cudaStream_t st) {
+    if (!g_prof.enabled) return;
+    if (!g_prof.created) {
+        for (int k = 0; k < StageProfile::N; k++) cudaEventCreate(&g_prof.ev[k]);
+        g_prof.created = true;
+    }
+    cudaEventRecord(g_prof.ev[i], st);
+    g_prof.valid = i + 1;
+}
+
 cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, int M, Mode mode, const float* gaze,
                          float alpha, uint32_t cap, cudaStream_t st) {
     SetupArgs a;
@@ -943,6 +955,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
     a.sh_degree = cam.sh_degree; a.M = M; a.P = P; a.tiles = a.gx * a.gy; a.cap = cap;
     const int T = a.tiles;
+    prof_mark(0, st);
     k_setup<<<(T + 255) / 256, 256, 0, st>>>(ws, a);
     if (mode == MODE_FOV) {
         k_tile_levels<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, gaze, a.W, a.H, a.gx, alpha);
@@ -967,16 +980,22 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const int T = gx * gy;
     const int pb = (in.P + 255) / 256;
+    prof_mark(1, st);
     k_preprocess<MODE><<<pb, 256, 0, st>>>(ws, in);
     STAGE_CHECK();
+    prof_mark(2, st);
     k_tile_scan<<<1, 1024, 0, st>>>(ws, T);
     STAGE_CHECK();
+    prof_mark(3, st);
     k_emit<MODE><<<pb, 256, 0, st>>>(ws, in);
     STAGE_CHECK();
+    prof_mark(4, st);
     k_tile_sort<<<T, 256, 0, st>>>(ws, in.out_ranges, in.out_point_list);
     STAGE_CHECK();
+    prof_mark(5, st);
     k_blend<MODE><<<T, 256, 0, st>>>(ws, in);
     STAGE_CHECK();
+    prof_mark(6, st);
     return cudaSuccess;
 }
 

@@ -133,6 +133,8 @@ EXPORTS = (
     "fovgs_fov_tile_tables",
     "fovgs_ps1_geometry",
     "fovgs_fov_geometry",
+    "fovgs_profile_enable",
+    "fovgs_profile_read",
     "fovgs_last_error",
     "fovgs_version",
 )
@@ -163,6 +165,10 @@ def lib():
     L.fovgs_fov_tile_tables.argtypes = [_f, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_ps1_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_fov_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_profile_enable.argtypes = [C.c_int32]
+    L.fovgs_profile_enable.restype = C.c_int
+    L.fovgs_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int32]
+    L.fovgs_profile_read.restype = C.c_int
     for fn in ("fovgs_forward_fov", "fovgs_forward_ps1", "fovgs_backward_ps1", "fovgs_mark_visible",
                "fovgs_read_stats_async", "fovgs_fov_tile_tables", "fovgs_ps1_geometry", "fovgs_fov_geometry"):
         getattr(L, fn).restype = C.c_int

@@ -408,3 +408,17 @@ def geometry(item, mode, P, W, H):
                                    depths.data_ptr(), conic.data_ptr(), cov3D.data_ptr() if mode == MODE_SUM else None,
                                    rgb.data_ptr(), stream), "fovgs_ps1_geometry")
     return {"means2D": means2D, "depths": depths, "conic": conic, "cov3D": cov3D, "rgb": rgb}
+
+
+STAGE_NAMES = ("setup", "preprocess", "tile_scan", "emit_colour", "tile_sort", "blend")
+
+
+def profile_enable(on=True):
+    check(lib().fovgs_profile_enable(1 if on else 0), "fovgs_profile_enable")
+
+
+def profile_read():
+    """Stage durations (ms) of the last profiled forward: dict keyed by STAGE_NAMES."""
+    buf = (C.c_float * 6)()
+    check(lib().fovgs_profile_read(buf, 6), "fovgs_profile_read")
+    return dict(zip(STAGE_NAMES, [float(x) for x in buf]))

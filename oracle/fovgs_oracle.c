@@ -23,9 +23,11 @@
  * (<= 2 ulp apart); rsqrt is 1/sqrtf here and MUFU.RSQ there.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #define BLOCK_X 16
 #define BLOCK_Y 16
@@ -403,11 +405,115 @@ static void fill_lists(const bin_out_t* o, int T, uint32_t* point_list, int64_t 
     }
 }
 
+/* ---- tile-parallel driver (pthreads; dynamic scheduling over tiles).  ORC_THREADS overrides the core count. ---- */
+typedef void (*tile_fn)(void* ctx, int tile);
+typedef struct { tile_fn fn; void* ctx; int T; int next; } tile_job_t;
+static void* tile_worker(void* arg) {
+    tile_job_t* j = (tile_job_t*)arg;
+    for (;;) {
+        const int t = __atomic_fetch_add(&j->next, 4, __ATOMIC_RELAXED);
+        if (t >= j->T) break;
+        for (int k = t; k < t + 4 && k < j->T; k++) j->fn(j->ctx, k);
+    }
+    return NULL;
+}
+int orc_num_threads(void) {
+    const char* e = getenv("ORC_THREADS");
+    long n = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+    if (n < 1) n = 1;
+    if (n > 256) n = 256;
+    return (int)n;
+}
+static void run_tiles(tile_fn fn, void* ctx, int T) {
+    tile_job_t job = {fn, ctx, T, 0};
+    const int nt = orc_num_threads();
+    if (nt <= 1) { tile_worker(&job); return; }
+    pthread_t th[256];
+    int started = 0;
+    for (int i = 0; i < nt - 1; i++) if (pthread_create(&th[started], NULL, tile_worker, &job) == 0) started++;
+    tile_worker(&job);
+    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+}
+static inline void atomic_add_f32(float* p, float v) {
+    uint32_t old = __atomic_load_n((uint32_t*)p, __ATOMIC_RELAXED), neu;
+    do { float f; memcpy(&f, &old, 4); f += v; memcpy(&neu, &f, 4); }
+    while (!__atomic_compare_exchange_n((uint32_t*)p, &old, neu, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+
 static inline float gauss_power(float conx, float cony, float conz, float dx, float dy) {
     const float a = dy * (dy * conz);
     const float s = fmaf(dx, dx * conx, a);
     const float c = dy * (dx * cony);
     return fmaf(s, -0.5f, -c);
+}
+
+typedef struct {
+    const orc_camera* cam; int mode, W, H, gx; const uint32_t* rng; const inst_t* inst; const splat_t* sp;
+    const float* opacity; const float* rgb; int* gaussians_count; float* contributions; float* final_T; uint32_t* n_contrib;
+    float* out_color;
+} ps1_blend_ctx;
+static void blend_tile_ps1(void* vctx, int tile) {
+    const ps1_blend_ctx* c = (const ps1_blend_ctx*)vctx;
+    const orc_camera* cam = c->cam; const int mode = c->mode, W = c->W, H = c->H, gx = c->gx;
+    const uint32_t* rng = c->rng; const float* opacity = c->opacity; const float* rgb = c->rgb;
+    int* gaussians_count = c->gaussians_count; float* contributions = c->contributions;
+    float* final_T = c->final_T; uint32_t* n_contrib = c->n_contrib; float* out_color = c->out_color;
+    struct { const inst_t* inst; const splat_t* sp; } o = {c->inst, c->sp};
+
+        const int tx = tile % gx, ty = tile / gx;
+        const uint32_t r0 = rng[2 * tile], r1 = rng[2 * tile + 1];
+        const int total = (int)(r1 - r0);
+        float Tt[256], C[256][3]; uint8_t done[256]; uint32_t contributor[256], last[256];
+        int ndone = 0;
+        for (int t = 0; t < 256; t++) {
+            const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
+            Tt[t] = 1.0f; C[t][0] = C[t][1] = C[t][2] = 0; contributor[t] = last[t] = 0;
+            done[t] = !(px < W && py < H); ndone += done[t];
+        }
+        const int rounds = (total + 255) / 256;
+        int toDo = total;
+        for (int b = 0; b < rounds; b++, toDo -= 256) {
+            if (ndone == 256) break;
+            const int lim = toDo < 256 ? toDo : 256;
+            if (mode == 1)
+                for (int j = 0; j < lim; j++) {
+                    const uint32_t id = o.inst[r0 + (size_t)b * 256 + j].id;
+                    __atomic_fetch_add(&gaussians_count[id], 1, __ATOMIC_RELAXED);
+                }
+            for (int t = 0; t < 256; t++) {
+                if (done[t]) continue;
+                const float pxf = (float)(tx * 16 + (t & 15)), pyf = (float)(ty * 16 + (t >> 4));
+                for (int j = 0; j < lim && !done[t]; j++) {
+                    const uint32_t id = o.inst[r0 + (size_t)b * 256 + j].id;
+                    const splat_t* s = &o.sp[id];
+                    contributor[t]++;
+                    const float dx = s->px - pxf, dy = s->py - pyf;
+                    const float power = gauss_power(s->conx, s->cony, s->conz, dx, dy);
+                    if (power > 0.0f || power < -4.5f) continue;
+                    const float alpha = fminf(0.99f, opacity[id] * expf(power));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = Tt[t] * (1 - alpha);
+                    if (test_T < 0.0001f) { done[t] = 1; ndone++; continue; }
+                    if (mode == 1) {
+                        atomic_add_f32(&contributions[id], alpha * Tt[t]);
+                        for (int ch = 0; ch < 3; ch++) C[t][ch] = fmaf(Tt[t], alpha * rgb[3 * id + ch], C[t][ch]);
+                    } else {
+                        const float w = alpha * Tt[t];
+                        for (int ch = 0; ch < 3; ch++) C[t][ch] = fmaf(rgb[3 * id + ch], w, C[t][ch]);
+                    }
+                    Tt[t] = test_T;
+                    last[t] = contributor[t];
+                }
+            }
+        }
+        for (int t = 0; t < 256; t++) {
+            const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
+            if (!(px < W && py < H)) continue;
+            const size_t pid = (size_t)W * py + px;
+            if (final_T) final_T[pid] = Tt[t];
+            if (n_contrib) n_contrib[pid] = last[t];
+            for (int ch = 0; ch < 3; ch++) out_color[(size_t)ch * H * W + pid] = fmaf(cam->bg[ch], Tt[t], C[t][ch]);
+        }
 }
 
 /* =================================================================================================================
@@ -451,119 +557,28 @@ int64_t orc_forward_ps1(const orc_camera* cam, int mode, int P, int M, const flo
     if (cov3D) memcpy(cov3D, o.cov3d, sizeof(float) * 6 * (size_t)P);
     if (rgb_out) memcpy(rgb_out, rgb, sizeof(float) * 3 * (size_t)P);
     if (clamped_out) memcpy(clamped_out, clamped, (size_t)3 * P);
-    /* blend: one 16x16 tile per iteration, 256-entry batches with the block-wide "all done" vote
+    /* blend: one 16x16 tile per work item, 256-entry batches with the block-wide "all done" vote
        (OBB/forward.cu:251-384, SUM/forward.cu:298-430) */
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int tile = 0; tile < T; tile++) {
-        const int tx = tile % gx, ty = tile / gx;
-        const uint32_t r0 = rng[2 * tile], r1 = rng[2 * tile + 1];
-        const int total = (int)(r1 - r0);
-        float Tt[256], C[256][3]; uint8_t done[256]; uint32_t contributor[256], last[256];
-        int ndone = 0;
-        for (int t = 0; t < 256; t++) {
-            const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
-            Tt[t] = 1.0f; C[t][0] = C[t][1] = C[t][2] = 0; contributor[t] = last[t] = 0;
-            done[t] = !(px < W && py < H); ndone += done[t];
-        }
-        const int rounds = (total + 255) / 256;
-        int toDo = total;
-        for (int b = 0; b < rounds; b++, toDo -= 256) {
-            if (ndone == 256) break;
-            const int lim = toDo < 256 ? toDo : 256;
-            if (mode == 1)
-                for (int j = 0; j < lim; j++) {
-                    const uint32_t id = o.inst[r0 + (size_t)b * 256 + j].id;
-#pragma omp atomic
-                    gaussians_count[id] += 1;
-                }
-            for (int t = 0; t < 256; t++) {
-                if (done[t]) continue;
-                const float pxf = (float)(tx * 16 + (t & 15)), pyf = (float)(ty * 16 + (t >> 4));
-                for (int j = 0; j < lim && !done[t]; j++) {
-                    const uint32_t id = o.inst[r0 + (size_t)b * 256 + j].id;
-                    const splat_t* s = &o.sp[id];
-                    contributor[t]++;
-                    const float dx = s->px - pxf, dy = s->py - pyf;
-                    const float power = gauss_power(s->conx, s->cony, s->conz, dx, dy);
-                    if (power > 0.0f || power < -4.5f) continue;
-                    const float alpha = fminf(0.99f, opacity[id] * expf(power));
-                    if (alpha < 1.0f / 255.0f) continue;
-                    const float test_T = Tt[t] * (1 - alpha);
-                    if (test_T < 0.0001f) { done[t] = 1; ndone++; continue; }
-                    if (mode == 1) {
-#pragma omp atomic
-                        contributions[id] += alpha * Tt[t];
-                        for (int ch = 0; ch < 3; ch++) C[t][ch] = fmaf(Tt[t], alpha * rgb[3 * id + ch], C[t][ch]);
-                    } else {
-                        const float w = alpha * Tt[t];
-                        for (int ch = 0; ch < 3; ch++) C[t][ch] = fmaf(rgb[3 * id + ch], w, C[t][ch]);
-                    }
-                    Tt[t] = test_T;
-                    last[t] = contributor[t];
-                }
-            }
-        }
-        for (int t = 0; t < 256; t++) {
-            const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
-            if (!(px < W && py < H)) continue;
-            const size_t pid = (size_t)W * py + px;
-            if (final_T) final_T[pid] = Tt[t];
-            if (n_contrib) n_contrib[pid] = last[t];
-            for (int ch = 0; ch < 3; ch++) out_color[(size_t)ch * H * W + pid] = fmaf(cam->bg[ch], Tt[t], C[t][ch]);
-        }
+    {
+        ps1_blend_ctx bc = {cam, mode, W, H, gx, rng, o.inst, o.sp, opacity, rgb, gaussians_count, contributions, final_T, n_contrib, out_color};
+        run_tiles(blend_tile_ps1, &bc, T);
     }
     free(o.sp); free(o.vis); free(o.cov3d); free(o.inst); free(rgb); free(clamped); free(rng);
     return n;
 }
 
-/* =================================================================================================================
- * Foveated forward (diff_gaussian_rasterization_fov_pcheck_obb).
- * ================================================================================================================= */
-int64_t orc_forward_fov(const orc_camera* cam, int P, int M_rest, const float* means3D, const float* opacities4,
-                        const float* scales, const float* rot, const float* shs_rest, const float* shs_dcs,
-                        const float* highest_levels, const float* gaze, float alpha_pool, float* out_color, int* radii,
-                        float* means2D, float* depths, float* conic, uint32_t* point_list, int64_t list_cap,
-                        uint32_t* ranges, float* tile_level_out, float* tile_min_out, uint8_t* tile_blend_out,
-                        int32_t* level_ranges_out) {
-    const int W = cam->W, H = cam->H, gx = (W + 15) / 16, gy = (H + 15) / 16, T = gx * gy;
-    const float fy = H / (2.0f * cam->tanfovy), fx = W / (2.0f * cam->tanfovx);
-    float* tl = (float*)malloc(sizeof(float) * T); float* tm = (float*)malloc(sizeof(float) * T);
-    float* tgx = (float*)malloc(sizeof(float) * T); float* tgy = (float*)malloc(sizeof(float) * T);
-    uint8_t* tb = (uint8_t*)malloc(T);
-    orc_tile_tables(W, H, gaze, alpha_pool, tl, tm, tgx, tgy, tb);
-    if (tile_level_out) memcpy(tile_level_out, tl, sizeof(float) * T);
-    if (tile_min_out) memcpy(tile_min_out, tm, sizeof(float) * T);
-    if (tile_blend_out) memcpy(tile_blend_out, tb, T);
-    bin_in_t in; memset(&in, 0, sizeof(in));
-    in.mode = 2; in.cam = cam; in.P = P; in.M = M_rest; in.means3D = means3D; in.scales = scales; in.rot = rot;
-    in.highest_levels = highest_levels; in.tile_min = tm; in.tile_blend = tb;   /* Q2: filter receives tile_level_min */
-    bin_out_t o; memset(&o, 0, sizeof(o));
-    o.sp = (splat_t*)calloc((size_t)P + 1, sizeof(splat_t)); o.vis = (uint8_t*)calloc((size_t)P + 1, 1);
-    o.radii = radii; o.cov3d = (float*)calloc((size_t)P * 6 + 6, sizeof(float));
-    o.lvl_lo = (int32_t*)calloc((size_t)P + 1, 4); o.lvl_hi = (int32_t*)calloc((size_t)P + 1, 4);
-    const int64_t n = run_binning(&in, &o, fx, fy, gx, gy);
-    uint32_t* rng = (uint32_t*)calloc((size_t)T * 2, sizeof(uint32_t));
-    fill_lists(&o, T, point_list, list_cap, rng);
-    if (ranges) memcpy(ranges, rng, sizeof(uint32_t) * 2 * (size_t)T);
-    /* compute_fov_colors (rasterizer_impl.cu:490-530): only levels in level_ranges are defined */
-    float* fc = (float*)calloc((size_t)P * 12 + 12, sizeof(float));
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < P; i++) {
-        if (radii[i] <= 0) continue;
-        float d[3]; view_dir(cam, means3D + 3 * i, d);
-        float res[3] = {0, 0, 0};
-        if (M_rest > 0) sh_accumulate(shs_rest + (size_t)3 * M_rest * i, 0, cam->sh_degree, d[0], d[1], d[2], res);
-        for (int ch = 0; ch < 3; ch++) res[ch] += 0.5f;
-        for (int l = o.lvl_lo[i]; l <= o.lvl_hi[i]; l++)
-            for (int ch = 0; ch < 3; ch++)
-                fc[(size_t)i * 12 + l * 3 + ch] = fmaxf(SH_C0 * shs_dcs[(size_t)i * 12 + l * 3 + ch] + res[ch], 0.0f);
-        if (means2D) { means2D[2 * i] = o.sp[i].px; means2D[2 * i + 1] = o.sp[i].py; }
-        if (depths) depths[i] = o.sp[i].depth;
-        if (conic) { conic[3 * i] = o.sp[i].conx; conic[3 * i + 1] = o.sp[i].cony; conic[3 * i + 2] = o.sp[i].conz; }
-        if (level_ranges_out) { level_ranges_out[2 * i] = o.lvl_lo[i]; level_ranges_out[2 * i + 1] = o.lvl_hi[i]; }
-    }
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int tile = 0; tile < T; tile++) {
+typedef struct {
+    const orc_camera* cam; int W, H, gx; const uint32_t* rng; const inst_t* inst; const splat_t* sp;
+    const float* tm; const float* tgx; const float* tgy; const uint8_t* tb; const float* opacities4; const float* fc;
+    const float* highest_levels; float* out_color;
+} fov_blend_ctx;
+static void blend_tile_fov(void* vctx, int tile) {
+    const fov_blend_ctx* c = (const fov_blend_ctx*)vctx;
+    const orc_camera* cam = c->cam; const int W = c->W, H = c->H, gx = c->gx;
+    const uint32_t* rng = c->rng; const float* tm = c->tm; const float* tgx = c->tgx; const float* tgy = c->tgy; const uint8_t* tb = c->tb;
+    const float* opacities4 = c->opacities4; const float* fc = c->fc; const float* highest_levels = c->highest_levels; float* out_color = c->out_color;
+    struct { const inst_t* inst; const splat_t* sp; } o = {c->inst, c->sp};
+
         const int tx = tile % gx, ty = tile / gx;
         const uint32_t r0 = rng[2 * tile], r1 = rng[2 * tile + 1];
         const int total = (int)(r1 - r0), rounds = (total + 255) / 256;
@@ -651,6 +666,57 @@ int64_t orc_forward_fov(const orc_camera* cam, int P, int M_rest, const float* m
                 }
             }
         }
+}
+
+/* =================================================================================================================
+ * Foveated forward (diff_gaussian_rasterization_fov_pcheck_obb).
+ * ================================================================================================================= */
+int64_t orc_forward_fov(const orc_camera* cam, int P, int M_rest, const float* means3D, const float* opacities4,
+                        const float* scales, const float* rot, const float* shs_rest, const float* shs_dcs,
+                        const float* highest_levels, const float* gaze, float alpha_pool, float* out_color, int* radii,
+                        float* means2D, float* depths, float* conic, uint32_t* point_list, int64_t list_cap,
+                        uint32_t* ranges, float* tile_level_out, float* tile_min_out, uint8_t* tile_blend_out,
+                        int32_t* level_ranges_out) {
+    const int W = cam->W, H = cam->H, gx = (W + 15) / 16, gy = (H + 15) / 16, T = gx * gy;
+    const float fy = H / (2.0f * cam->tanfovy), fx = W / (2.0f * cam->tanfovx);
+    float* tl = (float*)malloc(sizeof(float) * T); float* tm = (float*)malloc(sizeof(float) * T);
+    float* tgx = (float*)malloc(sizeof(float) * T); float* tgy = (float*)malloc(sizeof(float) * T);
+    uint8_t* tb = (uint8_t*)malloc(T);
+    orc_tile_tables(W, H, gaze, alpha_pool, tl, tm, tgx, tgy, tb);
+    if (tile_level_out) memcpy(tile_level_out, tl, sizeof(float) * T);
+    if (tile_min_out) memcpy(tile_min_out, tm, sizeof(float) * T);
+    if (tile_blend_out) memcpy(tile_blend_out, tb, T);
+    bin_in_t in; memset(&in, 0, sizeof(in));
+    in.mode = 2; in.cam = cam; in.P = P; in.M = M_rest; in.means3D = means3D; in.scales = scales; in.rot = rot;
+    in.highest_levels = highest_levels; in.tile_min = tm; in.tile_blend = tb;   /* Q2: filter receives tile_level_min */
+    bin_out_t o; memset(&o, 0, sizeof(o));
+    o.sp = (splat_t*)calloc((size_t)P + 1, sizeof(splat_t)); o.vis = (uint8_t*)calloc((size_t)P + 1, 1);
+    o.radii = radii; o.cov3d = (float*)calloc((size_t)P * 6 + 6, sizeof(float));
+    o.lvl_lo = (int32_t*)calloc((size_t)P + 1, 4); o.lvl_hi = (int32_t*)calloc((size_t)P + 1, 4);
+    const int64_t n = run_binning(&in, &o, fx, fy, gx, gy);
+    uint32_t* rng = (uint32_t*)calloc((size_t)T * 2, sizeof(uint32_t));
+    fill_lists(&o, T, point_list, list_cap, rng);
+    if (ranges) memcpy(ranges, rng, sizeof(uint32_t) * 2 * (size_t)T);
+    /* compute_fov_colors (rasterizer_impl.cu:490-530): only levels in level_ranges are defined */
+    float* fc = (float*)calloc((size_t)P * 12 + 12, sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; i++) {
+        if (radii[i] <= 0) continue;
+        float d[3]; view_dir(cam, means3D + 3 * i, d);
+        float res[3] = {0, 0, 0};
+        if (M_rest > 0) sh_accumulate(shs_rest + (size_t)3 * M_rest * i, 0, cam->sh_degree, d[0], d[1], d[2], res);
+        for (int ch = 0; ch < 3; ch++) res[ch] += 0.5f;
+        for (int l = o.lvl_lo[i]; l <= o.lvl_hi[i]; l++)
+            for (int ch = 0; ch < 3; ch++)
+                fc[(size_t)i * 12 + l * 3 + ch] = fmaxf(SH_C0 * shs_dcs[(size_t)i * 12 + l * 3 + ch] + res[ch], 0.0f);
+        if (means2D) { means2D[2 * i] = o.sp[i].px; means2D[2 * i + 1] = o.sp[i].py; }
+        if (depths) depths[i] = o.sp[i].depth;
+        if (conic) { conic[3 * i] = o.sp[i].conx; conic[3 * i + 1] = o.sp[i].cony; conic[3 * i + 2] = o.sp[i].conz; }
+        if (level_ranges_out) { level_ranges_out[2 * i] = o.lvl_lo[i]; level_ranges_out[2 * i + 1] = o.lvl_hi[i]; }
+    }
+    {
+        fov_blend_ctx bc = {cam, W, H, gx, rng, o.inst, o.sp, tm, tgx, tgy, tb, opacities4, fc, highest_levels, out_color};
+        run_tiles(blend_tile_fov, &bc, T);
     }
     free(tl); free(tm); free(tgx); free(tgy); free(tb); free(o.sp); free(o.vis); free(o.cov3d); free(o.lvl_lo); free(o.lvl_hi);
     free(o.inst); free(rng); free(fc);

@@ -1,0 +1,70 @@
+"""The C-ABI shared library loads and exports every symbol include/fovgs.h declares (no compute calls: no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "fovgs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fovgs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _header_symbols()
+    for s in ("fovgs_forward_fov", "fovgs_forward_ps1", "fovgs_backward_ps1", "fovgs_mark_visible", "fovgs_workspace_bytes",
+              "fovgs_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from fovgs import _lib
+    L = _lib.lib()
+    for s in _header_symbols():
+        assert hasattr(L, s), f"libfovgs.so does not export {s}"
+    assert sorted(_lib.EXPORTS) == _header_symbols()
+    assert L.fovgs_version() == 100
+
+
+def test_workspace_bytes_is_monotone_and_mode_dependent():
+    from fovgs import _lib
+    L = _lib.lib()
+    a = L.fovgs_workspace_bytes(10000, 256, 256, 1 << 20, 0, 0)
+    b = L.fovgs_workspace_bytes(10000, 256, 256, 1 << 21, 0, 0)
+    c = L.fovgs_workspace_bytes(20000, 256, 256, 1 << 20, 0, 0)
+    f = L.fovgs_workspace_bytes(10000, 256, 256, 1 << 20, 1, 0)
+    s = L.fovgs_workspace_bytes(10000, 256, 256, 1 << 20, 0, 1)
+    assert 0 < a < b and a < c and f > a and s > a
+    assert L.fovgs_workspace_bytes(-1, 256, 256, 10, 0, 0) == 0
+    assert L.fovgs_workspace_bytes(10, 0, 256, 10, 0, 0) == 0
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    """Null / malformed arguments are rejected before any CUDA call, with a message (reference: AT_ERROR)."""
+    from fovgs import _lib
+    L = _lib.lib()
+    assert L.fovgs_forward_fov(None, None) == -1
+    assert b"null args" in L.fovgs_last_error()
+    a = _lib.FovFwdArgs()
+    a.cam.image_width = 0
+    a.cam.image_height = 16
+    assert L.fovgs_forward_fov(ctypes.byref(a), None) == -1
+    assert b"image size" in L.fovgs_last_error()
+    p = _lib.Ps1FwdArgs()
+    p.cam.image_width = 16
+    p.cam.image_height = 16
+    assert L.fovgs_forward_ps1(ctypes.byref(p), None) == -1  # camera pointers null
+    assert L.fovgs_mark_visible(5, None, None, None, None, None) == -1
+    assert L.fovgs_mark_visible(0, None, None, None, None, None) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from fovgs import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfovgs.so")
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback|not found"):
+        _lib.lib()
