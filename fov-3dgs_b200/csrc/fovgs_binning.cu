@@ -1,0 +1,453 @@
+// fovgs_binning.cu — per-Gaussian stage of the forward path, written for load balance.
+//
+//   k_pre      project every Gaussian (pinned arithmetic, fovgs_math.cuh), then test its candidate tiles with a
+//              BLOCK-LEVEL LOAD-BALANCED EXPANSION: the 256 Gaussians of a batch publish their tile rectangles in
+//              shared memory, an exclusive scan turns rectangle sizes into a candidate index space, and all 256
+//              threads walk that space together (thread -> candidate -> owner via binary search).  A splat that
+//              covers 2000 tiles costs 8 block rounds instead of stalling one warp for 2000 serial iterations —
+//              the reference's `filter`/`OBB_test` and `duplicateWithKeys` (FOV/cuda_rasterizer/
+//              rasterizer_impl.cu:264-383, 423-486) are thread-per-Gaussian loops and account for ~58 % of its frame
+//              at 6 M Gaussians (profiles/r1_launches_fov_6M_reference.csv).
+//              Surviving (tile, depth|id) instances are staged densely (block-granular allocation, one global
+//              atomic per 4096 slots) and counted per tile; colours of visible Gaussians are evaluated in the same
+//              kernel.  Replaces preprocessCUDA + InclusiveSum x2 + filter + duplicateWithKeys + compute_fov_colors.
+//   k_tile_scan  one-block exclusive scan of the tile histogram (= the reference's `ranges`, no identifyTileRanges).
+//   k_scatter  staged instances -> tile-binned key array (trivially balanced: one thread per instance).
+#include "fovgs_internal.cuh"
+
+namespace fovgs {
+
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                       0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                       -0.5900435899266435f};
+
+// SH colour (OBB/rasterizer_impl.cu:32-82, SUM/forward.cu:20-71, FOV/rasterizer_impl.cu:37-84).
+// `first` = index of the first degree-1 triplet (1 for [P,16,3] tensors, 0 for the FOV "rest" tensor).
+__device__ __forceinline__ float3 sh_accumulate(const float* __restrict__ sh, int first, int deg, float x, float y, float z,
+                                                float3 init) {
+    float3 r = init;
+    auto C = [&](int k, int ch) { return sh[3 * (first + k) + ch]; };
+    if (deg > 0) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            float v = (&r.x)[ch];
+            v = v - SH_C1 * y * C(0, ch) + SH_C1 * z * C(1, ch) - SH_C1 * x * C(2, ch);
+            (&r.x)[ch] = v;
+        }
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z;
+            const float xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                float v = (&r.x)[ch];
+                v = v + SH_C2[0] * xy * C(3, ch) + SH_C2[1] * yz * C(4, ch) + SH_C2[2] * (2.0f * zz - xx - yy) * C(5, ch) +
+                    SH_C2[3] * xz * C(6, ch) + SH_C2[4] * (xx - yy) * C(7, ch);
+                (&r.x)[ch] = v;
+            }
+            if (deg > 2) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    float v = (&r.x)[ch];
+                    v = v + SH_C3[0] * y * (3.0f * xx - yy) * C(8, ch) + SH_C3[1] * xy * z * C(9, ch) +
+                        SH_C3[2] * y * (4.0f * zz - xx - yy) * C(10, ch) +
+                        SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * C(11, ch) +
+                        SH_C3[4] * x * (4.0f * zz - xx - yy) * C(12, ch) + SH_C3[5] * z * (xx - yy) * C(13, ch) +
+                        SH_C3[6] * x * (xx - 3.0f * yy) * C(14, ch);
+                    (&r.x)[ch] = v;
+                }
+            }
+        }
+    }
+    return r;
+}
+
+// precomputed-covariance variant of project_splat (FOV/forward.cu:155-158)
+__device__ __forceinline__ bool project_splat_cov(const CamParams& cam, float mx, float my, float mz, const float* c3, Splat& s) {
+    const float tz = xform_row(cam.view, 2, mx, my, mz);
+    if (tz <= 0.2f) return false;
+    const float hx = xform_row(cam.proj, 0, mx, my, mz);
+    const float hy = xform_row(cam.proj, 1, mx, my, mz);
+    const float hw = xform_row(cam.proj, 3, mx, my, mz);
+    const float pw = __frcp_rn(FA(hw, 0.0000001f));
+    const float tx = xform_row(cam.view, 0, mx, my, mz);
+    const float ty = xform_row(cam.view, 1, mx, my, mz);
+    cov2d_from_cov3d(cam, tx, ty, tz, c3, s.cxx, s.cxy, s.cyy);
+    const float bb = FM(s.cxy, s.cxy);
+    const float det = FF(s.cxx, s.cyy, -bb);
+    if (det == 0.0f) return false;
+    const float det_inv = __frcp_rn(det);
+    s.conx = FM(s.cyy, det_inv);
+    s.cony = FM(s.cxy, -det_inv);
+    s.conz = FM(s.cxx, det_inv);
+    const float mid = FM(FA(s.cxx, s.cyy), 0.5f);
+    const float sq = __fsqrt_rn(fmaxf(FF(mid, mid, -det), 0.1f));
+    const float l1 = FA(mid, sq), l2 = FS(mid, sq);
+    s.radius = __float2int_ru(FM(__fsqrt_rn(fmaxf(l1, l2)), 3.0f));
+    s.px = ndc2pix(FM(hx, pw), cam.W);
+    s.py = ndc2pix(FM(hy, pw), cam.H);
+    get_rect(s.px, s.py, s.radius, cam.grid_x, cam.grid_y, s.x0, s.y0, s.x1, s.y1);
+    const unsigned tnum = (unsigned)(s.y1 - s.y0) * (unsigned)(s.x1 - s.x0);
+    if (tnum == 0) return false;
+    s.depth = tz;
+    s.e1x = s.e1y = s.e2x = s.e2y = s.len1 = s.len2 = 0.0f;
+    if (tnum > 1) {
+        const float a1 = FS(s.cxx, l1), a2 = FS(s.cxx, l2);
+        const float q1 = rsqrtf(FF(a1, a1, bb)), q2 = rsqrtf(FF(a2, a2, bb));
+        s.e1x = FM(s.cxy, -q1); s.e1y = FM(a1, q1);
+        s.e2x = FM(s.cxy, -q2); s.e2y = FM(a2, q2);
+        s.len1 = FM(__fsqrt_rn(l1), 3.0f);
+        s.len2 = FM(__fsqrt_rn(l2), 3.0f);
+    }
+    return true;
+}
+
+constexpr int PB = 256;  // Gaussians per batch == threads per block
+
+struct PreSmem {
+    CamParams cam;
+    float px[PB], py[PB], e1x[PB], e1y[PB], e2x[PB], e2y[PB], l1[PB], l2[PB], hl1[PB];
+    uint32_t dbits[PB];
+    int x0[PB], y0[PB], w[PB];
+    uint32_t pref[PB + 1];
+    uint32_t cnt[PB];
+    int lo[PB], hi[PB];          // FOV: float bits of the (non-negative) lowest / highest level used
+    uint32_t bl[PB];             // FOV: any kept tile is a blending tile
+    uint32_t wtot[8];
+    uint32_t round_base;
+    uint32_t chunk_base, chunk_used, has_chunk;
+    uint32_t inval_beg, inval_end;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
+    __shared__ PreSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const int n = (int)(sizeof(CamParams) / 4);
+        const uint32_t* src = (const uint32_t*)&ws.hdr->cam;
+        uint32_t* dst = (uint32_t*)&sm.cam;
+        for (int i = tid; i < n; i += PB) dst[i] = src[i];
+        if (tid == 0) { sm.chunk_base = 0; sm.chunk_used = STAGE_CHUNK; sm.has_chunk = 0; }
+    }
+    __syncthreads();
+    const CamParams& cam = sm.cam;
+    const int gx = cam.grid_x;
+    const uint32_t stage_cap = ws.stage_cap;
+    unsigned visible_total = 0;
+
+    for (int base = blockIdx.x * PB; base < in.P; base += gridDim.x * PB) {
+        const int idx = base + tid;
+        // ---------------- phase A: projection (thread = Gaussian) ----------------
+        Splat s;
+        float c3[6];
+        bool ok = false;
+        float hl = 0.0f;
+        if (idx < in.P) {
+            const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
+            if (in.cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = in.cov3D_precomp[6 * (size_t)idx + k];
+                ok = project_splat_cov(cam, mx, my, mz, c3, s);
+            } else {
+                const float sx = in.scales[3 * (size_t)idx], sy = in.scales[3 * (size_t)idx + 1], sz = in.scales[3 * (size_t)idx + 2];
+                const float4 q = *reinterpret_cast<const float4*>(in.rotations + 4 * (size_t)idx);
+                ok = project_splat(cam, mx, my, mz, sx, sy, sz, q.x, q.y, q.z, q.w, s, c3);
+            }
+        }
+        uint32_t tnum = 0;
+        if (ok) {
+            tnum = (uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0);
+            sm.px[tid] = s.px; sm.py[tid] = s.py;
+            sm.e1x[tid] = s.e1x; sm.e1y[tid] = s.e1y; sm.e2x[tid] = s.e2x; sm.e2y[tid] = s.e2y;
+            sm.l1[tid] = s.len1; sm.l2[tid] = s.len2;
+            sm.dbits[tid] = __float_as_uint(s.depth);
+            sm.x0[tid] = s.x0; sm.y0[tid] = s.y0; sm.w[tid] = s.x1 - s.x0;
+            if (MODE == MODE_FOV) {
+                hl = in.highest_levels[idx];
+                sm.hl1[tid] = FA(hl, 1.0f);
+                sm.lo[tid] = __float_as_int(fmaxf(hl, 0.0f));
+                sm.hi[tid] = 0;
+                sm.bl[tid] = 0;
+            }
+        }
+        sm.cnt[tid] = 0;
+        // exclusive scan of tnum over the block
+        {
+            uint32_t x = tnum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) sm.wtot[warp] = x;
+            __syncthreads();
+            uint32_t wbase = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) if (w < warp) wbase += sm.wtot[w];
+            sm.pref[tid] = wbase + x - tnum;
+            if (tid == PB - 1) sm.pref[PB] = wbase + x;
+        }
+        __syncthreads();
+        const uint32_t total = sm.pref[PB];
+
+        // ---------------- phase B: candidate tiles (thread = candidate) ----------------
+        for (uint32_t r = 0; r < total; r += PB) {
+            const uint32_t c = r + tid;
+            const bool valid = c < total;
+            bool pass = false, single = false;
+            uint32_t tile = 0, owner = 0xffffu;
+            float level = 0.0f;
+            bool tblend = false;
+            if (valid) {
+                int lo_i = 0, hi_i = PB;
+                while (hi_i - lo_i > 1) {
+                    const int mid = (lo_i + hi_i) >> 1;
+                    if (sm.pref[mid] <= c) lo_i = mid; else hi_i = mid;
+                }
+                owner = (uint32_t)lo_i;
+                const uint32_t t = c - sm.pref[owner];
+                const int w = sm.w[owner];
+                const int ty = sm.y0[owner] + (int)(t / (uint32_t)w);
+                const int tx = sm.x0[owner] + (int)(t % (uint32_t)w);
+                tile = (uint32_t)ty * gx + tx;
+                single = (sm.pref[owner + 1] - sm.pref[owner]) == 1u;
+                pass = true;
+                if (MODE == MODE_FOV) {
+                    level = ws.tile_min[tile];
+                    pass = level < sm.hl1[owner];
+                }
+                if (pass && !single) {
+                    const float cx = sm.px[owner], cy = sm.py[owner];
+                    const float e1x = sm.e1x[owner], e1y = sm.e1y[owner], e2x = sm.e2x[owner], e2y = sm.e2y[owner];
+                    const float l1 = sm.l1[owner], l2 = sm.l2[owner];
+                    ObbCorners oc;
+                    obb_corners(cx, cy, e1x, e1y, e2x, e2y, l1, l2, oc);
+                    const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
+                    pass = obb_hits_tile(oc, cx, cy, e1x, e1y, e2x, e2y, l1, l2, tcx, tcy);
+                }
+                if (pass) {
+                    atomicAdd(&ws.tile_count[tile], 1u);
+                    if (MODE == MODE_FOV) tblend = ws.tile_blend[tile] != 0;
+                }
+            }
+            // per-owner bookkeeping, aggregated over the lanes that share an owner
+            const unsigned seg = __match_any_sync(0xffffffffu, owner);
+            const unsigned passmask = __ballot_sync(0xffffffffu, pass);
+            const bool head = valid && ((seg & ((1u << lane) - 1u)) == 0u);
+            const unsigned npass_seg = __popc(passmask & seg);
+            if (MODE == MODE_FOV) {
+                const unsigned blendmask = __ballot_sync(0xffffffffu, pass && tblend);
+                const int lb = pass ? __float_as_int(fmaxf(level, 0.0f)) : 0x7f800000;
+                const int hb = pass ? __float_as_int(fmaxf(level, 0.0f)) : 0;
+                const int lo_seg = __reduce_min_sync(seg, lb);
+                const int hi_seg = __reduce_max_sync(seg, hb);
+                if (head && npass_seg) {
+                    if (single) {   // reference assigns (not min/max) on the single-tile path: rasterizer_impl.cu:309-312
+                        sm.lo[owner] = lo_seg;
+                        sm.hi[owner] = hi_seg;
+                    } else {
+                        atomicMin(&sm.lo[owner], lo_seg);
+                        atomicMax(&sm.hi[owner], hi_seg);
+                    }
+                    if (blendmask & seg) atomicOr(&sm.bl[owner], 1u);
+                }
+            }
+            if (head && npass_seg) atomicAdd(&sm.cnt[owner], npass_seg);
+            // stage the surviving instances densely
+            const unsigned wrank = __popc(passmask & ((1u << lane) - 1u));
+            if (lane == 0) sm.wtot[warp] = __popc(passmask);
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t np = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) { const uint32_t t = sm.wtot[w]; sm.wtot[w] = np; np += t; }
+                sm.inval_beg = sm.inval_end = 0;
+                if (np) {
+                    if (sm.chunk_used + np > STAGE_CHUNK) {
+                        if (sm.has_chunk) { sm.inval_beg = sm.chunk_base + sm.chunk_used; sm.inval_end = sm.chunk_base + STAGE_CHUNK; }
+                        sm.chunk_base = atomicAdd(&ws.hdr->stage_cursor, STAGE_CHUNK);
+                        sm.chunk_used = 0;
+                        sm.has_chunk = 1;
+                    }
+                    sm.round_base = sm.chunk_base + sm.chunk_used;
+                    sm.chunk_used += np;
+                }
+            }
+            __syncthreads();
+            {
+                const uint32_t ib = sm.inval_beg, ie = sm.inval_end;
+                for (uint32_t p = ib + tid; p < ie; p += PB)
+                    if (p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
+            }
+            if (pass) {
+                const uint32_t pos = sm.round_base + sm.wtot[warp] + wrank;
+                if (pos < stage_cap) {
+                    ws.stage_tile[pos] = tile;
+                    ws.stage_key[pos] = ((uint64_t)sm.dbits[owner] << 32) | (uint32_t)(base + (int)owner);
+                }
+            }
+            __syncthreads();   // wtot / round_base are rewritten next round
+        }
+        __syncthreads();
+
+        // ---------------- phase C: per-Gaussian outputs + colour (thread = Gaussian) ----------------
+        bool visible = false;
+        if (idx < in.P) {
+            const uint32_t count = ok ? sm.cnt[tid] : 0u;
+            in.radii[idx] = count ? s.radius : 0;
+            if (count) {
+                visible = true;
+                const int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
+                float4* rec = ws.rec + (size_t)R * idx;
+                rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
+                const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
+                float dx = mx - cam.campos[0], dy = my - cam.campos[1], dz = mz - cam.campos[2];
+                const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+                dx = dx / len; dy = dy / len; dz = dz / len;
+                if (MODE == MODE_FOV) {
+                    rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
+                    float3 rest = make_float3(0.f, 0.f, 0.f);
+                    if (in.shs != nullptr && cam.M > 0)
+                        rest = sh_accumulate(in.shs + (size_t)3 * cam.M * idx, 0, cam.sh_degree, dx, dy, dz, rest);
+                    rest.x += 0.5f; rest.y += 0.5f; rest.z += 0.5f;
+                    const int l0 = (int)__int_as_float(sm.lo[tid]);
+                    int l1 = (int)__int_as_float(sm.hi[tid]);
+                    if (sm.bl[tid]) l1 = min(l1 + 1, FOV_LEVELS - 1);
+                    // levels outside [l0,l1] are never composited (the reference leaves them uninitialised, Q4);
+                    // they are zeroed so that the blending kernel's unconditional L2 load stays finite.
+#pragma unroll
+                    for (int l = 0; l < FOV_LEVELS; l++) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (l >= l0 && l <= l1) {
+                            const float* dc = in.shs_dcs + (size_t)idx * 3 * FOV_LEVELS + l * 3;
+                            o.x = in.opacities[(size_t)idx * FOV_LEVELS + l];
+                            o.y = fmaxf(SH_C0 * dc[0] + rest.x, 0.0f);
+                            o.z = fmaxf(SH_C0 * dc[1] + rest.y, 0.0f);
+                            o.w = fmaxf(SH_C0 * dc[2] + rest.z, 0.0f);
+                        }
+                        rec[2 + l] = o;
+                    }
+                } else {
+                    float3 c;
+                    bool cl0 = false, cl1 = false, cl2 = false;
+                    if (in.colors_precomp != nullptr) {
+                        c = make_float3(in.colors_precomp[3 * (size_t)idx], in.colors_precomp[3 * (size_t)idx + 1], in.colors_precomp[3 * (size_t)idx + 2]);
+                    } else {
+                        const float* sh = in.shs + (size_t)3 * cam.M * idx;
+                        c = sh_accumulate(sh, 1, cam.sh_degree, dx, dy, dz, make_float3(SH_C0 * sh[0], SH_C0 * sh[1], SH_C0 * sh[2]));
+                        c.x += 0.5f; c.y += 0.5f; c.z += 0.5f;
+                        cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
+                        c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
+                    }
+                    rec[1] = make_float4(s.conz, in.opacities[idx], c.x, c.y);
+                    rec[2] = make_float4(c.z, s.depth, 0.f, 0.f);
+                    if (MODE == MODE_SUM) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
+                        reinterpret_cast<uchar4*>(ws.clamped)[idx] = make_uchar4(cl0, cl1, cl2, 0);
+                    }
+                }
+            }
+        }
+        visible_total += __popc(__ballot_sync(0xffffffffu, visible));
+        __syncthreads();   // smem arrays are reused by the next batch
+    }
+    // retire the partially filled staging chunk
+    if (sm.has_chunk) {
+        const uint32_t ib = sm.chunk_base + sm.chunk_used, ie = sm.chunk_base + STAGE_CHUNK;
+        for (uint32_t p = ib + tid; p < ie; p += PB)
+            if (p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
+    }
+    if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tile scan: exclusive prefix sum of the per-tile histogram (one block); publishes N and the overflow flag.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    __shared__ uint32_t max_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_s = 0; max_s = 0; }
+    __syncthreads();
+    uint32_t local_max = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = (i < T) ? ws.tile_count[i] : 0u;
+        local_max = max(local_max, v);
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t incl = x + (wid ? warp_sums[wid - 1] : 0u) + carry;
+        if (i < T) ws.tile_offset[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if (lane == 0) atomicMax(&max_s, local_max);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = carry_s;
+        ws.tile_offset[T] = total;
+        ws.hdr->stats.num_rendered = total;
+        ws.hdr->stats.overflow = (total > ws.hdr->cap || ws.hdr->stage_cursor > ws.stage_cap) ? 1u : 0u;
+        ws.hdr->stats.max_tile_instances = max_s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Scatter: staged instance -> its tile's segment of the key array (cursor allocation inside the segment).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(Workspace ws) {
+    const uint32_t n = min(ws.hdr->stage_cursor, ws.stage_cap);
+    const uint32_t cap = ws.hdr->cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t t = ws.stage_tile[i];
+        if (t == TILE_INVALID) continue;
+        const uint32_t slot = ws.tile_offset[t] + atomicAdd(&ws.tile_cursor[t], 1u);
+        if (slot < cap) ws.keysA[slot] = ws.stage_key[i];
+    }
+}
+
+cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
+    const int need = (in.P + PB - 1) / PB;
+    const int grid = max(1, min(need, min(num_sms * 4, (int)STAGE_MAX_BLOCKS)));
+    switch (mode) {
+        case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, 0, st>>>(ws, in); break;
+        case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, 0, st>>>(ws, in); break;
+        default: k_pre<MODE_FOV><<<grid, PB, 0, st>>>(ws, in); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_scan(const Workspace& ws, int T, cudaStream_t st) {
+    k_tile_scan<<<1, 1024, 0, st>>>(ws, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(const Workspace& ws, int num_sms, cudaStream_t st) {
+    k_scatter<<<num_sms * 8, 256, 0, st>>>(ws);
+    return cudaGetLastError();
+}
+
+}  // namespace fovgs

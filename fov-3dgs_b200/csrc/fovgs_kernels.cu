@@ -190,6 +190,7 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->P = a.P;
             h->tiles = a.tiles;
             h->cap = a.cap;
+            h->stage_cursor = 0;
         }
     }
 }
@@ -200,461 +201,6 @@ __device__ __forceinline__ void load_cam(CamParams& dst_smem, const FrameHeader*
     uint32_t* dst = (uint32_t*)&dst_smem;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Pass 1: per-Gaussian preprocess + tile filter (count).  Replaces preprocessCUDA + InclusiveSum + filter/OBB_test
-// (FOV/forward.cu:104-238, FOV/rasterizer_impl.cu:264-383; SUM/rasterizer_impl.cu:70-146).
-// ------------------------------------------------------------------------------------------------------------------
-template <int MODE>
-__device__ __forceinline__ unsigned filter_rect(const Workspace& ws, const Splat& s, int gx, float hl1, bool emit,
-                                                uint64_t key, uint32_t cap, float& lo_level, float& hi_level,
-                                                bool& any_blend) {
-    const unsigned tnum = (unsigned)(s.y1 - s.y0) * (unsigned)(s.x1 - s.x0);
-    unsigned count = 0;
-    if (tnum == 1) {
-        const uint32_t tile = (uint32_t)s.y0 * gx + s.x0;
-        bool pass = true;
-        if (MODE == MODE_FOV) {
-            const float level = ws.tile_min[tile];
-            pass = level < hl1;
-            if (pass) {
-                lo_level = level;
-                hi_level = level;
-                any_blend = any_blend || ws.tile_blend[tile];
-            }
-        }
-        if (pass) {
-            count = 1;
-            if (emit) {
-                const uint32_t slot = ws.tile_offset[tile] + atomicAdd(&ws.tile_cursor[tile], 1u);
-                if (slot < cap) ws.keysA[slot] = key;
-            } else {
-                atomicAdd(&ws.tile_count[tile], 1u);
-            }
-        }
-        return count;
-    }
-    ObbCorners oc;
-    obb_corners(s.px, s.py, s.e1x, s.e1y, s.e2x, s.e2y, s.len1, s.len2, oc);
-    for (int y = s.y0; y < s.y1; y++) {
-        const float tcy = FF((float)y, 16.0f, 8.0f);
-        for (int x = s.x0; x < s.x1; x++) {
-            const uint32_t tile = (uint32_t)y * gx + x;
-            float level = 0.0f;
-            if (MODE == MODE_FOV) {
-                level = ws.tile_min[tile];
-                if (!(level < hl1)) continue;
-            }
-            const float tcx = FF((float)x, 16.0f, 8.0f);
-            if (!obb_hits_tile(oc, s.px, s.py, s.e1x, s.e1y, s.e2x, s.e2y, s.len1, s.len2, tcx, tcy)) continue;
-            count++;
-            if (MODE == MODE_FOV) {
-                lo_level = fminf(lo_level, level);
-                hi_level = fmaxf(hi_level, level);
-                any_blend = any_blend || ws.tile_blend[tile];
-            }
-            if (emit) {
-                const uint32_t slot = ws.tile_offset[tile] + atomicAdd(&ws.tile_cursor[tile], 1u);
-                if (slot < cap) ws.keysA[slot] = key;
-            } else {
-                atomicAdd(&ws.tile_count[tile], 1u);
-            }
-        }
-    }
-    return count;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256) k_preprocess(Workspace ws, FrameInputs in) {
-    __shared__ CamParams cam;
-    load_cam(cam, ws.hdr);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    bool visible = false;
-    if (idx < in.P) {
-        const float mx = in.means3D[3 * idx], my = in.means3D[3 * idx + 1], mz = in.means3D[3 * idx + 2];
-        Splat s;
-        float c3[6];
-        bool ok;
-        if (in.cov3D_precomp != nullptr) {
-            // precomputed Σ3D path (FOV/forward.cu:155-158): only the projection differs
-            const float tz = xform_row(cam.view, 2, mx, my, mz);
-            ok = tz > 0.2f;
-            if (ok) {
-                // reuse project_splat with an identity-free shortcut: compute everything but Σ3D
-                for (int k = 0; k < 6; k++) c3[k] = in.cov3D_precomp[6 * idx + k];
-                const float hx = xform_row(cam.proj, 0, mx, my, mz);
-                const float hy = xform_row(cam.proj, 1, mx, my, mz);
-                const float hw = xform_row(cam.proj, 3, mx, my, mz);
-                const float pw = __frcp_rn(FA(hw, 0.0000001f));
-                const float tx = xform_row(cam.view, 0, mx, my, mz);
-                const float ty = xform_row(cam.view, 1, mx, my, mz);
-                cov2d_from_cov3d(cam, tx, ty, tz, c3, s.cxx, s.cxy, s.cyy);
-                const float bb = FM(s.cxy, s.cxy);
-                const float det = FF(s.cxx, s.cyy, -bb);
-                ok = det != 0.0f;
-                if (ok) {
-                    const float det_inv = __frcp_rn(det);
-                    s.conx = FM(s.cyy, det_inv);
-                    s.cony = FM(s.cxy, -det_inv);
-                    s.conz = FM(s.cxx, det_inv);
-                    const float mid = FM(FA(s.cxx, s.cyy), 0.5f);
-                    const float sq = __fsqrt_rn(fmaxf(FF(mid, mid, -det), 0.1f));
-                    const float l1 = FA(mid, sq), l2 = FS(mid, sq);
-                    s.radius = __float2int_ru(FM(__fsqrt_rn(fmaxf(l1, l2)), 3.0f));
-                    s.px = ndc2pix(FM(hx, pw), cam.W);
-                    s.py = ndc2pix(FM(hy, pw), cam.H);
-                    get_rect(s.px, s.py, s.radius, cam.grid_x, cam.grid_y, s.x0, s.y0, s.x1, s.y1);
-                    const unsigned tnum = (unsigned)(s.y1 - s.y0) * (unsigned)(s.x1 - s.x0);
-                    ok = tnum != 0;
-                    s.depth = tz;
-                    s.e1x = s.e1y = s.e2x = s.e2y = s.len1 = s.len2 = 0.0f;
-                    if (tnum > 1) {
-                        const float a1 = FS(s.cxx, l1), a2 = FS(s.cxx, l2);
-                        const float q1 = rsqrtf(FF(a1, a1, bb)), q2 = rsqrtf(FF(a2, a2, bb));
-                        s.e1x = FM(s.cxy, -q1); s.e1y = FM(a1, q1);
-                        s.e2x = FM(s.cxy, -q2); s.e2y = FM(a2, q2);
-                        s.len1 = FM(__fsqrt_rn(l1), 3.0f);
-                        s.len2 = FM(__fsqrt_rn(l2), 3.0f);
-                    }
-                }
-            }
-        } else {
-            const float sx = in.scales[3 * idx], sy = in.scales[3 * idx + 1], sz = in.scales[3 * idx + 2];
-            const float4 q = *reinterpret_cast<const float4*>(in.rotations + 4 * idx);
-            ok = project_splat(cam, mx, my, mz, sx, sy, sz, q.x, q.y, q.z, q.w, s, c3);
-        }
-        unsigned count = 0;
-        float hl = 0.0f;
-        if (ok) {
-            float lo, hi;
-            bool ab = false;
-            float hl1 = 0.0f;
-            if (MODE == MODE_FOV) {
-                hl = in.highest_levels[idx];
-                hl1 = FA(hl, 1.0f);
-                lo = hl;
-                hi = 0.0f;
-            }
-            count = filter_rect<MODE>(ws, s, cam.grid_x, hl1, false, 0ull, 0u, lo, hi, ab);
-        }
-        in.radii[idx] = count ? s.radius : 0;
-        if (count) {
-            visible = true;
-            ws.geomA[idx] = make_float4(s.depth, __int_as_float(s.radius), s.len1, s.len2);
-            ws.geomB[idx] = make_float4(s.e1x, s.e1y, s.e2x, s.e2y);
-            const int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
-            float4* rec = ws.rec + (size_t)R * idx;
-            rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
-            if (MODE == MODE_FOV) {
-                rec[1] = make_float4(s.conz, hl, 0.0f, 0.0f);
-            } else {
-                rec[1] = make_float4(s.conz, in.opacities[idx], 0.0f, 0.0f);  // colour filled by the emit pass
-            }
-            if (MODE == MODE_SUM) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
-            }
-        }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, visible);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ws.hdr->stats.num_visible, __popc(m));
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Tile scan: exclusive prefix sum of the per-tile histogram (one block); publishes N and the overflow flag.
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    __shared__ uint32_t max_s;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { carry_s = 0; max_s = 0; }
-    __syncthreads();
-    uint32_t local_max = 0;
-    for (int base = 0; base < T; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = (i < T) ? ws.tile_count[i] : 0u;
-        local_max = max(local_max, v);
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        const uint32_t incl = x + (wid ? warp_sums[wid - 1] : 0u) + carry;
-        if (i < T) ws.tile_offset[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
-        __syncthreads();
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if (lane == 0) atomicMax(&max_s, local_max);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t total = carry_s;
-        ws.tile_offset[T] = total;
-        ws.hdr->stats.num_rendered = total;
-        ws.hdr->stats.overflow = total > ws.hdr->cap ? 1u : 0u;
-        ws.hdr->stats.max_tile_instances = max_s;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// SH colour (OBB/rasterizer_impl.cu:32-82, SUM/forward.cu:20-71, FOV/rasterizer_impl.cu:37-84)
-// ------------------------------------------------------------------------------------------------------------------
-// `sh` points at this Gaussian's coefficient triplets; `first` is the index of the degree-1 block:
-// 1 for the PS1 layout (DC at 0), 0 for the FOV "rest" layout.  Returns Σ_{deg>=1}.
-__device__ __forceinline__ float3 sh_rest_sum(const float* __restrict__ sh, int first, int deg, float x, float y, float z,
-                                              float3 init) {
-    float3 r = init;
-    auto C = [&](int k, int ch) { return sh[3 * (first + k) + ch]; };
-    if (deg > 0) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            float v = (&r.x)[ch];
-            v = v - SH_C1 * y * C(0, ch) + SH_C1 * z * C(1, ch) - SH_C1 * x * C(2, ch);
-            (&r.x)[ch] = v;
-        }
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z;
-            const float xy = x * y, yz = y * z, xz = x * z;
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                float v = (&r.x)[ch];
-                v = v + SH_C2[0] * xy * C(3, ch) + SH_C2[1] * yz * C(4, ch) + SH_C2[2] * (2.0f * zz - xx - yy) * C(5, ch) +
-                    SH_C2[3] * xz * C(6, ch) + SH_C2[4] * (xx - yy) * C(7, ch);
-                (&r.x)[ch] = v;
-            }
-            if (deg > 2) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    float v = (&r.x)[ch];
-                    v = v + SH_C3[0] * y * (3.0f * xx - yy) * C(8, ch) + SH_C3[1] * xy * z * C(9, ch) +
-                        SH_C3[2] * y * (4.0f * zz - xx - yy) * C(10, ch) +
-                        SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * C(11, ch) +
-                        SH_C3[4] * x * (4.0f * zz - xx - yy) * C(12, ch) + SH_C3[5] * z * (xx - yy) * C(13, ch) +
-                        SH_C3[6] * x * (xx - 3.0f * yy) * C(14, ch);
-                    (&r.x)[ch] = v;
-                }
-            }
-        }
-    }
-    return r;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Pass 2: emit (tile, depth, id) instances into the tile-binned key array + per-Gaussian colour.
-// Replaces duplicateWithKeys (FOV/rasterizer_impl.cu:423-486) and compute_fov_colors (:490-530).
-// ------------------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) k_emit(Workspace ws, FrameInputs in) {
-    __shared__ CamParams cam;
-    load_cam(cam, ws.hdr);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= in.P) return;
-    const int radius = in.radii[idx];
-    if (radius <= 0) return;
-    const int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
-    float4* rec = ws.rec + (size_t)R * idx;
-    const float4 r0 = rec[0];
-    const float4 gA = ws.geomA[idx];
-    const float4 gB = ws.geomB[idx];
-    Splat s;
-    s.px = r0.x; s.py = r0.y; s.depth = gA.x; s.radius = radius; s.len1 = gA.z; s.len2 = gA.w;
-    s.e1x = gB.x; s.e1y = gB.y; s.e2x = gB.z; s.e2y = gB.w;
-    get_rect(s.px, s.py, s.radius, cam.grid_x, cam.grid_y, s.x0, s.y0, s.x1, s.y1);
-    float lo = 0.f, hi = 0.f, hl1 = 0.f;
-    bool ab = false;
-    if (MODE == MODE_FOV) {
-        const float hl = rec[1].y;
-        hl1 = FA(hl, 1.0f);
-        lo = hl;
-        hi = 0.0f;
-    }
-    const uint64_t key = ((uint64_t)__float_as_uint(s.depth) << 32) | (uint32_t)idx;
-    filter_rect<MODE>(ws, s, cam.grid_x, hl1, true, key, ws.hdr->cap, lo, hi, ab);
-
-    // ---- colour ----
-    const float mx = in.means3D[3 * idx], my = in.means3D[3 * idx + 1], mz = in.means3D[3 * idx + 2];
-    float dx = mx - cam.campos[0], dy = my - cam.campos[1], dz = mz - cam.campos[2];
-    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-    dx = dx / len; dy = dy / len; dz = dz / len;
-    if (MODE == MODE_FOV) {
-        float3 rest = make_float3(0.f, 0.f, 0.f);
-        if (in.shs != nullptr && cam.M > 0) rest = sh_rest_sum(in.shs + (size_t)3 * cam.M * idx, 0, cam.sh_degree, dx, dy, dz, rest);
-        rest.x += 0.5f; rest.y += 0.5f; rest.z += 0.5f;
-        const int l0 = (int)lo;
-        int l1 = (int)hi;
-        if (ab) l1 = min(l1 + 1, FOV_LEVELS - 1);
-        for (int l = l0; l <= l1; l++) {
-            const float* dc = in.shs_dcs + (size_t)idx * 3 * FOV_LEVELS + l * 3;
-            float4 o;
-            o.x = in.opacities[(size_t)idx * FOV_LEVELS + l];
-            o.y = fmaxf(SH_C0 * dc[0] + rest.x, 0.0f);
-            o.z = fmaxf(SH_C0 * dc[1] + rest.y, 0.0f);
-            o.w = fmaxf(SH_C0 * dc[2] + rest.z, 0.0f);
-            rec[2 + l] = o;
-        }
-        // levels outside [l0,l1] are never composited (reference leaves them uninitialised, Q4); the blending
-        // kernel may still *load* level l+1 of a skipped Gaussian, so keep those slots finite.
-        for (int l = 0; l < FOV_LEVELS; l++)
-            if (l < l0 || l > l1) rec[2 + l] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-        float3 c;
-        bool cl0 = false, cl1 = false, cl2 = false;
-        if (in.colors_precomp != nullptr) {
-            c = make_float3(in.colors_precomp[3 * idx], in.colors_precomp[3 * idx + 1], in.colors_precomp[3 * idx + 2]);
-        } else {
-            const float* sh = in.shs + (size_t)3 * cam.M * idx;
-            // result = SH_C0*sh[0], higher bands accumulated onto it in the reference's order, then + 0.5
-            c = sh_rest_sum(sh, 1, cam.sh_degree, dx, dy, dz, make_float3(SH_C0 * sh[0], SH_C0 * sh[1], SH_C0 * sh[2]));
-            c.x += 0.5f; c.y += 0.5f; c.z += 0.5f;
-            cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
-            c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
-        }
-        float4 r1 = rec[1];
-        r1.z = c.x; r1.w = c.y;
-        rec[1] = r1;
-        rec[2] = make_float4(c.z, 0.f, 0.f, 0.f);
-        if (MODE == MODE_SUM) {
-            uchar4 cl = make_uchar4(cl0, cl1, cl2, 0);
-            reinterpret_cast<uchar4*>(ws.clamped)[idx] = cl;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Per-tile sort: block-local LSD radix sort on the 32 depth bits (uniform digits skipped), ties (equal depth
-// bits) ordered by Gaussian id.  Output order == stable sort on (tile, depth_bits) of the id-ascending emission
-// order == the reference's point_list.
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tile_sort(Workspace ws, uint32_t* __restrict__ out_ranges,
-                                                   uint32_t* __restrict__ out_point_list) {
-    __shared__ uint32_t whist[8][256];
-    __shared__ uint32_t totals[256];
-    __shared__ uint32_t wsum[8];
-    __shared__ unsigned long long vary_s;
-    const int tile = blockIdx.x;
-    const uint32_t cap = ws.hdr->cap;
-    uint32_t sbeg = ws.tile_offset[tile], send = ws.tile_offset[tile + 1];
-    if (out_ranges && threadIdx.x == 0) {
-        // reference semantics: untouched tiles keep the memset value (0,0)
-        out_ranges[2 * tile] = (send > sbeg) ? sbeg : 0u;
-        out_ranges[2 * tile + 1] = (send > sbeg) ? send : 0u;
-    }
-    sbeg = min(sbeg, cap);
-    send = min(send, cap);
-    const uint32_t n = send - sbeg;
-    if (n == 0) return;
-    uint64_t* src = ws.keysA + sbeg;
-    uint64_t* dst = ws.keysB + sbeg;
-    uint32_t* out = ws.point_list + sbeg;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t* out2 = out_point_list ? out_point_list + sbeg : nullptr;
-    if (n == 1) {
-        if (tid == 0) {
-            out[0] = (uint32_t)src[0];
-            if (out2) out2[0] = (uint32_t)src[0];
-        }
-        return;
-    }
-    // which depth digits vary inside this segment?
-    if (tid == 0) vary_s = 0ull;
-    __syncthreads();
-    {
-        const uint64_t k0 = src[0];
-        uint64_t v = 0;
-        for (uint32_t i = tid; i < n; i += 256) v |= (src[i] ^ k0);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicOr(&vary_s, (unsigned long long)v);
-    }
-    __syncthreads();
-    const uint64_t vary = vary_s;
-    // contiguous chunk per warp (multiple of 32 so that rounds stay warp-aligned)
-    const uint32_t chunk = ((n + 7) / 8 + 31) & ~31u;
-    const uint32_t wbeg = min(n, warp * chunk), wend = min(n, wbeg + chunk);
-    for (int pass = 0; pass < 4; pass++) {
-        const int shift = 32 + 8 * pass;
-        if (((vary >> shift) & 0xffull) == 0) continue;
-        for (int i = tid; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0;
-        __syncthreads();
-        for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&whist[warp][(src[i] >> shift) & 0xff], 1u);
-        __syncthreads();
-        {   // thread d: exclusive scan over warps for digit d, then block scan over digits
-            uint32_t t = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { const uint32_t c = whist[w][tid]; whist[w][tid] = t; t += c; }
-            uint32_t x = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) wsum[warp] = x;
-            __syncthreads();
-            uint32_t base = x - t;
-            for (int w = 0; w < warp; w++) base += wsum[w];
-            totals[tid] = base;
-        }
-        __syncthreads();
-        for (int i = tid; i < 8 * 256; i += 256) (&whist[0][0])[i] += totals[i & 255];
-        __syncthreads();
-        for (uint32_t i0 = wbeg; i0 < wend; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool valid = i < wend;
-            const uint64_t key = valid ? src[i] : 0ull;
-            const uint32_t d = valid ? (uint32_t)((key >> shift) & 0xff) : (256u + lane);
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t base = 0;
-            if (valid) base = whist[warp][d];
-            __syncwarp();
-            if (valid) {
-                dst[base + rank] = key;
-                if (rank == 0) whist[warp][d] = base + __popc(peers);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        uint64_t* t = src; src = dst; dst = t;
-    }
-    // tie fix: runs of equal depth bits are ordered by id.  Heads are found first, then each head thread
-    // insertion-sorts its (typically 2-element) run.
-    {
-        for (uint32_t i = tid; i < n; i += 256) {
-            const uint32_t dk = (uint32_t)(src[i] >> 32);
-            const bool head = (i == 0) || ((uint32_t)(src[i - 1] >> 32) != dk);
-            if (head && i + 1 < n && (uint32_t)(src[i + 1] >> 32) == dk) {
-                uint32_t j = i + 1;
-                while (j < n && (uint32_t)(src[j] >> 32) == dk) j++;
-                for (uint32_t a = i + 1; a < j; a++) {
-                    const uint64_t k = src[a];
-                    uint32_t b = a;
-                    while (b > i && src[b - 1] > k) { src[b] = src[b - 1]; b--; }
-                    src[b] = k;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < n; i += 256) {
-        const uint32_t id = (uint32_t)src[i];
-        out[i] = id;
-        if (out2) out2[i] = id;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -874,7 +420,7 @@ __global__ void k_export_geometry(Workspace ws, int P, int mode, const int* __re
     const float4* rec = ws.rec + (size_t)R * idx;
     const float4 r0 = rec[0], r1 = rec[1];
     if (means2D) { means2D[2 * idx] = r0.x; means2D[2 * idx + 1] = r0.y; }
-    if (depths) depths[idx] = ws.geomA[idx].x;
+    if (depths) depths[idx] = (mode == MODE_FOV) ? r1.z : rec[2].y;
     if (conic) { conic[3 * idx] = r0.z; conic[3 * idx + 1] = r0.w; conic[3 * idx + 2] = r1.x; }
     if (cov3D && mode == MODE_SUM) for (int k = 0; k < 6; k++) cov3D[6 * idx + k] = ws.cov3D[6 * (size_t)idx + k];
     if (rgb && mode != MODE_FOV) { rgb[3 * idx] = r1.z; rgb[3 * idx + 1] = r1.w; rgb[3 * idx + 2] = rec[2].x; }
@@ -914,8 +460,6 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
         ws.tile_gy = (float*)take(T * 4);
         ws.tile_blend = (uint8_t*)take(T);
     }
-    ws.geomA = (float4*)take((size_t)P * 16);
-    ws.geomB = (float4*)take((size_t)P * 16);
     ws.rec = (float4*)take((size_t)P * 16 * (mode == MODE_FOV ? REC_FOV : REC_PS1));
     if (mode == MODE_SUM) {
         ws.cov3D = (float*)take((size_t)P * 24);
@@ -923,8 +467,13 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
         ws.final_T = (float*)take((size_t)W * H * 4);
         ws.n_contrib = (uint32_t*)take((size_t)W * H * 4);
     }
+    // staging holds up to cap instances plus holes: < 1/16 per retired chunk, one open chunk per block
+    const size_t stage_cap = cap ? (size_t)cap + (size_t)cap / 8 + (size_t)STAGE_MAX_BLOCKS * STAGE_CHUNK : 0;
+    ws.stage_cap = (uint32_t)(stage_cap > 0xfffffff0ull ? 0xfffffff0ull : stage_cap);
     ws.keysA = (uint64_t*)take((size_t)cap * 8);
-    ws.keysB = (uint64_t*)take((size_t)cap * 8);
+    ws.keysB = (uint64_t*)take(stage_cap * 8);
+    ws.stage_key = ws.keysB;
+    ws.stage_tile = (uint32_t*)take(stage_cap * 4);
     ws.point_list = (uint32_t*)take((size_t)cap * 4);
     ws.total_bytes = off;
     return ws;
@@ -979,18 +528,24 @@ template <int MODE>
 static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int W, int H, bool debug, cudaStream_t st) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const int T = gx * gy;
-    const int pb = (in.P + 255) / 256;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
     prof_mark(1, st);
-    k_preprocess<MODE><<<pb, 256, 0, st>>>(ws, in);
+    launch_pre(ws, in, (Mode)MODE, num_sms, st);
     STAGE_CHECK();
     prof_mark(2, st);
-    k_tile_scan<<<1, 1024, 0, st>>>(ws, T);
+    launch_tile_scan(ws, T, st);
     STAGE_CHECK();
     prof_mark(3, st);
-    k_emit<MODE><<<pb, 256, 0, st>>>(ws, in);
+    launch_scatter(ws, num_sms, st);
     STAGE_CHECK();
     prof_mark(4, st);
-    k_tile_sort<<<T, 256, 0, st>>>(ws, in.out_ranges, in.out_point_list);
+    launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);
     STAGE_CHECK();
     prof_mark(5, st);
     k_blend<MODE><<<T, 256, 0, st>>>(ws, in);
