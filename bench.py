@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: frames/s of the foveated rasterizer call at 1920x1080 on a
+~6 M-Gaussian "bicycle-shaped" synthetic scene (BASELINE.json metric; config 3 "4-level foveated, moving gaze").
+
+  python bench.py --gpus 1 --steps K --warmup W            # our sm_100a library through the drop-in package
+  python bench.py --impl reference ...                     # the UNMODIFIED reference CUDA extension (oracle/_ref)
+  python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...   # frames sharded by (camera, gaze)
+
+A "step" is one rendered frame: camera = ring[f % 30], gaze = the reference's 9-gaze grid cycled per frame
+(render_compose_gazes_fps.py:26) so the tile levels change every frame.  Per rank the K frames are
+f = rank + i * world (weak scaling: the model is replicated, frames are independent; NCCL only gathers timings).
+
+value  : whole-job frames/s with every input resident in HBM, timed on the device (CUDA events around the K steps,
+         max over ranks), library called in its pipelined mode (no per-frame host read-back).
+e2e    : the same frames/s through the public API with HOST inputs: per frame the camera matrices + gaze are copied
+         from pinned host memory, the [3,H,W] image is copied back to pinned host memory, wall clock with a
+         synchronize on both sides.
+roofline: the dominant kernel (largest mean stage time from CUDA events recorded by the library between its stages
+         over the timed region) against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+cpu_baseline: the CPU oracle (oracle/fovgs_oracle.c, a port: the reference ships no CPU path) on ONE frame of the same
+         workload, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "fov-3dgs_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "frames_per_second_foveated_1080p_6M"
+UNIT = "frames/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def sample_clocks(stop_evt, out, gpu_index):
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop_evt.wait()
+    p.terminate()
+    t.join(timeout=1.0)
+
+
+def clocks_summary(lines):
+    sm, mx, reasons = [], 0.0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0])); mx = max(mx, float(f[1]))
+        except ValueError:
+            continue
+        for nm, v in zip(names, f[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(nm)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def to_dev(d, dev):
+    return {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+
+
+class Workload:
+    def __init__(self, size):
+        from fovgs import synth
+        self.synth = synth
+        if size == "big":
+            self.P, self.W, self.H = 6_000_000, 1920, 1080
+            scene = synth.make_scene_bicycle(self.P, 1)
+        elif size == "mid":
+            self.P, self.W, self.H = 300_000, 800, 600
+            scene = synth.make_scene_bicycle(self.P, 1, log_scale_mu=-3.6)
+        else:
+            raise SystemExit("unknown --size")
+        self.scene = synth.add_foveation(scene)
+        self.cams = synth.ring_cameras(30, self.W, self.H)
+        self.gazes = synth.GAZES_9
+        self.name = f"fov_{self.P // 1000}k_{self.W}x{self.H}_4level_moving_gaze_ring30"
+
+    def frame(self, f):
+        return self.cams[f % len(self.cams)], self.gazes[f % len(self.gazes)]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, world, dev):
+    from fovgs import ops
+    import diff_gaussian_rasterization_fov_pcheck_obb as fovpkg
+
+    sc = to_dev(wl.scene, dev)
+    bg = torch.zeros(3, device=dev)
+    cams_dev = [to_dev(c, dev) for c in wl.cams]
+    gazes_dev = [torch.tensor(g, dtype=torch.float32, device=dev) for g in wl.gazes]
+
+    def settings(c):
+        return fovpkg.GaussianRasterizationSettings(c["image_height"], c["image_width"], c["tanfovx"], c["tanfovy"], bg, 1.0,
+                                                    c["viewmatrix"], c["projmatrix"], wl.scene["sh_degree"], c["campos"], False, False)
+
+    rs_dev = [settings(c) for c in cams_dev]
+
+    def render(rs, gaze):
+        r = fovpkg.GaussianRasterizer(raster_settings=rs)
+        return r(means3D=sc["means3D"], means2D=None, opacities=sc["opacities4"], shs_rest=sc["shs_rest"], scales=sc["scales"],
+                 rotations=sc["rotations"], shs_dcs=sc["shs_dcs"], highest_levels=sc["highest_levels"], gazeArray=gaze,
+                 alpha=0.05, blending=True)
+
+    frames = [rank + i * world for i in range(args.steps + args.warmup)]
+    with torch.no_grad():
+        # ---------------- value: device-resident inputs, pipelined ----------------
+        ops.set_deferred_check(False)
+        for f in frames[: args.warmup]:
+            render(rs_dev[f % 30], gazes_dev[f % 9])
+        torch.cuda.synchronize(dev)
+        ops.set_deferred_check(True)
+        ops.profile_enable(True)
+        stop_evt, clk = threading.Event(), []
+        th = threading.Thread(target=sample_clocks, args=(stop_evt, clk, torch.cuda.current_device()), daemon=True)
+        th.start()
+        time.sleep(0.25)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        stats = []
+        for f in frames[args.warmup:]:
+            render(rs_dev[f % 30], gazes_dev[f % 9])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        stop_evt.set()
+        th.join(timeout=2.0)
+        ops.check_pending(dev)
+        stage_frames = ops.profile_read_all()[-args.steps:]
+        ops.profile_enable(False)
+        ops.set_deferred_check(False)
+
+        # per-frame statistics (N, V, blending tiles) for the roofline byte model: re-render synchronously, untimed
+        for f in frames[args.warmup: args.warmup + min(args.steps, 18)]:
+            render(rs_dev[f % 30], gazes_dev[f % 9])
+            stats.append(dict(ops.last_stats))
+
+        # ---------------- e2e: host inputs, image back to the host ----------------
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        cams_host = [{k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in c.items()} for c in wl.cams]
+        gazes_host = [pin(np.asarray(g, np.float32)) for g in wl.gazes]
+        img_host = torch.empty((3, wl.H, wl.W), dtype=torch.float32).pin_memory()
+        h2d = (16 + 16 + 3 + 2) * 4
+        d2h = 3 * wl.H * wl.W * 4
+
+        def e2e_frame(f):
+            c = cams_host[f % 30]
+            cd = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+            g = gazes_host[f % 9].to(dev, non_blocking=True)
+            img, _ = render(settings(cd), g)
+            img_host.copy_(img, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        for f in frames[: args.warmup]:
+            e2e_frame(f)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for f in frames[args.warmup:]:
+            e2e_frame(f)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+
+    return {"ms": ms, "e2e_s": e2e_s, "stages": stage_frames, "stats": stats, "clocks": clocks_summary(clk), "h2d": h2d, "d2h": d2h,
+            "launches_per_frame": 11}
+
+
+def run_reference(args, wl, rank, world, dev):
+    """The unmodified reference extension (oracle/_ref/ref_fov_C.so) through its pybind entry point, same frames."""
+    import ref_api
+    mod = ref_api.ref_module("ref_fov_C")
+    if mod is None:
+        return None
+    sc = to_dev(wl.scene, dev)
+    bg = torch.zeros(3, device=dev)
+    cams_dev = [to_dev(c, dev) for c in wl.cams]
+    gazes_dev = [torch.tensor(g, dtype=torch.float32, device=dev) for g in wl.gazes]
+    frames = [rank + i * world for i in range(args.steps + args.warmup)]
+
+    def render(c, g):
+        return ref_api.fov_forward(mod, sc, c, g, 0.05, True, bg)
+
+    with torch.no_grad():
+        for f in frames[: args.warmup]:
+            render(cams_dev[f % 30], gazes_dev[f % 9])
+        torch.cuda.synchronize(dev)
+        stop_evt, clk = threading.Event(), []
+        th = threading.Thread(target=sample_clocks, args=(stop_evt, clk, torch.cuda.current_device()), daemon=True)
+        th.start()
+        time.sleep(0.25)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f in frames[args.warmup:]:
+            render(cams_dev[f % 30], gazes_dev[f % 9])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        stop_evt.set()
+        th.join(timeout=2.0)
+        # e2e with host camera / gaze and image read-back, same protocol as our arm
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        cams_host = [{k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in c.items()} for c in wl.cams]
+        gazes_host = [pin(np.asarray(g, np.float32)) for g in wl.gazes]
+        img_host = torch.empty((3, wl.H, wl.W), dtype=torch.float32).pin_memory()
+
+        def e2e_frame(f):
+            c = cams_host[f % 30]
+            cd = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+            g = gazes_host[f % 9].to(dev, non_blocking=True)
+            out = render(cd, g)
+            img_host.copy_(out[1], non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        for f in frames[: args.warmup]:
+            e2e_frame(f)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for f in frames[args.warmup:]:
+            e2e_frame(f)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+    return {"ms": ms, "e2e_s": e2e_s, "clocks": clocks_summary(clk), "h2d": (16 + 16 + 3 + 2) * 4, "d2h": 3 * wl.H * wl.W * 4}
+
+
+def cpu_baseline(wl):
+    """One frame of the same workload on the host cores with the CPU oracle (a port; the reference has no CPU path)."""
+    import oracle
+    cam, gaze = wl.frame(0)
+    nthreads = oracle.lib().orc_num_threads()
+    t0 = time.perf_counter()
+    o = oracle.forward_fov(wl.scene, cam, gaze, list_cap=1 << 27)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": int(nthreads), "kind": "port",
+            "sample": f"1 frame (camera 0, gaze {gaze}) of {wl.name}; {o['num_rendered']} instances; {dt:.2f} s"}
+
+
+def roofline(res, wl, steps):
+    """Dominant stage vs HBM: algorithmic bytes per launch / mean stage duration (DESIGN.md §5 states the byte model)."""
+    stages = res["stages"]
+    names = list(stages[0].keys())
+    mean = {k: float(np.mean([s[k] for s in stages])) for k in names}
+    dom = max(mean, key=mean.get)
+    st = res["stats"]
+    N = float(np.mean([s["num_rendered"] for s in st]))
+    V = float(np.mean([s["num_visible"] for s in st]))
+    Tb = float(np.mean([s["num_blend_tiles"] for s in st]))
+    T = ((wl.W + 15) // 16) * ((wl.H + 15) // 16)
+    P, pix = wl.P, wl.W * wl.H
+    blend_share = Tb / T
+    bytes_model = {
+        # reads xyz+scale+rot+level for all P, SH-rest + 4 dc + 4 opacity for visible; writes radii, records, staged instances
+        "preprocess": P * (12 + 12 + 16 + 4) + V * (180 + 48 + 16) + P * 4 + V * 96 + N * (12 + 4),
+        "tile_scan": T * 8,
+        "scatter": N * (12 + 4 + 8),
+        "tile_sort": N * (8 + 4),
+        "blend": N * (4 + 48 + 16 * blend_share) + pix * 12,
+        "setup": T * 24,
+    }
+    peak, src = measured_peak_gbs()
+    achieved = bytes_model[dom] / (mean[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_model[dom],
+            "stage_ms_mean": mean, "N_mean": N, "V_mean": V, "blend_tile_share": blend_share}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=90)
+    ap.add_argument("--warmup", type=int, default=9)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="big", choices=["big", "mid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "error": "no CUDA device: the product path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    wl = Workload(args.size)
+    if args.impl == "reference":
+        res = run_reference(args, wl, rank, world, dev)
+        if res is None:
+            # reference extension not built here: fall back to the CPU oracle port on rank 0 (bounded sample)
+            if rank == 0:
+                cb = cpu_baseline(wl)
+                print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                                  "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+                                  "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                                  "config": {"workload": wl.name, "device": "cpu"}, "cpu_baseline": cb,
+                                  "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
+    else:
+        res = run_ours(args, wl, rank, world, dev)
+
+    # max over ranks (device time and wall time)
+    t = torch.tensor([res["ms"], res["e2e_s"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_max = float(t[0]), float(t[1])
+    total_frames = args.steps * world
+    value = total_frames / (ms_max * 1e-3)
+    e2e_v = total_frames / e2e_max
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "gaussians": wl.P, "width": wl.W, "height": wl.H, "levels": 4, "alpha": 0.05,
+                       "frames_per_rank": args.steps, "sharding": "frame (camera,gaze) round-robin, model replicated",
+                       "l2_policy": "inputs larger than L2 (model 1.7 GB + 0.6 GB of per-frame records vs 126 MB L2)"},
+            "clocks": res["clocks"],
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"]},
+        }
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["config"]["device"] = "cuda (the reference is a CUDA extension; built unmodified by oracle/build_ref.py)"
+            line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": "reference CUDA rasterizer on the same B200; see config.device"}
+            line["gpu_launches"] = 0
+        else:
+            line["gpu_launches"] = res["launches_per_frame"] * args.steps
+            line["roofline"] = roofline(res, wl, args.steps)
+            if not args.no_cpu_baseline and world == 1:
+                try:
+                    line["cpu_baseline"] = cpu_baseline(wl)
+                except Exception as ex:  # never lose the GPU numbers to a host-side problem
+                    line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

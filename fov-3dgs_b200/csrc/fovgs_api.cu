@@ -173,19 +173,34 @@ int fovgs_fov_geometry(const void* workspace, int32_t P, int32_t W, int32_t H, f
 int fovgs_profile_enable(int32_t on) {
     g_prof.enabled = on != 0;
     g_prof.valid = 0;
+    g_prof.frames = 0;
+    return 0;
+}
+
+int fovgs_profile_count(void) { return g_prof.frames < StageProfile::SLOTS ? g_prof.frames : StageProfile::SLOTS; }
+
+static int profile_read_slot(int slot, float* ms_out_host, int32_t n) {
+    if (!ms_out_host || n < StageProfile::N - 1) return fail(FOVGS_ERR_INVALID_ARG, "profile_read: need room for 6 floats%s");
+    if (!g_prof.created || g_prof.frames == 0 || g_prof.valid < StageProfile::N)
+        return fail(FOVGS_ERR_INVALID_ARG, "profile_read: no profiled frame%s");
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[slot][StageProfile::N - 1]);
+    if (e != cudaSuccess) return fail_cuda(e, "profile_read");
+    for (int i = 0; i + 1 < StageProfile::N; i++) {
+        e = cudaEventElapsedTime(&ms_out_host[i], g_prof.ev[slot][i], g_prof.ev[slot][i + 1]);
+        if (e != cudaSuccess) return fail_cuda(e, "profile_read");
+    }
     return 0;
 }
 
 int fovgs_profile_read(float* ms_out_host, int32_t n) {
-    if (!ms_out_host || n < StageProfile::N - 1) return fail(FOVGS_ERR_INVALID_ARG, "profile_read: need room for 6 floats%s");
-    if (!g_prof.enabled || g_prof.valid < StageProfile::N) return fail(FOVGS_ERR_INVALID_ARG, "profile_read: no profiled frame%s");
-    cudaError_t e = cudaEventSynchronize(g_prof.ev[StageProfile::N - 1]);
-    if (e != cudaSuccess) return fail_cuda(e, "profile_read");
-    for (int i = 0; i + 1 < StageProfile::N; i++) {
-        e = cudaEventElapsedTime(&ms_out_host[i], g_prof.ev[i], g_prof.ev[i + 1]);
-        if (e != cudaSuccess) return fail_cuda(e, "profile_read");
-    }
-    return 0;
+    return profile_read_slot((g_prof.frames > 0 ? g_prof.frames - 1 : 0) % StageProfile::SLOTS, ms_out_host, n);
+}
+
+int fovgs_profile_read_frame(int32_t k, float* ms_out_host, int32_t n) {
+    if (k < 0 || k >= fovgs_profile_count()) return fail(FOVGS_ERR_INVALID_ARG, "profile_read_frame: no such frame%s");
+    // frames older than SLOTS have been overwritten: index k counts from the oldest frame still held
+    const int oldest = g_prof.frames > StageProfile::SLOTS ? g_prof.frames - StageProfile::SLOTS : 0;
+    return profile_read_slot((oldest + k) % StageProfile::SLOTS, ms_out_host, n);
 }
 
 }  // extern "C"

@@ -112,6 +112,9 @@ struct PreSmem {
     float px[PB], py[PB], e1x[PB], e1y[PB], e2x[PB], e2y[PB], l1[PB], l2[PB], hl1[PB];
     uint32_t dbits[PB];
     int x0[PB], y0[PB], w[PB];
+    float rw[PB];                // 1 / w (candidate index -> (row, col) without an integer division)
+    uint8_t single[PB];          // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
+    int bbox[FOV_LEVELS][4];
     uint32_t pref[PB + 1];
     uint32_t cnt[PB];
     int lo[PB], hi[PB];          // FOV: float bits of the (non-negative) lowest / highest level used
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
         uint32_t* dst = (uint32_t*)&sm.cam;
         for (int i = tid; i < n; i += PB) dst[i] = src[i];
         if (tid == 0) { sm.chunk_base = 0; sm.chunk_used = STAGE_CHUNK; sm.has_chunk = 0; }
+        if (MODE == MODE_FOV && tid < FOV_LEVELS * 4) (&sm.bbox[0][0])[tid] = (&ws.hdr->lvl_bbox[0][0])[tid];
     }
     __syncthreads();
     const CamParams& cam = sm.cam;
@@ -160,14 +164,26 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
         }
         uint32_t tnum = 0;
         if (ok) {
-            tnum = (uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0);
+            const bool single0 = ((uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0)) == 1u;
+            int cx0 = s.x0, cy0 = s.y0, cx1 = s.x1, cy1 = s.y1;
+            if (MODE == MODE_FOV) {
+                hl = in.highest_levels[idx];
+                // tiles outside the level's bounding box fail `tile_min < hl + 1` anyway: do not even enumerate them
+                const int li = (int)hl;
+                if (hl >= 0.0f && hl <= (float)(FOV_LEVELS - 1) && (float)li == hl) {
+                    cx0 = max(cx0, sm.bbox[li][0]); cy0 = max(cy0, sm.bbox[li][1]);
+                    cx1 = min(cx1, sm.bbox[li][2]); cy1 = min(cy1, sm.bbox[li][3]);
+                }
+            }
+            const int cw = max(cx1 - cx0, 0), ch = max(cy1 - cy0, 0);
+            tnum = (uint32_t)cw * (uint32_t)ch;
+            sm.single[tid] = single0;
             sm.px[tid] = s.px; sm.py[tid] = s.py;
             sm.e1x[tid] = s.e1x; sm.e1y[tid] = s.e1y; sm.e2x[tid] = s.e2x; sm.e2y[tid] = s.e2y;
             sm.l1[tid] = s.len1; sm.l2[tid] = s.len2;
             sm.dbits[tid] = __float_as_uint(s.depth);
-            sm.x0[tid] = s.x0; sm.y0[tid] = s.y0; sm.w[tid] = s.x1 - s.x0;
+            sm.x0[tid] = cx0; sm.y0[tid] = cy0; sm.w[tid] = cw; sm.rw[tid] = 1.0f / (float)max(cw, 1);
             if (MODE == MODE_FOV) {
-                hl = in.highest_levels[idx];
                 sm.hl1[tid] = FA(hl, 1.0f);
                 sm.lo[tid] = __float_as_int(fmaxf(hl, 0.0f));
                 sm.hi[tid] = 0;
@@ -206,12 +222,15 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
                     if (sm.pref[mid] <= c) lo_i = mid; else hi_i = mid;
                 }
                 owner = (uint32_t)lo_i;
-                const uint32_t t = c - sm.pref[owner];
+                const int t = (int)(c - sm.pref[owner]);
                 const int w = sm.w[owner];
-                const int ty = sm.y0[owner] + (int)(t / (uint32_t)w);
-                const int tx = sm.x0[owner] + (int)(t % (uint32_t)w);
+                int q = (int)(((float)t + 0.5f) * sm.rw[owner]);
+                int rem = t - q * w;
+                if (rem < 0) { q--; rem += w; } else if (rem >= w) { q++; rem -= w; }
+                const int ty = sm.y0[owner] + q;
+                const int tx = sm.x0[owner] + rem;
                 tile = (uint32_t)ty * gx + tx;
-                single = (sm.pref[owner + 1] - sm.pref[owner]) == 1u;
+                single = sm.single[owner] != 0;
                 pass = true;
                 if (MODE == MODE_FOV) {
                     level = ws.tile_min[tile];
@@ -227,7 +246,7 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
                     pass = obb_hits_tile(oc, cx, cy, e1x, e1y, e2x, e2y, l1, l2, tcx, tcy);
                 }
                 if (pass) {
-                    atomicAdd(&ws.tile_count[tile], 1u);
+                    atomicAdd(&ws.tile_count[(size_t)tile * CSTRIDE], 1u);
                     if (MODE == MODE_FOV) tblend = ws.tile_blend[tile] != 0;
                 }
             }
@@ -369,13 +388,15 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     __shared__ uint32_t max_s;
+    __shared__ uint32_t bucket_cnt[33], bucket_base[33];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) { carry_s = 0; max_s = 0; }
+    if (threadIdx.x < 33) bucket_cnt[threadIdx.x] = 0;
     __syncthreads();
     uint32_t local_max = 0;
     for (int base = 0; base < T; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t v = (i < T) ? ws.tile_count[i] : 0u;
+        const uint32_t v = (i < T) ? ws.tile_count[(size_t)i * CSTRIDE] : 0u;
         local_max = max(local_max, v);
         uint32_t x = v;
 #pragma unroll
@@ -413,6 +434,22 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
         ws.hdr->stats.overflow = (total > ws.hdr->cap || ws.hdr->stage_cursor > ws.stage_cap) ? 1u : 0u;
         ws.hdr->stats.max_tile_instances = max_s;
     }
+    // tile order for the per-tile kernels: descending power-of-two size class (longest-processing-time-first)
+    for (int i = threadIdx.x; i < T; i += 1024) {
+        const uint32_t c = ws.tile_count[(size_t)i * CSTRIDE];
+        atomicAdd(&bucket_cnt[c ? 32 - __clz(c) : 0], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 32; b >= 0; b--) { bucket_base[b] = run; run += bucket_cnt[b]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += 1024) {
+        const uint32_t c = ws.tile_count[(size_t)i * CSTRIDE];
+        const uint32_t pos = atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u);
+        ws.tile_order[pos] = (uint32_t)i;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -424,7 +461,7 @@ __global__ void __launch_bounds__(256) k_scatter(Workspace ws) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t t = ws.stage_tile[i];
         if (t == TILE_INVALID) continue;
-        const uint32_t slot = ws.tile_offset[t] + atomicAdd(&ws.tile_cursor[t], 1u);
+        const uint32_t slot = ws.tile_offset[t] + atomicAdd(&ws.tile_cursor[(size_t)t * CSTRIDE], 1u);
         if (slot < cap) ws.keysA[slot] = ws.stage_key[i];
     }
 }

@@ -139,6 +139,26 @@ __global__ void k_tile_infos(int T, const float* __restrict__ tile_levels, const
     }
     const unsigned m = __ballot_sync(0xffffffffu, blend);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&hdr->stats.num_blend_tiles, __popc(m));
+    // bounding box of the tiles a Gaussian whose highest level is l can still land in: {tile_min < l + 1}
+    {
+        const bool in_range = idx < (uint64_t)T;
+        const float tm = in_range ? tile_level_min[idx] : 0.0f;
+        const int tx = in_range ? (int)(idx % tile_width_num) : 0, ty = in_range ? (int)(idx / tile_width_num) : 0;
+#pragma unroll
+        for (int l = 0; l < FOV_LEVELS; l++) {
+            const bool inl = in_range && (tm < (float)(l + 1));
+            const int x0 = __reduce_min_sync(0xffffffffu, inl ? tx : 0x7fffffff);
+            const int y0 = __reduce_min_sync(0xffffffffu, inl ? ty : 0x7fffffff);
+            const int x1 = __reduce_max_sync(0xffffffffu, inl ? tx + 1 : -1);
+            const int y1 = __reduce_max_sync(0xffffffffu, inl ? ty + 1 : -1);
+            if ((threadIdx.x & 31) == 0 && x1 > 0) {
+                atomicMin(&hdr->lvl_bbox[l][0], x0);
+                atomicMin(&hdr->lvl_bbox[l][1], y0);
+                atomicMax(&hdr->lvl_bbox[l][2], x1);
+                atomicMax(&hdr->lvl_bbox[l][3], y1);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -158,8 +178,8 @@ struct SetupArgs {
 __global__ void k_setup(Workspace ws, SetupArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.tiles) {
-        ws.tile_count[t] = 0;
-        ws.tile_cursor[t] = 0;
+        ws.tile_count[(size_t)t * CSTRIDE] = 0;
+        ws.tile_cursor[(size_t)t * CSTRIDE] = 0;
     }
     if (blockIdx.x == 0) {
         FrameHeader* h = ws.hdr;
@@ -192,6 +212,7 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->cap = a.cap;
             h->stage_cursor = 0;
         }
+        if (i < FOV_LEVELS * 4) (&h->lvl_bbox[0][0])[i] = ((i & 3) < 2) ? 0x7fffffff : -1;
     }
 }
 
@@ -201,204 +222,6 @@ __device__ __forceinline__ void load_cam(CamParams& dst_smem, const FrameHeader*
     uint32_t* dst = (uint32_t*)&dst_smem;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Blend (v1: one 16x16 tile per CTA, one pixel per thread; arithmetic pinned to the reference binary).
-// FOV plain tiles  : FOV/forward.cu:490-609   FOV blending tiles: FOV/forward.cu:262-476
-// OBB              : OBB/forward.cu:251-384   SUM: SUM/forward.cu:298-430
-// ------------------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
-    __shared__ float4 sA[256];   // px, py, conx, cony
-    __shared__ float4 sB[256];   // conz, opacity(L1), (PS1: r, g)
-    __shared__ float4 sC[256];   // PS1: b | FOV: colour L1 (x=op1,r,g,b)
-    __shared__ float4 sD[256];   // FOV blending: level L2 (op2, r, g, b)
-    __shared__ int sId[256];
-    const FrameHeader* __restrict__ hdr = ws.hdr;
-    const int W = hdr->cam.W, H = hdr->cam.H, gx = hdr->cam.grid_x;
-    const int tile = blockIdx.x;
-    const int tx = tile % gx, ty = tile / gx;
-    const int tid = threadIdx.x;
-    const int pxi = tx * TILE + (tid & 15), pyi = ty * TILE + (tid >> 4);
-    const bool inside = pxi < W && pyi < H;
-    const uint32_t pix_id = (uint32_t)W * pyi + pxi;
-    const float pixx = (float)pxi, pixy = (float)pyi;
-    const uint32_t cap = hdr->cap;
-    const uint32_t rbeg = min(ws.tile_offset[tile], cap), rend = min(ws.tile_offset[tile + 1], cap);
-    const int total = (int)(rend - rbeg);
-    const int rounds = (total + 255) / 256;
-    int toDo = total;
-    bool done = !inside;
-    const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
-    const size_t HW = (size_t)H * W;
-
-    if (MODE == MODE_FOV) {
-        const bool blending = ws.tile_blend[tile] != 0;
-        const float tile_level_f = ws.tile_min[tile];   // Q2: kernels receive tile_level_min
-        const int L1 = (int)tile_level_f;
-        if (!blending) {
-            float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-            for (int i = 0; i < rounds; i++, toDo -= 256) {
-                if (__syncthreads_count(done) == 256) break;
-                const int progress = i * 256 + tid;
-                if (progress < total) {
-                    const uint32_t id = ws.point_list[rbeg + progress];
-                    const float4* rec = ws.rec + (size_t)REC_FOV * id;
-                    sA[tid] = rec[0];
-                    sB[tid] = rec[1];
-                    sC[tid] = rec[2 + L1];
-                }
-                __syncthreads();
-                const int lim = min(256, toDo);
-                for (int j = 0; !done && j < lim; j++) {
-                    const float4 a = sA[j];
-                    const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-                    const float power = gauss_power(a.z, a.w, sB[j].x, dx, dy);
-                    if (power > 0.0f || power < -4.5f) continue;
-                    const float4 c = sC[j];
-                    const float alpha = fminf(0.99f, FM(c.x, expf(power)));
-                    if (alpha < 1.0f / 255.0f) continue;
-                    const float test_T = FM(T, FS(1.0f, alpha));
-                    if (test_T < 0.0001f) { done = true; continue; }
-                    const float w = FM(alpha, T);
-                    C0 = FF(c.y, w, C0); C1 = FF(c.z, w, C1); C2 = FF(c.w, w, C2);
-                    T = test_T;
-                }
-            }
-            if (inside) {
-                in.out_color[pix_id] = FF(bg0, T, C0);
-                in.out_color[HW + pix_id] = FF(bg1, T, C1);
-                in.out_color[2 * HW + pix_id] = FF(bg2, T, C2);
-            }
-        } else {
-            const int L2 = L1 + 1;
-            const float L2_f = FA(tile_level_f, 1.0f);
-            const float dxl = (float)(tid & 15), dyl = (float)(tid >> 4);
-            const float est = FF(FF(dxl, ws.tile_gx[tile], FM(dyl, ws.tile_gy[tile])), 0.0625f, tile_level_f);
-            bool L1_done = est > (float)L2;
-            bool L2_done = false;
-            float T1 = 1.0f, T2 = 1.0f, A0 = 0.f, A1 = 0.f, A2 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
-            for (int i = 0; i < rounds; i++, toDo -= 256) {
-                if (__syncthreads_count(done) == 256) break;
-                const int progress = i * 256 + tid;
-                if (progress < total) {
-                    const uint32_t id = ws.point_list[rbeg + progress];
-                    const float4* rec = ws.rec + (size_t)REC_FOV * id;
-                    sA[tid] = rec[0];
-                    sB[tid] = rec[1];
-                    sC[tid] = rec[2 + L1];
-                    sD[tid] = rec[2 + L2];
-                }
-                __syncthreads();
-                const int lim = min(256, toDo);
-                for (int j = 0; !done && j < lim; j++) {
-                    const float4 a = sA[j];
-                    const float4 b = sB[j];
-                    const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-                    const float power = gauss_power(a.z, a.w, b.x, dx, dy);
-                    if (power > 0.0f || power < -4.5f) continue;
-                    const float e = expf(power);
-                    if (!L1_done) {
-                        const float4 c = sC[j];
-                        const float alpha1 = fminf(0.99f, FM(c.x, e));
-                        if (!(alpha1 < 1.0f / 255.0f)) {
-                            const float test_T1 = FM(T1, FS(1.0f, alpha1));
-                            L1_done = test_T1 < 0.0001f;
-                            if (!L1_done) {
-                                const float w = FM(alpha1, T1);
-                                A0 = FF(c.y, w, A0); A1 = FF(c.z, w, A1); A2 = FF(c.w, w, A2);
-                                T1 = test_T1;
-                            }
-                        }
-                    }
-                    if (!L2_done) {
-                        const float4 c = sD[j];
-                        const float alpha2 = fminf(0.99f, FM(c.x, e));
-                        const bool skip2 = (alpha2 < 1.0f / 255.0f) || (FA(b.y, 1.0f) < L2_f);
-                        if (!skip2) {
-                            const float test_T2 = FM(T2, FS(1.0f, alpha2));
-                            L2_done = test_T2 < 0.0001f;
-                            if (!L2_done) {
-                                const float w = FM(alpha2, T2);
-                                B0 = FF(c.y, w, B0); B1 = FF(c.z, w, B1); B2 = FF(c.w, w, B2);
-                                T2 = test_T2;
-                            }
-                        }
-                    }
-                    if (L1_done && L2_done) { done = true; continue; }
-                }
-            }
-            if (inside) {
-                A0 = FF(bg0, T1, A0); A1 = FF(bg1, T1, A1); A2 = FF(bg2, T1, A2);
-                B0 = FF(bg0, T2, B0); B1 = FF(bg1, T2, B1); B2 = FF(bg2, T2, B2);
-                const float v = FS(est, FA((float)L1, kStartBlend));
-                const float x = __saturatef(FA(fabsf(v), fabsf(v)));   // |v| / blend_width(0.5), clamped to [0,1]
-                const float m3 = FM(x, FM(x, -3.0f));
-                const float nb = FF(x, FM(x, FA(x, x)), m3);            // -(3x^2 - 2x^3)
-                const float w1 = FA(nb, 1.0f);
-                const float w2 = FS(1.0f, w1);
-                in.out_color[pix_id] = FF(A0, w1, FM(B0, w2));
-                in.out_color[HW + pix_id] = FF(A1, w1, FM(B1, w2));
-                in.out_color[2 * HW + pix_id] = FF(A2, w1, FM(B2, w2));
-            }
-        }
-        return;
-    }
-
-    // ---- PS=1 (OBB / SUM) ----
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t contributor = 0, last_contributor = 0;
-    for (int i = 0; i < rounds; i++, toDo -= 256) {
-        if (__syncthreads_count(done) == 256) break;
-        const int progress = i * 256 + tid;
-        if (progress < total) {
-            const uint32_t id = ws.point_list[rbeg + progress];
-            const float4* rec = ws.rec + (size_t)REC_PS1 * id;
-            sA[tid] = rec[0];
-            sB[tid] = rec[1];
-            sC[tid] = rec[2];
-            if (MODE == MODE_SUM) {
-                sId[tid] = (int)id;
-                atomicAdd(&in.gaussians_count[id], 1);
-            }
-        }
-        __syncthreads();
-        const int lim = min(256, toDo);
-        for (int j = 0; !done && j < lim; j++) {
-            contributor++;
-            const float4 a = sA[j];
-            const float4 b = sB[j];
-            const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-            const float power = gauss_power(a.z, a.w, b.x, dx, dy);
-            if (power > 0.0f || power < -4.5f) continue;
-            const float alpha = fminf(0.99f, FM(b.y, expf(power)));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = FM(T, FS(1.0f, alpha));
-            if (test_T < 0.0001f) { done = true; continue; }
-            if (MODE == MODE_SUM) {
-                // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
-                atomicAdd(&in.contributions[sId[j]], FM(alpha, T));
-                C0 = FF(T, FM(alpha, b.z), C0);
-                C1 = FF(T, FM(alpha, b.w), C1);
-                C2 = FF(T, FM(alpha, sC[j].x), C2);
-            } else {
-                const float w = FM(alpha, T);
-                C0 = FF(b.z, w, C0); C1 = FF(b.w, w, C1); C2 = FF(sC[j].x, w, C2);
-            }
-            T = test_T;
-            last_contributor = contributor;
-        }
-    }
-    if (inside) {
-        if (MODE == MODE_SUM) {
-            ws.final_T[pix_id] = T;
-            ws.n_contrib[pix_id] = last_contributor;
-        }
-        in.out_color[pix_id] = FF(bg0, T, C0);
-        in.out_color[HW + pix_id] = FF(bg1, T, C1);
-        in.out_color[2 * HW + pix_id] = FF(bg2, T, C2);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -450,9 +273,10 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
         return p;
     };
     ws.hdr = (FrameHeader*)take(sizeof(FrameHeader));
-    ws.tile_count = (uint32_t*)take(T * 4);
+    ws.tile_count = (uint32_t*)take(T * 4 * CSTRIDE);
     ws.tile_offset = (uint32_t*)take((T + 1) * 4);
-    ws.tile_cursor = (uint32_t*)take(T * 4);
+    ws.tile_cursor = (uint32_t*)take(T * 4 * CSTRIDE);
+    ws.tile_order = (uint32_t*)take(T * 4);
     if (mode == MODE_FOV) {
         ws.tile_level = (float*)take(T * 4);
         ws.tile_min = (float*)take(T * 4);
@@ -484,10 +308,12 @@ StageProfile g_prof;
 static inline void prof_mark(int i, cudaStream_t st) {
     if (!g_prof.enabled) return;
     if (!g_prof.created) {
-        for (int k = 0; k < StageProfile::N; k++) cudaEventCreate(&g_prof.ev[k]);
+        for (int s = 0; s < StageProfile::SLOTS; s++)
+            for (int k = 0; k < StageProfile::N; k++) cudaEventCreate(&g_prof.ev[s][k]);
         g_prof.created = true;
     }
-    cudaEventRecord(g_prof.ev[i], st);
+    if (i == 0) g_prof.frames++;
+    cudaEventRecord(g_prof.ev[(g_prof.frames - 1) % StageProfile::SLOTS][i], st);
     g_prof.valid = i + 1;
 }
 
@@ -548,7 +374,7 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);
     STAGE_CHECK();
     prof_mark(5, st);
-    k_blend<MODE><<<T, 256, 0, st>>>(ws, in);
+    launch_blend(ws, in, T, (Mode)MODE, st);
     STAGE_CHECK();
     prof_mark(6, st);
     return cudaSuccess;

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) k_tile_sort_smem(Workspace ws, uint32_t* 
     __shared__ uint32_t totals[256];
     __shared__ uint32_t wsum[8];
     __shared__ unsigned long long vary_s;
-    const int tile = blockIdx.x;
+    const int tile = (int)ws.tile_order[blockIdx.x];
     const uint32_t cap = ws.hdr->cap;
     uint32_t sbeg = ws.tile_offset[tile], send = ws.tile_offset[tile + 1];
     if (out_ranges && threadIdx.x == 0) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_tile_sort_global(Workspace ws, uint32_t
     __shared__ uint32_t totals[256];
     __shared__ uint32_t wsum[8];
     __shared__ unsigned long long vary_s;
-    const int tile = blockIdx.x;
+    const int tile = (int)ws.tile_order[blockIdx.x];
     const uint32_t cap = ws.hdr->cap;
     uint32_t sbeg = ws.tile_offset[tile], send = ws.tile_offset[tile + 1];
     sbeg = min(sbeg, cap);

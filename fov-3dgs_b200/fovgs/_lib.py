@@ -135,6 +135,8 @@ EXPORTS = (
     "fovgs_fov_geometry",
     "fovgs_profile_enable",
     "fovgs_profile_read",
+    "fovgs_profile_count",
+    "fovgs_profile_read_frame",
     "fovgs_last_error",
     "fovgs_version",
 )
@@ -169,6 +171,9 @@ def lib():
     L.fovgs_profile_enable.restype = C.c_int
     L.fovgs_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int32]
     L.fovgs_profile_read.restype = C.c_int
+    L.fovgs_profile_count.restype = C.c_int
+    L.fovgs_profile_read_frame.argtypes = [C.c_int32, C.POINTER(C.c_float), C.c_int32]
+    L.fovgs_profile_read_frame.restype = C.c_int
     for fn in ("fovgs_forward_fov", "fovgs_forward_ps1", "fovgs_backward_ps1", "fovgs_mark_visible",
                "fovgs_read_stats_async", "fovgs_fov_tile_tables", "fovgs_ps1_geometry", "fovgs_fov_geometry"):
         getattr(L, fn).restype = C.c_int

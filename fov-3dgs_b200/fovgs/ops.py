@@ -24,6 +24,24 @@ MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
 _DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
 
 
+def set_deferred_check(on):
+    """Pipelined mode for the inference paths: skip the per-frame host read of the frame statistics; the previous
+    frame's overflow flag is checked at the next call (and by `check_pending()`)."""
+    global _DEFERRED
+    _DEFERRED = bool(on)
+
+
+def check_pending(device=None):
+    """Synchronise and validate every workspace whose statistics were not yet inspected (deferred mode)."""
+    torch.cuda.synchronize(device)
+    for item in _pool.items.values():
+        if item["pending"]:
+            st = _stats_dict(item)
+            item["pending"] = False
+            if st["overflow"]:
+                raise RuntimeError(f"fovgs: a deferred frame overflowed its instance capacity ({st['num_rendered']} > {item['cap']})")
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -422,3 +440,13 @@ def profile_read():
     buf = (C.c_float * 6)()
     check(lib().fovgs_profile_read(buf, 6), "fovgs_profile_read")
     return dict(zip(STAGE_NAMES, [float(x) for x in buf]))
+
+
+def profile_read_all():
+    """Stage durations (ms) of every profiled frame still held (<= 256, oldest first): list of dicts."""
+    out = []
+    buf = (C.c_float * 6)()
+    for k in range(lib().fovgs_profile_count()):
+        check(lib().fovgs_profile_read_frame(k, buf, 6), "fovgs_profile_read_frame")
+        out.append(dict(zip(STAGE_NAMES, [float(x) for x in buf])))
+    return out
