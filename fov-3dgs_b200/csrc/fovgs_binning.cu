@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
-        for (int b = 32; b >= 0; b--) { bucket_base[b] = run; run += bucket_cnt[b]; }
+        for (int b = 32; b >= 0; b--) { bucket_base[b] = run; run += bucket_cnt[b]; ws.hdr->cum_class[b] = run; }
+        ws.hdr->cum_class[33] = 0;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < T; i += 1024) {

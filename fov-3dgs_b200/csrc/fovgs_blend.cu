@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
     const size_t HW = (size_t)H * W;
     const uint32_t* __restrict__ plist = ws.point_list + rbeg;
+    int batches_done = 0;   // statistics: how much of the sorted list the tile actually consumed
 
     if (MODE == MODE_FOV) {
         const bool blending = ws.tile_blend[tile] != 0;
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             for (int i = 0; i < rounds; i++, toDo -= 256) {
                 if (__syncthreads_count(done) == 256) break;
                 if (pf.valid) { sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2]; }
+                batches_done = i + 1;
                 __syncthreads();
                 if (i + 1 < rounds) fetch((i + 1) * 256 + tid);
                 const int lim = min(256, toDo);
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                 in.out_color[HW + pix_id] = FF(bg1, T, C1);
                 in.out_color[2 * HW + pix_id] = FF(bg2, T, C2);
             }
+            if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
         } else {
             const int L2 = L1 + 1;
             const float L2_f = FA(tile_level_f, 1.0f);
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             for (int i = 0; i < rounds; i++, toDo -= 256) {
                 if (__syncthreads_count(done) == 256) break;
                 if (pf.valid) { sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2]; sD[tid] = pf.r[3]; }
+                batches_done = i + 1;
                 __syncthreads();
                 if (i + 1 < rounds) fetch((i + 1) * 256 + tid);
                 const int lim = min(256, toDo);
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                 in.out_color[HW + pix_id] = FF(A1, w1, FM(B1, w2));
                 in.out_color[2 * HW + pix_id] = FF(A2, w1, FM(B2, w2));
             }
+            if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
         }
         return;
     }
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                 atomicAdd(&in.gaussians_count[pf.id], 1);   // counted when the batch is staged, as in the reference
             }
         }
+        batches_done = i + 1;
         __syncthreads();
         if (i + 1 < rounds) fetch((i + 1) * 256 + tid);
         const int lim = min(256, toDo);
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             last_contributor = contributor;
         }
     }
+    if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
     if (inside) {
         if (MODE == MODE_SUM) {
             ws.final_T[pix_id] = T;
