@@ -305,6 +305,7 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
 
 // ---- optional stage timing (bench.py roofline): CUDA events between the stages of a frame ----
 StageProfile g_prof;
+bool g_force_full_sort = false;   // fovgs_set_option(FOVGS_OPT_FULL_SORT, 1): always run the complete per-tile sort
 static inline void prof_mark(int i, cudaStream_t st) {
     if (!g_prof.enabled) return;
     if (!g_prof.created) {
@@ -370,11 +371,17 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     prof_mark(3, st);
     launch_scatter(ws, num_sms, st);
     STAGE_CHECK();
+    // Inference variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the
+    // sorted lists; the training variant always needs complete lists (backward, batch-granular gaussians_count).
+    const bool lazy = (MODE != MODE_SUM) && in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
     prof_mark(4, st);
-    launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);
-    STAGE_CHECK();
+    if (!lazy) {
+        launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);
+        STAGE_CHECK();
+    }
     prof_mark(5, st);
-    launch_blend(ws, in, T, (Mode)MODE, st);
+    if (lazy) launch_lazy_blend(ws, in, T, (Mode)MODE, st);
+    else launch_blend(ws, in, T, (Mode)MODE, st);
     STAGE_CHECK();
     prof_mark(6, st);
     return cudaSuccess;

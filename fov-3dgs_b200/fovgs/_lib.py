@@ -133,6 +133,7 @@ EXPORTS = (
     "fovgs_fov_tile_tables",
     "fovgs_ps1_geometry",
     "fovgs_fov_geometry",
+    "fovgs_set_option",
     "fovgs_profile_enable",
     "fovgs_profile_read",
     "fovgs_profile_count",
@@ -167,6 +168,8 @@ def lib():
     L.fovgs_fov_tile_tables.argtypes = [_f, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_ps1_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_fov_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_set_option.argtypes = [C.c_int32, C.c_int32]
+    L.fovgs_set_option.restype = C.c_int
     L.fovgs_profile_enable.argtypes = [C.c_int32]
     L.fovgs_profile_enable.restype = C.c_int
     L.fovgs_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int32]

@@ -24,6 +24,11 @@ MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
 _DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
 
 
+def set_full_sort(on):
+    """Force the complete per-tile depth sort in the inference variants (default: lazy, consumption-driven)."""
+    check(lib().fovgs_set_option(1, 1 if on else 0), "fovgs_set_option")
+
+
 def set_deferred_check(on):
     """Pipelined mode for the inference paths: skip the per-frame host read of the frame statistics; the previous
     frame's overflow flag is checked at the next call (and by `check_pending()`)."""

@@ -206,6 +206,36 @@ def test_equal_depth_ties_are_ordered_by_id():
     assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
 
 
+def test_lazy_sort_blend_equals_full_sort_blend():
+    """The consumption-driven (lazy) path and the full-sort path must produce bit-identical images, including the
+    oversize-bucket fallback (thousands of instances per tile with identical depth bits) and multi-bucket tiles."""
+    import oracle
+    # (a) dense fronto-parallel slab: every tile holds > 2048 instances with equal depth
+    s = synth.make_scene_cube(30000, 4)
+    s["means3D"][:, 2] = 0.5
+    s["scales"][:] *= 3.0
+    c = synth.look_at_camera(64, 64, 50.0, (0.0, 0.0, -3.0))
+    (n, col_full, radii, item, pl, rg), _, _ = _run_ps1(ops.MODE_OBB, s, c, want_lists=True)
+    assert int(ops.last_stats["max_tile_instances"]) > 2048
+    (n2, col_lazy, radii2, item2), _, _ = _run_ps1(ops.MODE_OBB, s, c, want_lists=False)
+    assert n2 == n and torch.equal(col_full, col_lazy)
+    o = oracle.forward_ps1(s, c, "obb")
+    assert np.abs(col_lazy.cpu().numpy() - o["color"]).max() <= IMG_TOL
+    # (b) deep scene, many depth buckets per tile, foveated + blending tiles
+    f = synth.add_foveation(synth.make_scene_bicycle(400000, 2, log_scale_mu=-3.2))
+    cam = synth.ring_cameras(30, 640, 360)[5]
+    (nf, col_f, _, _, _, _), _, _ = _run_fov(f, cam, (0.5, 0.5), want_lists=True)
+    assert int(ops.last_stats["max_tile_instances"]) > 2048
+    (nl, col_l, _), _, _ = _run_fov(f, cam, (0.5, 0.5), want_lists=False)
+    assert nl == nf and torch.equal(col_f, col_l)
+    ops.set_full_sort(True)
+    try:
+        (nl2, col_l2, _), _, _ = _run_fov(f, cam, (0.5, 0.5), want_lists=False)
+    finally:
+        ops.set_full_sort(False)
+    assert torch.equal(col_f, col_l2)
+
+
 def test_capacity_overflow_regrows(monkeypatch):
     monkeypatch.setenv("FOVGS_INSTANCE_CAPACITY", "1000")
     ops._pool.clear()

@@ -120,6 +120,9 @@ def run_fov(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
             ours = {"n": n_o, "color": col_o, "radii": rad_o, "point_list": pl_o, "ranges": rg_o}
             compare_common(rep, ref, ours, gr, go, W, H)
             rep["stats"] = dict(ops.last_stats)
+            _, col_l, rad_l = ops.forward_fov(sc["means3D"], sc["opacities4"], sc["scales"], sc["rotations"], sc["shs_rest"], sc["shs_dcs"],
+                                              sc["highest_levels"], gaze, 0.05, True, rs)
+            rep["lazy_img_max_abs"] = float((col_l - col_r).abs().max().item()); rep["lazy_stats"] = dict(ops.last_stats)
             if golden_dir and gi < 2:
                 lvl, mn, gx, gy, bl = ops.fov_tile_tables(item, W, H)
                 np.savez_compressed(os.path.join(golden_dir, f"fov_{tag}_g{gi}.npz"), gaze=np.array(g, np.float32),
@@ -162,6 +165,9 @@ def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
         go = ops.geometry(item, mode, P, W, H)
         ours = {"n": n_o, "color": col_o, "radii": rad_o, "point_list": pl_o, "ranges": rg_o}
         compare_common(rep, ref, ours, gr, go, W, H)
+        if not sum_mode:
+            lz = ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs)
+            rep["lazy_img_max_abs"] = float((lz[1] - col_r).abs().max().item()); rep["lazy_stats"] = dict(ops.last_stats)
         vis = (rad_r > 0)
         rep["rgb_max_abs"] = float(((gr["rgb"] - go["rgb"]).abs() * vis.unsqueeze(-1)).max().item())
         if sum_mode:
