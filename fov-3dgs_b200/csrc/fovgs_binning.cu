@@ -105,24 +105,29 @@ __device__ __forceinline__ bool project_splat_cov(const CamParams& cam, float mx
     return true;
 }
 
-constexpr int PB = 256;  // Gaussians per batch == threads per block
+constexpr int PB = 256;            // threads per block
+constexpr int WPB = PB / 32;       // warps per block; every warp is an autonomous worker (no block barriers)
+constexpr uint32_t WCHUNK = 512;   // staging slots a warp reserves per global atomic
+constexpr int SHG = 8;             // visible Gaussians whose SH inputs are staged per cooperative round
+constexpr int SHW = 65;            // floats per staged Gaussian (64 + 1 pad: conflict-free lane-strided reads)
+
+struct WarpSmem {
+    float px[32], py[32], e1x[32], e1y[32], e2x[32], e2y[32], l1[32], l2[32], hl1[32], rw[32];
+    uint32_t dbits[32];
+    int x0[32], y0[32], w[32];
+    uint32_t pref[33];
+    uint32_t nzlist[32];         // lane of the k-th Gaussian with a non-empty candidate rectangle
+    uint32_t cnt[32];
+    int lo[32], hi[32];          // FOV: float bits of the (non-negative) lowest / highest level used
+    uint32_t bl[32];             // FOV: any kept tile is a blending tile
+    uint32_t single[32];         // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
+    float shbuf[SHG][SHW];       // cooperative staging of SH / dc / opacity inputs
+};
 
 struct PreSmem {
     CamParams cam;
-    float px[PB], py[PB], e1x[PB], e1y[PB], e2x[PB], e2y[PB], l1[PB], l2[PB], hl1[PB];
-    uint32_t dbits[PB];
-    int x0[PB], y0[PB], w[PB];
-    float rw[PB];                // 1 / w (candidate index -> (row, col) without an integer division)
-    uint8_t single[PB];          // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
     int bbox[FOV_LEVELS][4];
-    uint32_t pref[PB + 1];
-    uint32_t cnt[PB];
-    int lo[PB], hi[PB];          // FOV: float bits of the (non-negative) lowest / highest level used
-    uint32_t bl[PB];             // FOV: any kept tile is a blending tile
-    uint32_t wtot[8];
-    uint32_t round_base;
-    uint32_t chunk_base, chunk_used, has_chunk;
-    uint32_t inval_beg, inval_end;
+    WarpSmem w[WPB];
 };
 
 template <int MODE>
@@ -134,18 +139,24 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
         const uint32_t* src = (const uint32_t*)&ws.hdr->cam;
         uint32_t* dst = (uint32_t*)&sm.cam;
         for (int i = tid; i < n; i += PB) dst[i] = src[i];
-        if (tid == 0) { sm.chunk_base = 0; sm.chunk_used = STAGE_CHUNK; sm.has_chunk = 0; }
         if (MODE == MODE_FOV && tid < FOV_LEVELS * 4) (&sm.bbox[0][0])[tid] = (&ws.hdr->lvl_bbox[0][0])[tid];
     }
-    __syncthreads();
+    __syncthreads();   // the only block barrier: from here on warps never wait for each other
     const CamParams& cam = sm.cam;
+    WarpSmem& wm = sm.w[warp];
     const int gx = cam.grid_x;
     const uint32_t stage_cap = ws.stage_cap;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned le_mask = lt_mask | (1u << lane);
+    // staging chunk of this warp (identical in all lanes)
+    uint32_t chunk_base = 0, chunk_used = WCHUNK;
+    bool has_chunk = false;
     unsigned visible_total = 0;
 
-    for (int base = blockIdx.x * PB; base < in.P; base += gridDim.x * PB) {
-        const int idx = base + tid;
-        // ---------------- phase A: projection (thread = Gaussian) ----------------
+    const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
+    for (int base = gwarp * 32; base < in.P; base += nwarps * 32) {
+        const int idx = base + lane;
+        // ---------------- phase A: projection (lane = Gaussian) ----------------
         Splat s;
         float c3[6];
         bool ok = false;
@@ -177,69 +188,63 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
             }
             const int cw = max(cx1 - cx0, 0), ch = max(cy1 - cy0, 0);
             tnum = (uint32_t)cw * (uint32_t)ch;
-            sm.single[tid] = single0;
-            sm.px[tid] = s.px; sm.py[tid] = s.py;
-            sm.e1x[tid] = s.e1x; sm.e1y[tid] = s.e1y; sm.e2x[tid] = s.e2x; sm.e2y[tid] = s.e2y;
-            sm.l1[tid] = s.len1; sm.l2[tid] = s.len2;
-            sm.dbits[tid] = __float_as_uint(s.depth);
-            sm.x0[tid] = cx0; sm.y0[tid] = cy0; sm.w[tid] = cw; sm.rw[tid] = 1.0f / (float)max(cw, 1);
+            wm.single[lane] = single0;
+            wm.px[lane] = s.px; wm.py[lane] = s.py;
+            wm.e1x[lane] = s.e1x; wm.e1y[lane] = s.e1y; wm.e2x[lane] = s.e2x; wm.e2y[lane] = s.e2y;
+            wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
+            wm.dbits[lane] = __float_as_uint(s.depth);
+            wm.x0[lane] = cx0; wm.y0[lane] = cy0; wm.w[lane] = cw; wm.rw[lane] = 1.0f / (float)max(cw, 1);
             if (MODE == MODE_FOV) {
-                sm.hl1[tid] = FA(hl, 1.0f);
-                sm.lo[tid] = __float_as_int(fmaxf(hl, 0.0f));
-                sm.hi[tid] = 0;
-                sm.bl[tid] = 0;
+                wm.hl1[lane] = FA(hl, 1.0f);
+                wm.lo[lane] = __float_as_int(fmaxf(hl, 0.0f));
+                wm.hi[lane] = 0;
+                wm.bl[lane] = 0;
             }
         }
-        sm.cnt[tid] = 0;
-        // exclusive scan of tnum over the block
-        {
-            uint32_t x = tnum;
+        wm.cnt[lane] = 0;
+        // exclusive scan of the candidate counts over the warp; compact list of non-empty owners
+        uint32_t incl = tnum;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) sm.wtot[warp] = x;
-            __syncthreads();
-            uint32_t wbase = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) if (w < warp) wbase += sm.wtot[w];
-            sm.pref[tid] = wbase + x - tnum;
-            if (tid == PB - 1) sm.pref[PB] = wbase + x;
-        }
-        __syncthreads();
-        const uint32_t total = sm.pref[PB];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const uint32_t my_start = incl - tnum;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned nz = __ballot_sync(0xffffffffu, tnum > 0);
+        wm.pref[lane] = my_start;
+        if (lane == 31) wm.pref[32] = total;
+        if (tnum > 0) wm.nzlist[__popc(nz & lt_mask)] = (uint32_t)lane;
+        __syncwarp();
 
-        // ---------------- phase B: candidate tiles (thread = candidate) ----------------
-        for (uint32_t r = 0; r < total; r += PB) {
-            const uint32_t c = r + tid;
+        // ---------------- phase B: candidate tiles (lane = candidate), 32 per round ----------------
+        uint32_t owners_before = 0;   // non-empty owners whose range starts before the current window
+        for (uint32_t r = 0; r < total; r += 32) {
+            const uint32_t c = r + lane;
             const bool valid = c < total;
-            bool pass = false, single = false;
-            uint32_t tile = 0, owner = 0xffffu;
+            // heads: window positions at which a non-empty owner's range starts
+            const unsigned hbit = (tnum > 0 && my_start >= r && my_start < r + 32) ? (1u << (my_start - r)) : 0u;
+            const unsigned H = __reduce_or_sync(0xffffffffu, hbit);
+            bool pass = false, single = false, tblend = false;
+            uint32_t tile = 0, owner = 0;
             float level = 0.0f;
-            bool tblend = false;
             if (valid) {
-                int lo_i = 0, hi_i = PB;
-                while (hi_i - lo_i > 1) {
-                    const int mid = (lo_i + hi_i) >> 1;
-                    if (sm.pref[mid] <= c) lo_i = mid; else hi_i = mid;
-                }
-                owner = (uint32_t)lo_i;
-                const int t = (int)(c - sm.pref[owner]);
-                const int w = sm.w[owner];
-                int q = (int)(((float)t + 0.5f) * sm.rw[owner]);
+                owner = wm.nzlist[owners_before + __popc(H & le_mask) - 1];
+                const int t = (int)(c - wm.pref[owner]);
+                const int w = wm.w[owner];
+                int q = (int)(((float)t + 0.5f) * wm.rw[owner]);
                 int rem = t - q * w;
                 if (rem < 0) { q--; rem += w; } else if (rem >= w) { q++; rem -= w; }
-                const int ty = sm.y0[owner] + q;
-                const int tx = sm.x0[owner] + rem;
+                const int ty = wm.y0[owner] + q;
+                const int tx = wm.x0[owner] + rem;
                 tile = (uint32_t)ty * gx + tx;
-                single = sm.single[owner] != 0;
+                single = wm.single[owner] != 0;
                 pass = true;
                 if (MODE == MODE_FOV) {
                     level = ws.tile_min[tile];
-                    pass = level < sm.hl1[owner];
+                    pass = level < wm.hl1[owner];
                 }
                 if (pass && !single) {
-                    const float cx = sm.px[owner], cy = sm.py[owner];
-                    const float e1x = sm.e1x[owner], e1y = sm.e1y[owner], e2x = sm.e2x[owner], e2y = sm.e2y[owner];
-                    const float l1 = sm.l1[owner], l2 = sm.l2[owner];
+                    const float cx = wm.px[owner], cy = wm.py[owner];
+                    const float e1x = wm.e1x[owner], e1y = wm.e1y[owner], e2x = wm.e2x[owner], e2y = wm.e2y[owner];
+                    const float l1 = wm.l1[owner], l2 = wm.l2[owner];
                     ObbCorners oc;
                     obb_corners(cx, cy, e1x, e1y, e2x, e2y, l1, l2, oc);
                     const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
@@ -250,10 +255,21 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
                     if (MODE == MODE_FOV) tblend = ws.tile_blend[tile] != 0;
                 }
             }
-            // per-owner bookkeeping, aggregated over the lanes that share an owner
-            const unsigned seg = __match_any_sync(0xffffffffu, owner);
+            // per-owner bookkeeping over the lanes that share an owner: segments are delimited by the heads
+            const unsigned validmask = __ballot_sync(0xffffffffu, valid);
             const unsigned passmask = __ballot_sync(0xffffffffu, pass);
-            const bool head = valid && ((seg & ((1u << lane) - 1u)) == 0u);
+            unsigned seg;
+            bool head;
+            {
+                const unsigned Hx = H | 1u;                                   // position 0 continues the carried-over owner
+                const int start = 31 - __clz(Hx & le_mask);
+                const unsigned above = (lane == 31) ? 0u : (Hx >> (lane + 1));
+                const int end = above ? (lane + 1 + (__ffs(above) - 1)) : 32;
+                const unsigned upto_end = (end == 32) ? 0xffffffffu : ((1u << end) - 1u);
+                seg = upto_end & ~((1u << start) - 1u) & validmask;
+                head = valid && (lane == start);
+                if (!valid) seg = ~validmask;                                 // idle lanes form their own group
+            }
             const unsigned npass_seg = __popc(passmask & seg);
             if (MODE == MODE_FOV) {
                 const unsigned blendmask = __ballot_sync(0xffffffffu, pass && tblend);
@@ -263,87 +279,110 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
                 const int hi_seg = __reduce_max_sync(seg, hb);
                 if (head && npass_seg) {
                     if (single) {   // reference assigns (not min/max) on the single-tile path: rasterizer_impl.cu:309-312
-                        sm.lo[owner] = lo_seg;
-                        sm.hi[owner] = hi_seg;
+                        wm.lo[owner] = lo_seg;
+                        wm.hi[owner] = hi_seg;
                     } else {
-                        atomicMin(&sm.lo[owner], lo_seg);
-                        atomicMax(&sm.hi[owner], hi_seg);
+                        wm.lo[owner] = min(wm.lo[owner], lo_seg);
+                        wm.hi[owner] = max(wm.hi[owner], hi_seg);
                     }
-                    if (blendmask & seg) atomicOr(&sm.bl[owner], 1u);
+                    if (blendmask & seg) wm.bl[owner] = 1u;
                 }
             }
-            if (head && npass_seg) atomicAdd(&sm.cnt[owner], npass_seg);
-            // stage the surviving instances densely
-            const unsigned wrank = __popc(passmask & ((1u << lane) - 1u));
-            if (lane == 0) sm.wtot[warp] = __popc(passmask);
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t np = 0;
-#pragma unroll
-                for (int w = 0; w < 8; w++) { const uint32_t t = sm.wtot[w]; sm.wtot[w] = np; np += t; }
-                sm.inval_beg = sm.inval_end = 0;
-                if (np) {
-                    if (sm.chunk_used + np > STAGE_CHUNK) {
-                        if (sm.has_chunk) { sm.inval_beg = sm.chunk_base + sm.chunk_used; sm.inval_end = sm.chunk_base + STAGE_CHUNK; }
-                        sm.chunk_base = atomicAdd(&ws.hdr->stage_cursor, STAGE_CHUNK);
-                        sm.chunk_used = 0;
-                        sm.has_chunk = 1;
+            if (head && npass_seg) wm.cnt[owner] += npass_seg;   // one head per owner per round: no atomics needed
+            // stage the surviving instances densely in this warp's chunk
+            const uint32_t np = __popc(passmask);
+            if (np) {
+                if (chunk_used + np > WCHUNK) {
+                    if (has_chunk) {
+                        const uint32_t p = chunk_base + chunk_used + lane;    // < 32 slots are left
+                        if (p < chunk_base + WCHUNK && p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
                     }
-                    sm.round_base = sm.chunk_base + sm.chunk_used;
-                    sm.chunk_used += np;
+                    uint32_t nb = 0;
+                    if (lane == 0) nb = atomicAdd(&ws.hdr->stage_cursor, WCHUNK);
+                    chunk_base = __shfl_sync(0xffffffffu, nb, 0);
+                    chunk_used = 0;
+                    has_chunk = true;
                 }
-            }
-            __syncthreads();
-            {
-                const uint32_t ib = sm.inval_beg, ie = sm.inval_end;
-                for (uint32_t p = ib + tid; p < ie; p += PB)
-                    if (p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
-            }
-            if (pass) {
-                const uint32_t pos = sm.round_base + sm.wtot[warp] + wrank;
-                if (pos < stage_cap) {
-                    ws.stage_tile[pos] = tile;
-                    ws.stage_key[pos] = ((uint64_t)sm.dbits[owner] << 32) | (uint32_t)(base + (int)owner);
+                if (pass) {
+                    const uint32_t pos = chunk_base + chunk_used + __popc(passmask & lt_mask);
+                    if (pos < stage_cap) {
+                        ws.stage_tile[pos] = tile;
+                        ws.stage_key[pos] = ((uint64_t)wm.dbits[owner] << 32) | (uint32_t)(base + (int)owner);
+                    }
                 }
+                chunk_used += np;
             }
-            __syncthreads();   // wtot / round_base are rewritten next round
+            owners_before += __popc(H);
+            __syncwarp();
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---------------- phase C: per-Gaussian outputs + colour (thread = Gaussian) ----------------
-        bool visible = false;
-        if (idx < in.P) {
-            const uint32_t count = ok ? sm.cnt[tid] : 0u;
-            in.radii[idx] = count ? s.radius : 0;
-            if (count) {
-                visible = true;
-                const int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
-                float4* rec = ws.rec + (size_t)R * idx;
-                rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
-                const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
-                float dx = mx - cam.campos[0], dy = my - cam.campos[1], dz = mz - cam.campos[2];
-                const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-                dx = dx / len; dy = dy / len; dz = dz / len;
+        // ---------------- phase C: per-Gaussian outputs + colour ----------------
+        const uint32_t count = ok ? wm.cnt[lane] : 0u;
+        const bool visible = (idx < in.P) && count > 0;
+        if (idx < in.P) in.radii[idx] = count ? s.radius : 0;
+        const unsigned vismask = __ballot_sync(0xffffffffu, visible);
+        visible_total += __popc(vismask);
+        constexpr int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
+        float4* rec = ws.rec + (size_t)R * (idx < in.P ? idx : 0);
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (visible) {
+            rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
+            const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
+            dx = mx - cam.campos[0]; dy = my - cam.campos[1]; dz = mz - cam.campos[2];
+            const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+            dx = dx / len; dy = dy / len; dz = dz / len;
+            if (MODE == MODE_SUM) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
+            }
+        }
+        // SH / dc / opacity inputs of the visible Gaussians are copied with coalesced warp-wide loads into shared
+        // memory, SHG Gaussians per round; each visible lane then evaluates its own colour from its slot.
+        const int nsh = (MODE == MODE_FOV) ? 3 * cam.M : ((in.colors_precomp != nullptr) ? 0 : 3 * cam.M);   // floats of SH per Gaussian
+        unsigned todo = vismask;
+        while (todo) {
+            unsigned grp = 0;
+            int g = 0;
+            unsigned rest = todo;
+            while (rest && g < SHG) {
+                const int v = __ffs(rest) - 1;
+                rest &= rest - 1;
+                grp |= 1u << v;
+                float* buf = wm.shbuf[g];
+                const size_t gid = (size_t)(base + v);
+                if (in.shs != nullptr) {
+                    const float* src = in.shs + gid * (size_t)nsh;
+                    for (int k = lane; k < nsh; k += 32) buf[k] = src[k];
+                }
+                if (MODE == MODE_FOV) {
+                    if (lane < 12) buf[48 + lane] = in.shs_dcs[gid * 12 + lane];
+                    else if (lane < 16) buf[48 + lane] = in.opacities[gid * 4 + (lane - 12)];
+                }
+                g++;
+            }
+            todo = rest;
+            __syncwarp();
+            if (grp & (1u << lane)) {
+                const float* buf = wm.shbuf[__popc(grp & lt_mask)];
                 if (MODE == MODE_FOV) {
                     rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
-                    float3 rest = make_float3(0.f, 0.f, 0.f);
-                    if (in.shs != nullptr && cam.M > 0)
-                        rest = sh_accumulate(in.shs + (size_t)3 * cam.M * idx, 0, cam.sh_degree, dx, dy, dz, rest);
-                    rest.x += 0.5f; rest.y += 0.5f; rest.z += 0.5f;
-                    const int l0 = (int)__int_as_float(sm.lo[tid]);
-                    int l1 = (int)__int_as_float(sm.hi[tid]);
-                    if (sm.bl[tid]) l1 = min(l1 + 1, FOV_LEVELS - 1);
+                    float3 rs = make_float3(0.f, 0.f, 0.f);
+                    if (in.shs != nullptr && cam.M > 0) rs = sh_accumulate(buf, 0, cam.sh_degree, dx, dy, dz, rs);
+                    rs.x += 0.5f; rs.y += 0.5f; rs.z += 0.5f;
+                    const int l0 = (int)__int_as_float(wm.lo[lane]);
+                    int l1 = (int)__int_as_float(wm.hi[lane]);
+                    if (wm.bl[lane]) l1 = min(l1 + 1, FOV_LEVELS - 1);
                     // levels outside [l0,l1] are never composited (the reference leaves them uninitialised, Q4);
                     // they are zeroed so that the blending kernel's unconditional L2 load stays finite.
 #pragma unroll
                     for (int l = 0; l < FOV_LEVELS; l++) {
                         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (l >= l0 && l <= l1) {
-                            const float* dc = in.shs_dcs + (size_t)idx * 3 * FOV_LEVELS + l * 3;
-                            o.x = in.opacities[(size_t)idx * FOV_LEVELS + l];
-                            o.y = fmaxf(SH_C0 * dc[0] + rest.x, 0.0f);
-                            o.z = fmaxf(SH_C0 * dc[1] + rest.y, 0.0f);
-                            o.w = fmaxf(SH_C0 * dc[2] + rest.z, 0.0f);
+                            o.x = buf[60 + l];
+                            o.y = fmaxf(SH_C0 * buf[48 + 3 * l + 0] + rs.x, 0.0f);
+                            o.z = fmaxf(SH_C0 * buf[48 + 3 * l + 1] + rs.y, 0.0f);
+                            o.w = fmaxf(SH_C0 * buf[48 + 3 * l + 2] + rs.z, 0.0f);
                         }
                         rec[2 + l] = o;
                     }
@@ -353,29 +392,22 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
                     if (in.colors_precomp != nullptr) {
                         c = make_float3(in.colors_precomp[3 * (size_t)idx], in.colors_precomp[3 * (size_t)idx + 1], in.colors_precomp[3 * (size_t)idx + 2]);
                     } else {
-                        const float* sh = in.shs + (size_t)3 * cam.M * idx;
-                        c = sh_accumulate(sh, 1, cam.sh_degree, dx, dy, dz, make_float3(SH_C0 * sh[0], SH_C0 * sh[1], SH_C0 * sh[2]));
+                        c = sh_accumulate(buf, 1, cam.sh_degree, dx, dy, dz, make_float3(SH_C0 * buf[0], SH_C0 * buf[1], SH_C0 * buf[2]));
                         c.x += 0.5f; c.y += 0.5f; c.z += 0.5f;
                         cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
                         c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
                     }
                     rec[1] = make_float4(s.conz, in.opacities[idx], c.x, c.y);
                     rec[2] = make_float4(c.z, s.depth, 0.f, 0.f);
-                    if (MODE == MODE_SUM) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
-                        reinterpret_cast<uchar4*>(ws.clamped)[idx] = make_uchar4(cl0, cl1, cl2, 0);
-                    }
+                    if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[idx] = make_uchar4(cl0, cl1, cl2, 0);
                 }
             }
+            __syncwarp();
         }
-        visible_total += __popc(__ballot_sync(0xffffffffu, visible));
-        __syncthreads();   // smem arrays are reused by the next batch
     }
     // retire the partially filled staging chunk
-    if (sm.has_chunk) {
-        const uint32_t ib = sm.chunk_base + sm.chunk_used, ie = sm.chunk_base + STAGE_CHUNK;
-        for (uint32_t p = ib + tid; p < ie; p += PB)
+    if (has_chunk) {
+        for (uint32_t p = chunk_base + chunk_used + lane; p < chunk_base + WCHUNK; p += 32)
             if (p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
     }
     if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
