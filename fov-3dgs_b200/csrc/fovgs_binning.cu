@@ -131,7 +131,7 @@ struct PreSmem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
+__global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
     __shared__ PreSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -342,24 +342,45 @@ __global__ void __launch_bounds__(PB) k_pre(Workspace ws, FrameInputs in) {
         const int nsh = (MODE == MODE_FOV) ? 3 * cam.M : ((in.colors_precomp != nullptr) ? 0 : 3 * cam.M);   // floats of SH per Gaussian
         unsigned todo = vismask;
         while (todo) {
+            // pick up to SHG visible lanes (warp-uniform), issue ALL their loads, then store: 2*SHG loads in flight per lane
             unsigned grp = 0;
-            int g = 0;
             unsigned rest = todo;
-            while (rest && g < SHG) {
-                const int v = __ffs(rest) - 1;
-                rest &= rest - 1;
-                grp |= 1u << v;
-                float* buf = wm.shbuf[g];
-                const size_t gid = (size_t)(base + v);
-                if (in.shs != nullptr) {
-                    const float* src = in.shs + gid * (size_t)nsh;
-                    for (int k = lane; k < nsh; k += 32) buf[k] = src[k];
+            int vs[SHG];
+            int ng = 0;
+#pragma unroll
+            for (int g = 0; g < SHG; g++) {
+                vs[g] = 0;
+                if (rest) {
+                    vs[g] = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    grp |= 1u << vs[g];
+                    ng = g + 1;
                 }
-                if (MODE == MODE_FOV) {
-                    if (lane < 12) buf[48 + lane] = in.shs_dcs[gid * 12 + lane];
-                    else if (lane < 16) buf[48 + lane] = in.opacities[gid * 4 + (lane - 12)];
+            }
+            float a0[SHG], a1[SHG];
+#pragma unroll
+            for (int g = 0; g < SHG; g++) {
+                a0[g] = 0.f; a1[g] = 0.f;
+                if (g < ng) {
+                    const size_t gid = (size_t)(base + vs[g]);
+                    if (in.shs != nullptr) {
+                        const float* src = in.shs + gid * (size_t)nsh;
+                        if (lane < nsh) a0[g] = src[lane];
+                        if (32 + lane < nsh) a1[g] = src[32 + lane];
+                    }
+                    if (MODE == MODE_FOV) {
+                        // second half of the 64-float slot: [32,45) SH rest, [48,60) the 4 dc triplets, [60,64) the 4 opacities
+                        if (lane >= 16 && lane < 28) a1[g] = in.shs_dcs[gid * 12 + (lane - 16)];
+                        else if (lane >= 28) a1[g] = in.opacities[gid * 4 + (lane - 28)];
+                    }
                 }
-                g++;
+            }
+#pragma unroll
+            for (int g = 0; g < SHG; g++) {
+                if (g < ng) {
+                    wm.shbuf[g][lane] = a0[g];
+                    wm.shbuf[g][32 + lane] = a1[g];
+                }
             }
             todo = rest;
             __syncwarp();
