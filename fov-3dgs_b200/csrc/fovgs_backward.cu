@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
                                                     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors) {
     __shared__ float4 sA[256];
     __shared__ float4 sB[256];
-    __shared__ float sCb[256];
+    __shared__ float4 sC[256];
     __shared__ int sId[256];
     __shared__ float acc[9][256];
     const FrameHeader* __restrict__ hdr = ws.hdr;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
             sId[tid] = (int)id;
             sA[tid] = rec[0];
             sB[tid] = rec[1];
-            sCb[tid] = rec[2].x;
+            sC[tid] = rec[2];
         }
 #pragma unroll
         for (int k = 0; k < 9; k++) acc[k][tid] = 0.0f;
@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
                             T = T / (1.f - alpha);
                             const float dchannel_dcolor = alpha * T;
                             float dL_dalpha = 0.0f;
-                            const float col[3] = {b.z, b.w, sCb[j]};
+                            const float4 cc = sC[j];
+                            const float col[3] = {cc.x, cc.y, cc.z};
 #pragma unroll
                             for (int ch = 0; ch < 3; ch++) {
                                 const float c = col[ch];

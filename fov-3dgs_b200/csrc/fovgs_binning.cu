@@ -108,8 +108,8 @@ __device__ __forceinline__ bool project_splat_cov(const CamParams& cam, float mx
 constexpr int PB = 256;            // threads per block
 constexpr int WPB = PB / 32;       // warps per block; every warp is an autonomous worker (no block barriers)
 constexpr uint32_t WCHUNK = 512;   // staging slots a warp reserves per global atomic
-constexpr int SHG = 8;             // visible Gaussians whose SH inputs are staged per cooperative round
-constexpr int SHW = 65;            // floats per staged Gaussian (64 + 1 pad: conflict-free lane-strided reads)
+constexpr uint32_t VCHUNK = 128;   // visible-list slots a warp reserves per global atomic
+constexpr int SHW = 65;            // k_color: floats per staged Gaussian (64 + 1 pad: conflict-free lane-strided reads)
 
 struct WarpSmem {
     float px[32], py[32], e1x[32], e1y[32], e2x[32], e2y[32], l1[32], l2[32], hl1[32], rw[32];
@@ -121,7 +121,6 @@ struct WarpSmem {
     int lo[32], hi[32];          // FOV: float bits of the (non-negative) lowest / highest level used
     uint32_t bl[32];             // FOV: any kept tile is a blending tile
     uint32_t single[32];         // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
-    float shbuf[SHG][SHW];       // cooperative staging of SH / dc / opacity inputs
 };
 
 struct PreSmem {
@@ -151,6 +150,8 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
     // staging chunk of this warp (identical in all lanes)
     uint32_t chunk_base = 0, chunk_used = WCHUNK;
     bool has_chunk = false;
+    uint32_t vbase = 0, vused = VCHUNK;   // this warp's chunk of the visible list
+    bool has_vchunk = false;
     unsigned visible_total = 0;
 
     const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
@@ -317,121 +318,169 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         }
         __syncwarp();
 
-        // ---------------- phase C: per-Gaussian outputs + colour ----------------
+        // ---------------- phase C: per-Gaussian outputs; colour work is queued for k_color ----------------
         const uint32_t count = ok ? wm.cnt[lane] : 0u;
         const bool visible = (idx < in.P) && count > 0;
         if (idx < in.P) in.radii[idx] = count ? s.radius : 0;
         const unsigned vismask = __ballot_sync(0xffffffffu, visible);
-        visible_total += __popc(vismask);
-        constexpr int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
-        float4* rec = ws.rec + (size_t)R * (idx < in.P ? idx : 0);
-        float dx = 0.f, dy = 0.f, dz = 0.f;
+        const uint32_t nv = __popc(vismask);
+        visible_total += nv;
+        uint32_t lv = 0;
         if (visible) {
+            constexpr int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
+            float4* rec = ws.rec + (size_t)R * idx;
             rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
-            const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
-            dx = mx - cam.campos[0]; dy = my - cam.campos[1]; dz = mz - cam.campos[2];
-            const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-            dx = dx / len; dy = dy / len; dz = dz / len;
-            if (MODE == MODE_SUM) {
+            if (MODE == MODE_FOV) {
+                rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
+                const int l0 = (int)__int_as_float(wm.lo[lane]);
+                int l1 = (int)__int_as_float(wm.hi[lane]);
+                if (wm.bl[lane]) l1 = min(l1 + 1, FOV_LEVELS - 1);
+                lv = (uint32_t)l0 | ((uint32_t)l1 << 8);
+            } else {
+                rec[1] = make_float4(s.conz, in.opacities[idx], s.depth, 0.0f);
+                if (MODE == MODE_SUM) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
-            }
-        }
-        // SH / dc / opacity inputs of the visible Gaussians are copied with coalesced warp-wide loads into shared
-        // memory, SHG Gaussians per round; each visible lane then evaluates its own colour from its slot.
-        const int nsh = (MODE == MODE_FOV) ? 3 * cam.M : ((in.colors_precomp != nullptr) ? 0 : 3 * cam.M);   // floats of SH per Gaussian
-        unsigned todo = vismask;
-        while (todo) {
-            // pick up to SHG visible lanes (warp-uniform), issue ALL their loads, then store: 2*SHG loads in flight per lane
-            unsigned grp = 0;
-            unsigned rest = todo;
-            int vs[SHG];
-            int ng = 0;
-#pragma unroll
-            for (int g = 0; g < SHG; g++) {
-                vs[g] = 0;
-                if (rest) {
-                    vs[g] = __ffs(rest) - 1;
-                    rest &= rest - 1;
-                    grp |= 1u << vs[g];
-                    ng = g + 1;
+                    for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
                 }
             }
-            float a0[SHG], a1[SHG];
+        }
+        if (nv) {
+            if (vused + nv > VCHUNK) {
+                if (has_vchunk) {
+                    const uint32_t p = vbase + vused + lane;              // < 32 slots are left
+                    if (p < vbase + VCHUNK && p < ws.vis_cap) ws.vis_list[p] = TILE_INVALID;
+                }
+                uint32_t nb = 0;
+                if (lane == 0) nb = atomicAdd(&ws.hdr->vis_cursor, VCHUNK);
+                vbase = __shfl_sync(0xffffffffu, nb, 0);
+                vused = 0;
+                has_vchunk = true;
+            }
+            if (visible) {
+                const uint32_t p = vbase + vused + __popc(vismask & lt_mask);
+                if (p < ws.vis_cap) { ws.vis_list[p] = (uint32_t)idx; ws.vis_lv[p] = lv; }
+            }
+            vused += nv;
+        }
+    }
+    // retire the partially filled staging / visible-list chunks
+    if (has_chunk) {
+        for (uint32_t p = chunk_base + chunk_used + lane; p < chunk_base + WCHUNK; p += 32)
+            if (p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
+    }
+    if (has_vchunk) {
+        for (uint32_t p = vbase + vused + lane; p < vbase + VCHUNK; p += 32)
+            if (p < ws.vis_cap) ws.vis_list[p] = TILE_INVALID;
+    }
+    if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_color: SH -> RGB for the visible Gaussians, fully packed.  k_pre queued the visible ids densely; here one warp takes
+// 32 of them, copies their SH / dc / opacity inputs with coalesced warp-wide loads into shared memory (8 Gaussians =
+// 16 loads in flight per lane), then every lane evaluates its own Gaussian from its slot with all 32 lanes busy.
+// Replaces compute_fov_colors (FOV/rasterizer_impl.cu:490-530), OBB's compute_fov_colors (:118-138) and the SH part of
+// SUM's preprocessCUDA (SUM/forward.cu:20-71, 282-288).  A thread-per-Gaussian SH read costs 61 L1 wavefronts per
+// Gaussian (one 4-byte element of 32 different lines per load); the cooperative copy needs 2-4.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CW = 4;   // warps per CTA in k_color
+
+template <int MODE>
+__global__ void __launch_bounds__(CW * 32) k_color(Workspace ws, FrameInputs in) {
+    __shared__ float shbuf[CW][32][SHW];
+    __shared__ float campos_s[3];
+    __shared__ int deg_s, M_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 3) campos_s[tid] = ws.hdr->cam.campos[tid];
+    if (tid == 0) { deg_s = ws.hdr->cam.sh_degree; M_s = ws.hdr->cam.M; }
+    __syncthreads();
+    const int deg = deg_s, M = M_s;
+    const int nsh = (in.shs != nullptr) ? 3 * M : 0;
+    const uint32_t nslots = min(ws.hdr->vis_cursor, ws.vis_cap);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float (*buf)[SHW] = shbuf[warp];
+    const uint32_t gw = blockIdx.x * CW + warp, nw = gridDim.x * CW;
+    for (uint32_t s0 = gw * 32; s0 < nslots; s0 += nw * 32) {
+        const uint32_t slot = s0 + lane;
+        uint32_t id = TILE_INVALID, lv = 0;
+        if (slot < nslots) { id = ws.vis_list[slot]; lv = ws.vis_lv[slot]; }
+        const bool valid = id != TILE_INVALID;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (vmask == 0) continue;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (valid) {
+            const float mx = in.means3D[3 * (size_t)id], my = in.means3D[3 * (size_t)id + 1], mz = in.means3D[3 * (size_t)id + 2];
+            dx = mx - campos_s[0]; dy = my - campos_s[1]; dz = mz - campos_s[2];
+            const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+            dx = dx / len; dy = dy / len; dz = dz / len;
+        }
+        // cooperative copy, 8 Gaussians per round; the id of Gaussian g is broadcast from lane g
+#pragma unroll 1
+        for (int g0 = 0; g0 < 32; g0 += 8) {
+            if (((vmask >> g0) & 0xffu) == 0) continue;
+            float a0[8], a1[8];
 #pragma unroll
-            for (int g = 0; g < SHG; g++) {
+            for (int g = 0; g < 8; g++) {
                 a0[g] = 0.f; a1[g] = 0.f;
-                if (g < ng) {
-                    const size_t gid = (size_t)(base + vs[g]);
-                    if (in.shs != nullptr) {
+                const uint32_t gid32 = __shfl_sync(0xffffffffu, id, g0 + g);
+                if (gid32 != TILE_INVALID) {
+                    const size_t gid = gid32;
+                    if (nsh) {
                         const float* src = in.shs + gid * (size_t)nsh;
                         if (lane < nsh) a0[g] = src[lane];
                         if (32 + lane < nsh) a1[g] = src[32 + lane];
                     }
                     if (MODE == MODE_FOV) {
-                        // second half of the 64-float slot: [32,45) SH rest, [48,60) the 4 dc triplets, [60,64) the 4 opacities
+                        // second half of the slot: [32,45) SH rest, [48,60) the 4 dc triplets, [60,64) the 4 opacities
                         if (lane >= 16 && lane < 28) a1[g] = in.shs_dcs[gid * 12 + (lane - 16)];
                         else if (lane >= 28) a1[g] = in.opacities[gid * 4 + (lane - 28)];
                     }
                 }
             }
 #pragma unroll
-            for (int g = 0; g < SHG; g++) {
-                if (g < ng) {
-                    wm.shbuf[g][lane] = a0[g];
-                    wm.shbuf[g][32 + lane] = a1[g];
-                }
-            }
-            todo = rest;
-            __syncwarp();
-            if (grp & (1u << lane)) {
-                const float* buf = wm.shbuf[__popc(grp & lt_mask)];
-                if (MODE == MODE_FOV) {
-                    rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
-                    float3 rs = make_float3(0.f, 0.f, 0.f);
-                    if (in.shs != nullptr && cam.M > 0) rs = sh_accumulate(buf, 0, cam.sh_degree, dx, dy, dz, rs);
-                    rs.x += 0.5f; rs.y += 0.5f; rs.z += 0.5f;
-                    const int l0 = (int)__int_as_float(wm.lo[lane]);
-                    int l1 = (int)__int_as_float(wm.hi[lane]);
-                    if (wm.bl[lane]) l1 = min(l1 + 1, FOV_LEVELS - 1);
-                    // levels outside [l0,l1] are never composited (the reference leaves them uninitialised, Q4);
-                    // they are zeroed so that the blending kernel's unconditional L2 load stays finite.
-#pragma unroll
-                    for (int l = 0; l < FOV_LEVELS; l++) {
-                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (l >= l0 && l <= l1) {
-                            o.x = buf[60 + l];
-                            o.y = fmaxf(SH_C0 * buf[48 + 3 * l + 0] + rs.x, 0.0f);
-                            o.z = fmaxf(SH_C0 * buf[48 + 3 * l + 1] + rs.y, 0.0f);
-                            o.w = fmaxf(SH_C0 * buf[48 + 3 * l + 2] + rs.z, 0.0f);
-                        }
-                        rec[2 + l] = o;
-                    }
-                } else {
-                    float3 c;
-                    bool cl0 = false, cl1 = false, cl2 = false;
-                    if (in.colors_precomp != nullptr) {
-                        c = make_float3(in.colors_precomp[3 * (size_t)idx], in.colors_precomp[3 * (size_t)idx + 1], in.colors_precomp[3 * (size_t)idx + 2]);
-                    } else {
-                        c = sh_accumulate(buf, 1, cam.sh_degree, dx, dy, dz, make_float3(SH_C0 * buf[0], SH_C0 * buf[1], SH_C0 * buf[2]));
-                        c.x += 0.5f; c.y += 0.5f; c.z += 0.5f;
-                        cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
-                        c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
-                    }
-                    rec[1] = make_float4(s.conz, in.opacities[idx], c.x, c.y);
-                    rec[2] = make_float4(c.z, s.depth, 0.f, 0.f);
-                    if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[idx] = make_uchar4(cl0, cl1, cl2, 0);
-                }
-            }
-            __syncwarp();
+            for (int g = 0; g < 8; g++) { buf[g0 + g][lane] = a0[g]; buf[g0 + g][32 + lane] = a1[g]; }
         }
+        __syncwarp();
+        if (valid) {
+            const float* b = buf[lane];
+            if (MODE == MODE_FOV) {
+                float4* rec = ws.rec + (size_t)REC_FOV * id;
+                float3 rs = make_float3(0.f, 0.f, 0.f);
+                if (nsh) rs = sh_accumulate(b, 0, deg, dx, dy, dz, rs);
+                rs.x += 0.5f; rs.y += 0.5f; rs.z += 0.5f;
+                const int l0 = (int)(lv & 0xff), l1 = (int)((lv >> 8) & 0xff);
+                // levels outside [l0,l1] are never composited (the reference leaves them uninitialised, Q4); they are
+                // zeroed so that the blending tiles' unconditional level-L2 load stays finite.
+#pragma unroll
+                for (int l = 0; l < FOV_LEVELS; l++) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (l >= l0 && l <= l1) {
+                        o.x = b[60 + l];
+                        o.y = fmaxf(SH_C0 * b[48 + 3 * l + 0] + rs.x, 0.0f);
+                        o.z = fmaxf(SH_C0 * b[48 + 3 * l + 1] + rs.y, 0.0f);
+                        o.w = fmaxf(SH_C0 * b[48 + 3 * l + 2] + rs.z, 0.0f);
+                    }
+                    rec[2 + l] = o;
+                }
+            } else {
+                float4* rec = ws.rec + (size_t)REC_PS1 * id;
+                float3 c;
+                bool cl0 = false, cl1 = false, cl2 = false;
+                if (in.colors_precomp != nullptr) {
+                    c = make_float3(in.colors_precomp[3 * (size_t)id], in.colors_precomp[3 * (size_t)id + 1], in.colors_precomp[3 * (size_t)id + 2]);
+                } else {
+                    c = sh_accumulate(b, 1, deg, dx, dy, dz, make_float3(SH_C0 * b[0], SH_C0 * b[1], SH_C0 * b[2]));
+                    c.x += 0.5f; c.y += 0.5f; c.z += 0.5f;
+                    cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
+                    c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
+                }
+                rec[2] = make_float4(c.x, c.y, c.z, 0.f);
+                if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[id] = make_uchar4(cl0, cl1, cl2, 0);
+            }
+        }
+        __syncwarp();
     }
-    // retire the partially filled staging chunk
-    if (has_chunk) {
-        for (uint32_t p = chunk_base + chunk_used + lane; p < chunk_base + WCHUNK; p += 32)
-            if (p < stage_cap) ws.stage_tile[p] = TILE_INVALID;
-    }
-    if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
+    (void)lt_mask;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -527,6 +576,16 @@ cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, in
         case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, 0, st>>>(ws, in); break;
         case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, 0, st>>>(ws, in); break;
         default: k_pre<MODE_FOV><<<grid, PB, 0, st>>>(ws, in); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
+    const int grid = num_sms * 6;
+    switch (mode) {
+        case MODE_OBB: k_color<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in); break;
+        case MODE_SUM: k_color<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in); break;
+        default: k_color<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();
 }

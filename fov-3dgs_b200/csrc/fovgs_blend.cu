@@ -29,8 +29,8 @@ struct Prefetch {
 template <int MODE>
 __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     __shared__ float4 sA[256];   // px, py, conx, cony
-    __shared__ float4 sB[256];   // conz, opacity | highest_level, (PS1: r, g)
-    __shared__ float4 sC[256];   // PS1: (b, ...) | FOV: level L1 (opacity, r, g, b)
+    __shared__ float4 sB[256];   // conz, opacity | highest_level, depth
+    __shared__ float4 sC[256];   // PS1: (r, g, b, -) | FOV: level L1 (opacity, r, g, b)
     __shared__ float4 sD[(MODE == MODE_FOV) ? 256 : 1];   // FOV blending tiles: level L2 (opacity, r, g, b)
     __shared__ int sId[(MODE == MODE_SUM) ? 256 : 1];
     const FrameHeader* __restrict__ hdr = ws.hdr;
@@ -217,13 +217,15 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             if (test_T < 0.0001f) { done = true; continue; }
             if (MODE == MODE_SUM) {
                 // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
+                const float4 c = sC[j];
                 atomicAdd(&in.contributions[sId[j]], FM(alpha, T));
-                C0 = FF(T, FM(alpha, b.z), C0);
-                C1 = FF(T, FM(alpha, b.w), C1);
-                C2 = FF(T, FM(alpha, sC[j].x), C2);
+                C0 = FF(T, FM(alpha, c.x), C0);
+                C1 = FF(T, FM(alpha, c.y), C1);
+                C2 = FF(T, FM(alpha, c.z), C2);
             } else {
+                const float4 c = sC[j];
                 const float w = FM(alpha, T);
-                C0 = FF(b.z, w, C0); C1 = FF(b.w, w, C1); C2 = FF(sC[j].x, w, C2);
+                C0 = FF(c.x, w, C0); C1 = FF(c.y, w, C1); C2 = FF(c.z, w, C2);
             }
             T = test_T;
             last_contributor = contributor;

@@ -211,6 +211,7 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->tiles = a.tiles;
             h->cap = a.cap;
             h->stage_cursor = 0;
+            h->vis_cursor = 0;
         }
         if (i < FOV_LEVELS * 4) (&h->lvl_bbox[0][0])[i] = ((i & 3) < 2) ? 0x7fffffff : -1;
     }
@@ -243,10 +244,10 @@ __global__ void k_export_geometry(Workspace ws, int P, int mode, const int* __re
     const float4* rec = ws.rec + (size_t)R * idx;
     const float4 r0 = rec[0], r1 = rec[1];
     if (means2D) { means2D[2 * idx] = r0.x; means2D[2 * idx + 1] = r0.y; }
-    if (depths) depths[idx] = (mode == MODE_FOV) ? r1.z : rec[2].y;
+    if (depths) depths[idx] = r1.z;
     if (conic) { conic[3 * idx] = r0.z; conic[3 * idx + 1] = r0.w; conic[3 * idx + 2] = r1.x; }
     if (cov3D && mode == MODE_SUM) for (int k = 0; k < 6; k++) cov3D[6 * idx + k] = ws.cov3D[6 * (size_t)idx + k];
-    if (rgb && mode != MODE_FOV) { rgb[3 * idx] = r1.z; rgb[3 * idx + 1] = r1.w; rgb[3 * idx + 2] = rec[2].x; }
+    if (rgb && mode != MODE_FOV) { const float4 c = rec[2]; rgb[3 * idx] = c.x; rgb[3 * idx + 1] = c.y; rgb[3 * idx + 2] = c.z; }
     if (level_colors && mode == MODE_FOV)
         for (int l = 0; l < FOV_LEVELS; l++) {
             const float4 c = rec[2 + l];
@@ -285,6 +286,9 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
         ws.tile_blend = (uint8_t*)take(T);
     }
     ws.rec = (float4*)take((size_t)P * 16 * (mode == MODE_FOV ? REC_FOV : REC_PS1));
+    ws.vis_cap = (uint32_t)((size_t)P + (size_t)P / 4 + (size_t)STAGE_MAX_BLOCKS * 8 * 128);
+    ws.vis_list = (uint32_t*)take((size_t)ws.vis_cap * 4);
+    ws.vis_lv = (uint32_t*)take((size_t)ws.vis_cap * 4);
     if (mode == MODE_SUM) {
         ws.cov3D = (float*)take((size_t)P * 24);
         ws.clamped = (uint8_t*)take((size_t)P * 4);
@@ -364,6 +368,8 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     }
     prof_mark(1, st);
     launch_pre(ws, in, (Mode)MODE, num_sms, st);
+    STAGE_CHECK();
+    launch_color(ws, in, (Mode)MODE, num_sms, st);
     STAGE_CHECK();
     prof_mark(2, st);
     launch_tile_scan(ws, T, st);

@@ -49,8 +49,9 @@ struct PixPS1 {      // OBB/forward.cu:251-384
         if (alpha < 1.0f / 255.0f) return;
         const float test_T = FM(T, FS(1.0f, alpha));
         if (test_T < 0.0001f) { done = true; return; }
+        const float4 c = sm.sC[j];
         const float w = FM(alpha, T);
-        C0 = FF(b.z, w, C0); C1 = FF(b.w, w, C1); C2 = FF(sm.sC[j].x, w, C2);
+        C0 = FF(c.x, w, C0); C1 = FF(c.y, w, C1); C2 = FF(c.z, w, C2);
         T = test_T;
     }
 };
