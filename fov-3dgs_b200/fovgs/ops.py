@@ -29,6 +29,11 @@ def set_full_sort(on):
     check(lib().fovgs_set_option(1, 1 if on else 0), "fovgs_set_option")
 
 
+def set_no_tma(on):
+    """Colour stage: use register-staged cooperative loads instead of TMA bulk copies (debug / comparison)."""
+    check(lib().fovgs_set_option(2, 1 if on else 0), "fovgs_set_option")
+
+
 def set_deferred_check(on):
     """Pipelined mode for the inference paths: skip the per-frame host read of the frame statistics; the previous
     frame's overflow flag is checked at the next call (and by `check_pending()`)."""

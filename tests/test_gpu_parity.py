@@ -236,6 +236,28 @@ def test_lazy_sort_blend_equals_full_sort_blend():
     assert torch.equal(col_f, col_l2)
 
 
+def test_tma_colour_stage_equals_register_staged_stage(scene_small):
+    """k_color_tma (cp.async.bulk gathers) and k_color (register-staged loads) must give identical colours, including
+    Gaussian 0 / P-1 (window clipping at the tensor ends) and odd ids (4-byte aligned SH blocks)."""
+    s, c = scene_small
+    f = synth.add_foveation(s)
+    outs = []
+    for no_tma in (False, True):
+        ops.set_no_tma(no_tma)
+        try:
+            (n, col, radii, pl, rg, item), _, _ = _run_fov(f, c, (0.5, 0.5))
+            geo = ops.geometry(item, ops.MODE_FOV, radii.numel(), c["image_width"], c["image_height"])
+            (n2, col2, radii2, item2, pl2, rg2), _, _ = _run_ps1(ops.MODE_OBB, s, c)
+            geo2 = ops.geometry(item2, ops.MODE_OBB, radii2.numel(), c["image_width"], c["image_height"])
+            vis = (radii > 0).unsqueeze(-1).unsqueeze(-1)
+            outs.append((col.clone(), col2.clone(), (geo["level_colors"] * 1.0).clone(), geo2["rgb"].clone(), radii.clone(), radii2.clone()))
+        finally:
+            ops.set_no_tma(False)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    v2 = outs[0][5] > 0
+    assert torch.equal(outs[0][3][v2], outs[1][3][v2])
+
+
 def test_capacity_overflow_regrows(monkeypatch):
     monkeypatch.setenv("FOVGS_INSTANCE_CAPACITY", "1000")
     ops._pool.clear()
