@@ -117,9 +117,7 @@ struct WarpSmem {
     int x0[32], y0[32], w[32];
     uint32_t pref[33];
     uint32_t nzlist[32];         // lane of the k-th Gaussian with a non-empty candidate rectangle
-    uint32_t cnt[32];
-    int lo[32], hi[32];          // FOV: float bits of the (non-negative) lowest / highest level used
-    uint32_t bl[32];             // FOV: any kept tile is a blending tile
+    uint32_t cnt[32];            // != 0: at least one candidate tile survived (the Gaussian is visible)
     uint32_t single[32];         // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
 };
 
@@ -195,12 +193,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
             wm.dbits[lane] = __float_as_uint(s.depth);
             wm.x0[lane] = cx0; wm.y0[lane] = cy0; wm.w[lane] = cw; wm.rw[lane] = 1.0f / (float)max(cw, 1);
-            if (MODE == MODE_FOV) {
-                wm.hl1[lane] = FA(hl, 1.0f);
-                wm.lo[lane] = __float_as_int(fmaxf(hl, 0.0f));
-                wm.hi[lane] = 0;
-                wm.bl[lane] = 0;
-            }
+            if (MODE == MODE_FOV) wm.hl1[lane] = FA(hl, 1.0f);
         }
         wm.cnt[lane] = 0;
         // exclusive scan of the candidate counts over the warp; compact list of non-empty owners
@@ -223,9 +216,8 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             // heads: window positions at which a non-empty owner's range starts
             const unsigned hbit = (tnum > 0 && my_start >= r && my_start < r + 32) ? (1u << (my_start - r)) : 0u;
             const unsigned H = __reduce_or_sync(0xffffffffu, hbit);
-            bool pass = false, single = false, tblend = false;
+            bool pass = false, single = false;
             uint32_t tile = 0, owner = 0;
-            float level = 0.0f;
             if (valid) {
                 owner = wm.nzlist[owners_before + __popc(H & le_mask) - 1];
                 const int t = (int)(c - wm.pref[owner]);
@@ -238,10 +230,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                 tile = (uint32_t)ty * gx + tx;
                 single = wm.single[owner] != 0;
                 pass = true;
-                if (MODE == MODE_FOV) {
-                    level = ws.tile_min[tile];
-                    pass = level < wm.hl1[owner];
-                }
+                if (MODE == MODE_FOV) pass = ws.tile_min[tile] < wm.hl1[owner];
                 if (pass && !single) {
                     const float cx = wm.px[owner], cy = wm.py[owner];
                     const float e1x = wm.e1x[owner], e1y = wm.e1y[owner], e2x = wm.e2x[owner], e2y = wm.e2y[owner];
@@ -251,45 +240,13 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                     const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
                     pass = obb_hits_tile(oc, cx, cy, e1x, e1y, e2x, e2y, l1, l2, tcx, tcy);
                 }
-                if (pass) {
-                    atomicAdd(&ws.tile_count[(size_t)tile * CSTRIDE], 1u);
-                    if (MODE == MODE_FOV) tblend = ws.tile_blend[tile] != 0;
-                }
+                if (pass) atomicAdd(&ws.tile_count[(size_t)tile * CSTRIDE], 1u);
             }
-            // per-owner bookkeeping over the lanes that share an owner: segments are delimited by the heads
-            const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+            // per-owner bookkeeping: a Gaussian is visible iff any of its candidate tiles survives (benign same-value race).
+            // The reference also tracks the range of levels a Gaussian lands in (rasterizer_impl.cu:375-380) to colour only
+            // those; k_color simply colours all four levels — the unused ones are never composited.
+            if (pass) wm.cnt[owner] = 1u;
             const unsigned passmask = __ballot_sync(0xffffffffu, pass);
-            unsigned seg;
-            bool head;
-            {
-                const unsigned Hx = H | 1u;                                   // position 0 continues the carried-over owner
-                const int start = 31 - __clz(Hx & le_mask);
-                const unsigned above = (lane == 31) ? 0u : (Hx >> (lane + 1));
-                const int end = above ? (lane + 1 + (__ffs(above) - 1)) : 32;
-                const unsigned upto_end = (end == 32) ? 0xffffffffu : ((1u << end) - 1u);
-                seg = upto_end & ~((1u << start) - 1u) & validmask;
-                head = valid && (lane == start);
-                if (!valid) seg = ~validmask;                                 // idle lanes form their own group
-            }
-            const unsigned npass_seg = __popc(passmask & seg);
-            if (MODE == MODE_FOV) {
-                const unsigned blendmask = __ballot_sync(0xffffffffu, pass && tblend);
-                const int lb = pass ? __float_as_int(fmaxf(level, 0.0f)) : 0x7f800000;
-                const int hb = pass ? __float_as_int(fmaxf(level, 0.0f)) : 0;
-                const int lo_seg = __reduce_min_sync(seg, lb);
-                const int hi_seg = __reduce_max_sync(seg, hb);
-                if (head && npass_seg) {
-                    if (single) {   // reference assigns (not min/max) on the single-tile path: rasterizer_impl.cu:309-312
-                        wm.lo[owner] = lo_seg;
-                        wm.hi[owner] = hi_seg;
-                    } else {
-                        wm.lo[owner] = min(wm.lo[owner], lo_seg);
-                        wm.hi[owner] = max(wm.hi[owner], hi_seg);
-                    }
-                    if (blendmask & seg) wm.bl[owner] = 1u;
-                }
-            }
-            if (head && npass_seg) wm.cnt[owner] += npass_seg;   // one head per owner per round: no atomics needed
             // stage the surviving instances densely in this warp's chunk
             const uint32_t np = __popc(passmask);
             if (np) {
@@ -332,10 +289,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
             if (MODE == MODE_FOV) {
                 rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
-                const int l0 = (int)__int_as_float(wm.lo[lane]);
-                int l1 = (int)__int_as_float(wm.hi[lane]);
-                if (wm.bl[lane]) l1 = min(l1 + 1, FOV_LEVELS - 1);
-                lv = (uint32_t)l0 | ((uint32_t)l1 << 8);
+                lv = (uint32_t)(FOV_LEVELS - 1) << 8;   // all levels
             } else {
                 rec[1] = make_float4(s.conz, in.opacities[idx], s.depth, 0.0f);
                 if (MODE == MODE_SUM) {
