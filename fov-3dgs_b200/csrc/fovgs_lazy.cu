@@ -39,12 +39,14 @@ struct PixPS1 {      // OBB/forward.cu:251-384
     float T, C0, C1, C2;
     bool done;
     __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
-    __device__ __forceinline__ void step(const LazySmem& sm, int j, float pixx, float pixy) {
+    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
         const float4 a = sm.sA[j];
-        const float4 b = sm.sB[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        const float power = gauss_power(a.z, a.w, b.x, dx, dy);
+        return gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+    }
+    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
+        const float4 b = sm.sB[j];
         const float alpha = fminf(0.99f, FM(b.y, expf(power)));
         if (alpha < 1.0f / 255.0f) return;
         const float test_T = FM(T, FS(1.0f, alpha));
@@ -59,10 +61,12 @@ struct PixFov {      // FOV/forward.cu:490-609
     float T, C0, C1, C2;
     bool done;
     __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
-    __device__ __forceinline__ void step(const LazySmem& sm, int j, float pixx, float pixy) {
+    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
         const float4 a = sm.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        const float power = gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+    }
+    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
         const float4 c = sm.sC[j];
         const float alpha = fminf(0.99f, FM(c.x, expf(power)));
@@ -81,12 +85,14 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
         T1 = T2 = 1.0f; A0 = A1 = A2 = B0 = B1 = B2 = 0.f; L2_f = l2f;
         L1_done = est > (float)L2; L2_done = false; done = !inside;
     }
-    __device__ __forceinline__ void step(const LazySmem& sm, int j, float pixx, float pixy) {
+    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
         const float4 a = sm.sA[j];
-        const float4 b = sm.sB[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        const float power = gauss_power(a.z, a.w, b.x, dx, dy);
+        return gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+    }
+    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
+        const float4 b = sm.sB[j];
         const float e = expf(power);
         if (!L1_done) {
             const float4 c = sm.sC[j];
@@ -318,7 +324,18 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
         const int lim = (int)min(256u, m - b0);
         consumed += (uint32_t)lim;
         if (b0 + 256 < m) fetch(b0 + 256 + tid);
-        for (int j = 0; !px.done && j < lim; j++) px.step(sm, j, pixx, pixy);
+        // four falloff exponents are evaluated together (independent shared loads + FMAs in flight), then applied in
+        // list order: the per-pixel sequence of operations is unchanged
+        int j = 0;
+        for (; !px.done && j + 3 < lim; j += 4) {
+            const float p0 = px.power(sm, j, pixx, pixy), p1 = px.power(sm, j + 1, pixx, pixy);
+            const float p2 = px.power(sm, j + 2, pixx, pixy), p3 = px.power(sm, j + 3, pixx, pixy);
+            px.apply(sm, j, p0);
+            if (!px.done) px.apply(sm, j + 1, p1);
+            if (!px.done) px.apply(sm, j + 2, p2);
+            if (!px.done) px.apply(sm, j + 3, p3);
+        }
+        for (; !px.done && j < lim; j++) px.apply(sm, j, px.power(sm, j, pixx, pixy));
     }
     return false;
 }
