@@ -17,22 +17,56 @@
 // The training variant (SUM) keeps the full sort: its backward needs the complete lists, and its
 // `gaussians_count` is defined by 256-entry batch boundaries.  `out_point_list` requests also use the full path.
 #include "fovgs_internal.cuh"
+#ifdef FOVGS_TILE_TIMING
+#include <cstdio>
+#endif
 
 namespace fovgs {
 
 constexpr int LCAP = 2048;
 constexpr float kStartBlendL = 0.5f;
 
+struct SortScratch { uint32_t whist[8][256]; uint32_t totals[256]; };
+struct BlendStage { float4 sA[256], sB[256], sC[256], sD[256]; };
 struct LazySmem {
     uint64_t keys[2][LCAP];
-    uint32_t whist[8][256];
-    uint32_t totals[256];
+    union {                 // a tile alternates sort and composite phases (block barriers in between): one footprint
+        SortScratch srt;
+        BlendStage bl;
+    };
     uint32_t bucket_off[257];
     uint32_t bucket_cur[256];
     uint32_t wsum[8];
     unsigned long long vary;
-    float4 sA[256], sB[256], sC[256], sD[256];
+    uint8_t widx[8][256];   // per warp: batch slots whose footprint can reach the warp's 8x4 pixel block
 };
+
+// ---- conservative footprint test of one splat against a warp's pixel block -----------------------------------------
+// A splat changes a pixel only if its falloff exponent is >= -4.5 and opacity*exp(exponent) >= 1/255
+// (FOV/forward.cu:556-566, OBB/forward.cu:330-342).  q = -exponent is a convex quadratic in (dx, dy); its minimum over the
+// block [X0, X0+7] x [Y0, Y0+3] is 0 when the centre lies inside and otherwise sits on one of the four edges, where it
+// is a clamped 1-D parabola.  The splat is dropped for this warp only when that minimum exceeds the threshold by more
+// than a bound on every fp32 rounding involved (relative 8e-6 of the largest term magnitudes + 2e-3 absolute), so a
+// dropped splat is one the exact per-pixel code below would have skipped for all 32 pixels: images are unchanged.
+__device__ __forceinline__ bool block_may_touch(const float4 a, const float conz, const float op, const float X0, const float Y0) {
+    const float dx0 = a.x - (X0 + 7.0f), dx1 = a.x - X0, dy0 = a.y - (Y0 + 3.0f), dy1 = a.y - Y0;
+    if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
+    const float A = a.z, B = a.w, C = conz;
+    const float tau = fminf(4.5f, __logf(255.0f * op));
+    const float iA = __frcp_rn(A), iC = __frcp_rn(C);
+    auto edge_x = [&](float ex) {   // dx fixed
+        const float t = fminf(fmaxf(-B * ex * iC, dy0), dy1);
+        return 0.5f * A * ex * ex + B * ex * t + 0.5f * C * t * t;
+    };
+    auto edge_y = [&](float ey) {   // dy fixed
+        const float t = fminf(fmaxf(-B * ey * iA, dx0), dx1);
+        return 0.5f * C * ey * ey + B * ey * t + 0.5f * A * t * t;
+    };
+    const float qmin = fminf(fminf(edge_x(dx0), edge_x(dx1)), fminf(edge_y(dy0), edge_y(dy1)));
+    const float mx = fmaxf(fabsf(dx0), fabsf(dx1)), my = fmaxf(fabsf(dy0), fabsf(dy1));
+    const float mag = 0.5f * A * mx * mx + 0.5f * C * my * my + fabsf(B) * mx * my;
+    return !(qmin - (8e-6f * mag + 2e-3f) > tau);   // NaN anywhere -> keep
+}
 
 // ---- per-pixel compositing state (identical arithmetic to k_blend) -------------------------------------------------
 struct PixPS1 {      // OBB/forward.cu:251-384
@@ -40,18 +74,18 @@ struct PixPS1 {      // OBB/forward.cu:251-384
     bool done;
     __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
     __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.sA[j];
+        const float4 a = sm.bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
     }
     __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
-        const float4 b = sm.sB[j];
+        const float4 b = sm.bl.sB[j];
         const float alpha = fminf(0.99f, FM(b.y, expf(power)));
         if (alpha < 1.0f / 255.0f) return;
         const float test_T = FM(T, FS(1.0f, alpha));
         if (test_T < 0.0001f) { done = true; return; }
-        const float4 c = sm.sC[j];
+        const float4 c = sm.bl.sC[j];
         const float w = FM(alpha, T);
         C0 = FF(c.x, w, C0); C1 = FF(c.y, w, C1); C2 = FF(c.z, w, C2);
         T = test_T;
@@ -62,13 +96,13 @@ struct PixFov {      // FOV/forward.cu:490-609
     bool done;
     __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
     __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.sA[j];
+        const float4 a = sm.bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
     }
     __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
-        const float4 c = sm.sC[j];
+        const float4 c = sm.bl.sC[j];
         const float alpha = fminf(0.99f, FM(c.x, expf(power)));
         if (alpha < 1.0f / 255.0f) return;
         const float test_T = FM(T, FS(1.0f, alpha));
@@ -86,16 +120,16 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
         L1_done = est > (float)L2; L2_done = false; done = !inside;
     }
     __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.sA[j];
+        const float4 a = sm.bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
     }
     __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
-        const float4 b = sm.sB[j];
+        const float4 b = sm.bl.sB[j];
         const float e = expf(power);
         if (!L1_done) {
-            const float4 c = sm.sC[j];
+            const float4 c = sm.bl.sC[j];
             const float alpha1 = fminf(0.99f, FM(c.x, e));
             if (!(alpha1 < 1.0f / 255.0f)) {
                 const float test_T1 = FM(T1, FS(1.0f, alpha1));
@@ -108,7 +142,7 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
             }
         }
         if (!L2_done) {
-            const float4 c = sm.sD[j];
+            const float4 c = sm.bl.sD[j];
             const float alpha2 = fminf(0.99f, FM(c.x, e));
             const bool skip2 = (alpha2 < 1.0f / 255.0f) || (FA(b.y, 1.0f) < L2_f);
             if (!skip2) {
@@ -159,14 +193,14 @@ __device__ __forceinline__ int lazy_sort_group(LazySmem& sm, const uint32_t m) {
         if (((vary >> shift) & 0xffull) == 0) continue;
         uint64_t* src = sm.keys[cur];
         uint64_t* dst = sm.keys[cur ^ 1];
-        for (int i = tid; i < 8 * 256; i += 256) (&sm.whist[0][0])[i] = 0;
+        for (int i = tid; i < 8 * 256; i += 256) (&sm.srt.whist[0][0])[i] = 0;
         __syncthreads();
-        for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&sm.whist[warp][(src[i] >> shift) & 0xff], 1u);
+        for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&sm.srt.whist[warp][(src[i] >> shift) & 0xff], 1u);
         __syncthreads();
         {
             uint32_t t = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const uint32_t c = sm.whist[w][tid]; sm.whist[w][tid] = t; t += c; }
+            for (int w = 0; w < 8; w++) { const uint32_t c = sm.srt.whist[w][tid]; sm.srt.whist[w][tid] = t; t += c; }
             uint32_t x = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -174,10 +208,10 @@ __device__ __forceinline__ int lazy_sort_group(LazySmem& sm, const uint32_t m) {
             __syncthreads();
             uint32_t base = x - t;
             for (int w = 0; w < warp; w++) base += sm.wsum[w];
-            sm.totals[tid] = base;
+            sm.srt.totals[tid] = base;
         }
         __syncthreads();
-        for (int i = tid; i < 8 * 256; i += 256) (&sm.whist[0][0])[i] += sm.totals[i & 255];
+        for (int i = tid; i < 8 * 256; i += 256) (&sm.srt.whist[0][0])[i] += sm.srt.totals[i & 255];
         __syncthreads();
         for (uint32_t i0 = wbeg; i0 < wend; i0 += 32) {
             const uint32_t i = i0 + lane;
@@ -187,11 +221,11 @@ __device__ __forceinline__ int lazy_sort_group(LazySmem& sm, const uint32_t m) {
             const unsigned peers = __match_any_sync(0xffffffffu, d);
             const unsigned rank = __popc(peers & ((1u << lane) - 1u));
             uint32_t base = 0;
-            if (valid) base = sm.whist[warp][d];
+            if (valid) base = sm.srt.whist[warp][d];
             __syncwarp();
             if (valid) {
                 dst[base + rank] = key;
-                if (rank == 0) sm.whist[warp][d] = base + __popc(peers);
+                if (rank == 0) sm.srt.whist[warp][d] = base + __popc(peers);
             }
             __syncwarp();
         }
@@ -237,14 +271,14 @@ __device__ __forceinline__ const uint64_t* lazy_global_sort(LazySmem& sm, uint64
     for (int pass = 0; pass < 4; pass++) {
         const int shift = 32 + 8 * pass;
         if (((vary >> shift) & 0xffull) == 0) continue;
-        for (int i = tid; i < 8 * 256; i += 256) (&sm.whist[0][0])[i] = 0;
+        for (int i = tid; i < 8 * 256; i += 256) (&sm.srt.whist[0][0])[i] = 0;
         __syncthreads();
-        for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&sm.whist[warp][(src[i] >> shift) & 0xff], 1u);
+        for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&sm.srt.whist[warp][(src[i] >> shift) & 0xff], 1u);
         __syncthreads();
         {
             uint32_t t = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const uint32_t c = sm.whist[w][tid]; sm.whist[w][tid] = t; t += c; }
+            for (int w = 0; w < 8; w++) { const uint32_t c = sm.srt.whist[w][tid]; sm.srt.whist[w][tid] = t; t += c; }
             uint32_t x = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -252,10 +286,10 @@ __device__ __forceinline__ const uint64_t* lazy_global_sort(LazySmem& sm, uint64
             __syncthreads();
             uint32_t base = x - t;
             for (int w = 0; w < warp; w++) base += sm.wsum[w];
-            sm.totals[tid] = base;
+            sm.srt.totals[tid] = base;
         }
         __syncthreads();
-        for (int i = tid; i < 8 * 256; i += 256) (&sm.whist[0][0])[i] += sm.totals[i & 255];
+        for (int i = tid; i < 8 * 256; i += 256) (&sm.srt.whist[0][0])[i] += sm.srt.totals[i & 255];
         __syncthreads();
         for (uint32_t i0 = wbeg; i0 < wend; i0 += 32) {
             const uint32_t i = i0 + lane;
@@ -265,11 +299,11 @@ __device__ __forceinline__ const uint64_t* lazy_global_sort(LazySmem& sm, uint64
             const unsigned peers = __match_any_sync(0xffffffffu, d);
             const unsigned rank = __popc(peers & ((1u << lane) - 1u));
             uint32_t base = 0;
-            if (valid) base = sm.whist[warp][d];
+            if (valid) base = sm.srt.whist[warp][d];
             __syncwarp();
             if (valid) {
                 dst[base + rank] = key;
-                if (rank == 0) sm.whist[warp][d] = base + __popc(peers);
+                if (rank == 0) sm.srt.whist[warp][d] = base + __popc(peers);
             }
             __syncwarp();
         }
@@ -295,11 +329,14 @@ __device__ __forceinline__ const uint64_t* lazy_global_sort(LazySmem& sm, uint64
 }
 
 // ---- composite the m sorted keys `sk` (shared memory) in 256-entry batches; returns true when every pixel is done ----
+// Thread layout: warp w owns the 8x4 pixel block at (8*(w&1), 4*(w>>1)) of the tile.  Per batch each warp first builds
+// the list of slots that can reach its block (block_may_touch, one slot per lane), then all lanes walk that list.
 template <int KIND, class PIX>
 __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& ws, const uint64_t* sk, const uint32_t m,
-                                                 PIX& px, const float pixx, const float pixy, const int L1, const int L2,
-                                                 uint32_t& consumed) {
-    const int tid = threadIdx.x;
+                                                 PIX& px, const float pixx, const float pixy, const float blkx,
+                                                 const float blky, const int L1, const int L2, uint32_t& consumed,
+                                                 uint32_t& kept) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int R = (KIND == 0) ? REC_PS1 : REC_FOV;
     float4 r0, r1, r2, r3;
     bool valid;
@@ -314,57 +351,84 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
         }
     };
     fetch(tid);
+    uint8_t* __restrict__ wl = sm.widx[warp];
+    const uint32_t* __restrict__ wl4 = reinterpret_cast<const uint32_t*>(sm.widx[warp]);
     for (uint32_t b0 = 0; b0 < m; b0 += 256) {
         if (__syncthreads_count(px.done) == 256) return true;
         if (valid) {
-            sm.sA[tid] = r0; sm.sB[tid] = r1; sm.sC[tid] = r2;
-            if (KIND == 2) sm.sD[tid] = r3;
+            sm.bl.sA[tid] = r0; sm.bl.sB[tid] = r1; sm.bl.sC[tid] = r2;
+            if (KIND == 2) sm.bl.sD[tid] = r3;
         }
         __syncthreads();
         const int lim = (int)min(256u, m - b0);
         consumed += (uint32_t)lim;
         if (b0 + 256 < m) fetch(b0 + 256 + tid);
+        if (__all_sync(0xffffffffu, px.done)) continue;
+        uint32_t cnt = 0;
+        for (int jb = 0; jb < lim; jb += 32) {
+            const int j = jb + lane;
+            bool keep = false;
+            if (j < lim) {
+                const float op = (KIND == 0) ? sm.bl.sB[j].y : (KIND == 1) ? sm.bl.sC[j].x : fmaxf(sm.bl.sC[j].x, sm.bl.sD[j].x);
+                keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, op, blkx, blky);
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+            if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
+            cnt += __popc(mk);
+        }
+        __syncwarp();
+        kept += cnt;
         // four falloff exponents are evaluated together (independent shared loads + FMAs in flight), then applied in
         // list order: the per-pixel sequence of operations is unchanged
-        int j = 0;
-        for (; !px.done && j + 3 < lim; j += 4) {
-            const float p0 = px.power(sm, j, pixx, pixy), p1 = px.power(sm, j + 1, pixx, pixy);
-            const float p2 = px.power(sm, j + 2, pixx, pixy), p3 = px.power(sm, j + 3, pixx, pixy);
-            px.apply(sm, j, p0);
-            if (!px.done) px.apply(sm, j + 1, p1);
-            if (!px.done) px.apply(sm, j + 2, p2);
-            if (!px.done) px.apply(sm, j + 3, p3);
+        uint32_t k = 0;
+        for (; !px.done && k + 3 < cnt; k += 4) {
+            const uint32_t q = wl4[k >> 2];
+            const int j0 = q & 0xff, j1 = (q >> 8) & 0xff, j2 = (q >> 16) & 0xff, j3 = q >> 24;
+            const float p0 = px.power(sm, j0, pixx, pixy), p1 = px.power(sm, j1, pixx, pixy);
+            const float p2 = px.power(sm, j2, pixx, pixy), p3 = px.power(sm, j3, pixx, pixy);
+            px.apply(sm, j0, p0);
+            if (!px.done) px.apply(sm, j1, p1);
+            if (!px.done) px.apply(sm, j2, p2);
+            if (!px.done) px.apply(sm, j3, p3);
         }
-        for (; !px.done && j < lim; j++) px.apply(sm, j, px.power(sm, j, pixx, pixy));
+        for (; !px.done && k < cnt; k++) { const int j = wl[k]; px.apply(sm, j, px.power(sm, j, pixx, pixy)); }
     }
     return false;
 }
 
 template <int KIND, class PIX>
 __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, const int tile, PIX& px, const float pixx,
-                                          const float pixy, const int L1, const int L2) {
+                                          const float pixy, const float blkx, const float blky, const int L1, const int L2) {
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t cap = ws.hdr->cap;
     const uint32_t sbeg = min(ws.tile_offset[tile], cap), send = min(ws.tile_offset[tile + 1], cap);
     const uint32_t n = send - sbeg;
-    uint32_t consumed = 0;
+    uint32_t consumed = 0, kept = 0;
     if (n == 0) return;
     const uint64_t* __restrict__ gA = ws.keysA + sbeg;
     if (n <= (uint32_t)LCAP) {
+#pragma unroll 4
         for (uint32_t i = tid; i < n; i += 256) sm.keys[0][i] = gA[i];
         __syncthreads();
         const int cur = lazy_sort_group(sm, n);
-        lazy_blend_group<KIND>(sm, ws, sm.keys[cur], n, px, pixx, pixy, L1, L2, consumed);
+        lazy_blend_group<KIND>(sm, ws, sm.keys[cur], n, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
     } else {
         // ---- MSD partition of the tile's keys by their highest varying depth byte ----
         uint64_t* gB = ws.keysB + sbeg;
         if (tid == 0) sm.vary = 0ull;
         sm.bucket_cur[tid] = 0;
         __syncthreads();
+        constexpr int MU = 8;   // keys in flight per thread in the three partition passes (L2 round trips overlap)
         {
             const uint64_t k0 = gA[0];
             uint64_t v = 0;
-            for (uint32_t i = tid; i < n; i += 256) v |= (gA[i] ^ k0);
+            for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
+                uint64_t k[MU];
+#pragma unroll
+                for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : k0; }
+#pragma unroll
+                for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
@@ -373,7 +437,13 @@ __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, con
         const uint32_t vhi = (uint32_t)(sm.vary >> 32);
         // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile)
         const int shift = vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32;
-        for (uint32_t i = tid; i < n; i += 256) atomicAdd(&sm.bucket_cur[(gA[i] >> shift) & 0xff], 1u);
+        for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
+            uint64_t k[MU];
+#pragma unroll
+            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < MU; u++) if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+        }
         __syncthreads();
         {   // exclusive scan of the 256 bucket sizes
             const uint32_t c = sm.bucket_cur[tid];
@@ -389,10 +459,17 @@ __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, con
             sm.bucket_cur[tid] = base;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += 256) {
-            const uint64_t k = gA[i];
-            const uint32_t pos = atomicAdd(&sm.bucket_cur[(k >> shift) & 0xff], 1u);
-            gB[pos] = k;
+        for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
+            uint64_t k[MU];
+#pragma unroll
+            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < MU; u++) {
+                if (i0 + u * 256 < n) {
+                    const uint32_t pos = atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+                    gB[pos] = k[u];
+                }
+            }
         }
         __syncthreads();   // gB is read below by this CTA only
         // ---- front-to-back over groups of buckets ----
@@ -412,17 +489,18 @@ __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, con
                     const uint32_t m = min((uint32_t)LCAP, bs - c0);
                     for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = sorted[c0 + i];
                     __syncthreads();
-                    all_done = lazy_blend_group<KIND>(sm, ws, sm.keys[0], m, px, pixx, pixy, L1, L2, consumed);
+                    all_done = lazy_blend_group<KIND>(sm, ws, sm.keys[0], m, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
                     __syncthreads();
                 }
                 b = b + 1;
             } else {
                 const uint32_t m = sm.bucket_off[e] - g0;
                 if (m) {
+#pragma unroll 4
                     for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = gB[g0 + i];
                     __syncthreads();
                     const int cur = lazy_sort_group(sm, m);
-                    all_done = lazy_blend_group<KIND>(sm, ws, sm.keys[cur], m, px, pixx, pixy, L1, L2, consumed);
+                    all_done = lazy_blend_group<KIND>(sm, ws, sm.keys[cur], m, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
                     __syncthreads();
                 }
                 b = e;
@@ -430,10 +508,11 @@ __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, con
         }
     }
     if (tid == 0 && consumed) atomicAdd(&ws.hdr->stats.reserved[0], consumed);
+    if (lane == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);   // (warp, splat) pairs that passed block_may_touch
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) k_lazy_blend(Workspace ws, FrameInputs in) {
+__global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs in) {
     extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
     LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
     const FrameHeader* __restrict__ hdr = ws.hdr;
@@ -441,7 +520,18 @@ __global__ void __launch_bounds__(256, 3) k_lazy_blend(Workspace ws, FrameInputs
     const int tile = (int)ws.tile_order[blockIdx.x];
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x;
-    const int pxi = tx * TILE + (tid & 15), pyi = ty * TILE + (tid >> 4);
+#ifdef FOVGS_TILE_TIMING
+    unsigned long long tt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
+    struct TT { unsigned long long t0; int tile; uint32_t n; const Workspace* w; unsigned sm;
+                __device__ ~TT() { if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    printf("TT %d %u %llu %llu %u %u\n", tile, n, t0, t1, sm, blockIdx.x); } } };
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    TT tt_guard{tt0, tile, min(ws.tile_offset[tile + 1], hdr->cap) - min(ws.tile_offset[tile], hdr->cap), &ws, smid};
+#endif
+    const int bx = ((tid >> 5) & 1) * 8, by = (tid >> 6) * 4;             // this warp's 8x4 pixel block inside the tile
+    const int lxi = bx + (tid & 7), lyi = by + ((tid >> 3) & 3);
+    const int pxi = tx * TILE + lxi, pyi = ty * TILE + lyi;
+    const float blkx = (float)(tx * TILE + bx), blky = (float)(ty * TILE + by);
     const bool inside = pxi < W && pyi < H;
     const uint32_t pix_id = (uint32_t)W * pyi + pxi;
     const float pixx = (float)pxi, pixy = (float)pyi;
@@ -454,7 +544,7 @@ __global__ void __launch_bounds__(256, 3) k_lazy_blend(Workspace ws, FrameInputs
         if (!blending) {
             PixFov px;
             px.init(inside);
-            lazy_tile<1>(sm, ws, tile, px, pixx, pixy, L1, 0);
+            lazy_tile<1>(sm, ws, tile, px, pixx, pixy, blkx, blky, L1, 0);
             if (inside) {
                 in.out_color[pix_id] = FF(bg0, px.T, px.C0);
                 in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);
@@ -462,11 +552,11 @@ __global__ void __launch_bounds__(256, 3) k_lazy_blend(Workspace ws, FrameInputs
             }
         } else {
             const int L2 = L1 + 1;
-            const float dxl = (float)(tid & 15), dyl = (float)(tid >> 4);
+            const float dxl = (float)lxi, dyl = (float)lyi;
             const float est = FF(FF(dxl, ws.tile_gx[tile], FM(dyl, ws.tile_gy[tile])), 0.0625f, tile_level_f);
             PixFovBlend px;
             px.init(inside, est, L2, FA(tile_level_f, 1.0f));
-            lazy_tile<2>(sm, ws, tile, px, pixx, pixy, L1, L2);
+            lazy_tile<2>(sm, ws, tile, px, pixx, pixy, blkx, blky, L1, L2);
             if (inside) {
                 const float A0 = FF(bg0, px.T1, px.A0), A1 = FF(bg1, px.T1, px.A1), A2 = FF(bg2, px.T1, px.A2);
                 const float B0 = FF(bg0, px.T2, px.B0), B1 = FF(bg1, px.T2, px.B1), B2 = FF(bg2, px.T2, px.B2);
@@ -484,7 +574,7 @@ __global__ void __launch_bounds__(256, 3) k_lazy_blend(Workspace ws, FrameInputs
     } else {
         PixPS1 px;
         px.init(inside);
-        lazy_tile<0>(sm, ws, tile, px, pixx, pixy, 0, 0);
+        lazy_tile<0>(sm, ws, tile, px, pixx, pixy, blkx, blky, 0, 0);
         if (inside) {
             in.out_color[pix_id] = FF(bg0, px.T, px.C0);
             in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);

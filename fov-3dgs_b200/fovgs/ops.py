@@ -146,6 +146,7 @@ def _stats_dict(item):
         "num_blend_tiles": int(s[3]) & 0xFFFFFFFF,
         "max_tile_instances": int(s[4]) & 0xFFFFFFFF,
         "blend_consumed": int(s[5]) & 0xFFFFFFFF,
+        "blend_block_pairs": int(s[6]) & 0xFFFFFFFF,
     }
 
 
