@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
     bool has_chunk = false;
     uint32_t vbase = 0, vused = VCHUNK;   // this warp's chunk of the visible list
     bool has_vchunk = false;
-    unsigned visible_total = 0;
+    unsigned visible_total = 0, cand_total = 0;
 
     const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
     for (int base = gwarp * 32; base < in.P; base += nwarps * 32) {
@@ -185,6 +185,28 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                     cx1 = min(cx1, sm.bbox[li][2]); cy1 = min(cy1, sm.bbox[li][3]);
                 }
             }
+            if (!single0 && true) {
+                // The OBB test starts with the two tile-axis separations (auxiliary.h:95-118; obb_hits_tile): a tile
+                // column tx can only pass when max(vx) - (16 tx + 8) >= -8 and min(vx) - (16 tx + 8) <= 8, same for
+                // rows.  Clip the candidate rectangle to that band (widened by far more than one fp32 rounding of the
+                // subtraction) so the tiles it removes are exactly tiles the test would reject.
+                ObbCorners oc;
+                obb_corners(s.px, s.py, s.e1x, s.e1y, s.e2x, s.e2y, s.len1, s.len2, oc);
+                const float mnx = fminf(fminf(oc.vx[0], oc.vx[1]), fminf(oc.vx[2], oc.vx[3]));
+                const float mxx = fmaxf(fmaxf(oc.vx[0], oc.vx[1]), fmaxf(oc.vx[2], oc.vx[3]));
+                const float mny = fminf(fminf(oc.vy[0], oc.vy[1]), fminf(oc.vy[2], oc.vy[3]));
+                const float mxy = fmaxf(fmaxf(oc.vy[0], oc.vy[1]), fmaxf(oc.vy[2], oc.vy[3]));
+                if (fabsf(mnx) < 1e8f && fabsf(mxx) < 1e8f) {
+                    const float e = 0.05f + 1e-6f * (fabsf(mnx) + fabsf(mxx));
+                    cx0 = max(cx0, (int)fmaxf(ceilf((mnx - 16.0f - e) * 0.0625f), 0.0f));
+                    cx1 = min(cx1, (int)fminf(floorf((mxx + e) * 0.0625f) + 1.0f, 1e6f));
+                }
+                if (fabsf(mny) < 1e8f && fabsf(mxy) < 1e8f) {
+                    const float e = 0.05f + 1e-6f * (fabsf(mny) + fabsf(mxy));
+                    cy0 = max(cy0, (int)fmaxf(ceilf((mny - 16.0f - e) * 0.0625f), 0.0f));
+                    cy1 = min(cy1, (int)fminf(floorf((mxy + e) * 0.0625f) + 1.0f, 1e6f));
+                }
+            }
             const int cw = max(cx1 - cx0, 0), ch = max(cy1 - cy0, 0);
             tnum = (uint32_t)cw * (uint32_t)ch;
             wm.single[lane] = single0;
@@ -203,6 +225,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         const uint32_t my_start = incl - tnum;
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const unsigned nz = __ballot_sync(0xffffffffu, tnum > 0);
+        cand_total += total;
         wm.pref[lane] = my_start;
         if (lane == 31) wm.pref[32] = total;
         if (tnum > 0) wm.nzlist[__popc(nz & lt_mask)] = (uint32_t)lane;
@@ -327,6 +350,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             if (p < ws.vis_cap) ws.vis_list[p] = TILE_INVALID;
     }
     if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
+    if (lane == 0 && cand_total) atomicAdd(&ws.hdr->stats.reserved[2], cand_total);   // candidate tiles enumerated
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -665,11 +689,33 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
 __global__ void __launch_bounds__(256) k_scatter(Workspace ws) {
     const uint32_t n = min(ws.hdr->stage_cursor, ws.stage_cap);
     const uint32_t cap = ws.hdr->cap;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t t = ws.stage_tile[i];
-        if (t == TILE_INVALID) continue;
-        const uint32_t slot = ws.tile_offset[t] + atomicAdd(&ws.tile_cursor[(size_t)t * CSTRIDE], 1u);
-        if (slot < cap) ws.keysA[slot] = ws.stage_key[i];
+    // each instance is a chain load(tile) -> atomic(cursor) -> store(key); four chains per thread are kept in flight
+    constexpr int U = 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
+        uint32_t t[U];
+        uint64_t k[U];
+        uint32_t off[U], r[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * stride;
+            t[u] = (i < n) ? ws.stage_tile[i] : TILE_INVALID;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (t[u] != TILE_INVALID) {
+                k[u] = ws.stage_key[i0 + u * stride];
+                off[u] = ws.tile_offset[t[u]];
+                r[u] = atomicAdd(&ws.tile_cursor[(size_t)t[u] * CSTRIDE], 1u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (t[u] != TILE_INVALID) {
+                const uint32_t slot = off[u] + r[u];
+                if (slot < cap) ws.keysA[slot] = k[u];
+            }
+        }
     }
 }
 

@@ -147,6 +147,7 @@ def _stats_dict(item):
         "max_tile_instances": int(s[4]) & 0xFFFFFFFF,
         "blend_consumed": int(s[5]) & 0xFFFFFFFF,
         "blend_block_pairs": int(s[6]) & 0xFFFFFFFF,
+        "candidates": int(s[7]) & 0xFFFFFFFF,
     }
 
 
