@@ -25,6 +25,37 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Conservative footprint test of one splat against a warp's 8x4 pixel block: false only when no pixel of the block can pass
+// `power >= -4.5 && opacity*exp(power) >= 1/255` (same bound as block_may_touch in fovgs_lazy.cu; margins cover every fp32
+// rounding involved), i.e. when the exact per-pixel code would produce no gradient for any of the 32 pixels.
+__device__ __forceinline__ bool bwd_block_may_touch(const float4 a, const float conz, const float op, const float X0, const float Y0) {
+    const float dx0 = a.x - (X0 + 7.0f), dx1 = a.x - X0, dy0 = a.y - (Y0 + 3.0f), dy1 = a.y - Y0;
+    if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
+    const float A = a.z, B = a.w, C = conz;
+    const float tau = fminf(4.5f, __logf(255.0f * op));
+    const float iA = __frcp_rn(A), iC = __frcp_rn(C);
+    auto edge_x = [&](float ex) {
+        const float t = fminf(fmaxf(-B * ex * iC, dy0), dy1);
+        return 0.5f * A * ex * ex + B * ex * t + 0.5f * C * t * t;
+    };
+    auto edge_y = [&](float ey) {
+        const float t = fminf(fmaxf(-B * ey * iA, dx0), dx1);
+        return 0.5f * C * ey * ey + B * ey * t + 0.5f * A * t * t;
+    };
+    const float qmin = fminf(fminf(edge_x(dx0), edge_x(dx1)), fminf(edge_y(dy0), edge_y(dy1)));
+    const float mx = fmaxf(fabsf(dx0), fabsf(dx1)), my = fmaxf(fabsf(dy0), fabsf(dy1));
+    const float mag = 0.5f * A * mx * mx + 0.5f * C * my * my + fabsf(B) * mx * my;
+    return !(qmin - (8e-6f * mag + 2e-3f) > tau);
+}
+
+constexpr int ACC_STRIDE = 9;   // acc[j][k], odd stride: the 9 partial sums of one splat sit in 9 different banks
+
+// Gradient of the compositing (SUM/backward.cu:399-557).  Differences from the reference's schedule, none in the math:
+//  * the walk starts at the tile's largest n_contrib instead of the end of the tile's list: entries behind it are
+//    skipped by every pixel (`contributor >= last_contributor`), and the lazy forward never sorted them;
+//  * warp = 8x4 pixel block; splats whose footprint cannot reach the block are dropped per warp before the pixel loop;
+//  * the 9 per-hit atomics become a transposed warp reduction (14 shuffles for 9 values), one shared-memory add per
+//    (warp, splat, value) and one global atomic per (tile, splat, value).
 __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* __restrict__ dL_dpixels,
                                                     float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
                                                     float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors) {
@@ -32,27 +63,38 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
     __shared__ float4 sB[256];
     __shared__ float4 sC[256];
     __shared__ int sId[256];
-    __shared__ float acc[9][256];
+    __shared__ float acc[256 * ACC_STRIDE];
+    __shared__ uint8_t widx[8][256];
+    __shared__ int s_max;
     const FrameHeader* __restrict__ hdr = ws.hdr;
     const int W = hdr->cam.W, H = hdr->cam.H, gx = hdr->cam.grid_x;
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int pxi = tx * TILE + (tid & 15), pyi = ty * TILE + (tid >> 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bx = (warp & 1) * 8, by = (warp >> 1) * 4;
+    const int pxi = tx * TILE + bx + (lane & 7), pyi = ty * TILE + by + (lane >> 3);
+    const float blkx = (float)(tx * TILE + bx), blky = (float)(ty * TILE + by);
     const bool inside = pxi < W && pyi < H;
     const uint32_t pix_id = (uint32_t)W * pyi + pxi;
     const float pixx = (float)pxi, pixy = (float)pyi;
     const uint32_t cap = hdr->cap;
     const uint32_t rbeg = min(ws.tile_offset[tile], cap), rend = min(ws.tile_offset[tile + 1], cap);
-    const int total = (int)(rend - rbeg);
-    if (total == 0) return;
-    const int rounds = (total + 255) / 256;
+    if (rend == rbeg) return;
     const size_t HW = (size_t)H * W;
 
     const float T_final = inside ? ws.final_T[pix_id] : 0.0f;
     float T = T_final;
-    uint32_t contributor = (uint32_t)total;
     const int last_contributor = inside ? (int)ws.n_contrib[pix_id] : 0;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    {
+        const int wm = __reduce_max_sync(0xffffffffu, last_contributor);
+        if (lane == 0 && wm) atomicMax(&s_max, wm);
+    }
+    __syncthreads();
+    const int total = min(s_max, (int)(rend - rbeg));   // entries [0, total) of the tile's sorted list can matter
+    if (total == 0) return;
+    const int rounds = (total + 255) / 256;
     float accum_rec[3] = {0.f, 0.f, 0.f};
     float dL_dpixel[3] = {0.f, 0.f, 0.f};
     if (inside) {
@@ -65,13 +107,16 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
     const float ddelx_dx = 0.5 * W;
     const float ddely_dy = 0.5 * H;
     const float bg_dot_dpixel = hdr->bg[0] * dL_dpixel[0] + hdr->bg[1] * dL_dpixel[1] + hdr->bg[2] * dL_dpixel[2];
+    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0, hi4 = (lane & 4) != 0;
+    const int myk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // value this lane ends up owning
+    uint8_t* __restrict__ wl = widx[warp];
 
     int toDo = total;
     for (int i = 0; i < rounds; i++, toDo -= 256) {
         __syncthreads();
         const int progress = i * 256 + tid;
         if (progress < total) {
-            const uint32_t id = ws.point_list[rend - progress - 1];
+            const uint32_t id = ws.point_list[rbeg + (uint32_t)(total - progress - 1)];
             const float4* rec = ws.rec + (size_t)REC_PS1 * id;
             sId[tid] = (int)id;
             sA[tid] = rec[0];
@@ -79,64 +124,98 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
             sC[tid] = rec[2];
         }
 #pragma unroll
-        for (int k = 0; k < 9; k++) acc[k][tid] = 0.0f;
+        for (int k = 0; k < ACC_STRIDE; k++) acc[k * 256 + tid] = 0.0f;
         __syncthreads();
         const int lim = min(256, toDo);
-        for (int j = 0; j < lim; j++) {
+        // entry j of this batch sits at list position total - 1 - (i*256 + j): the reference's `contributor` after its
+        // decrement.  A warp keeps the slots that can reach its block and that some pixel of it has not skipped.
+        const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+        uint32_t cnt = 0;
+        for (int jb = 0; jb < lim; jb += 32) {
+            const int j = jb + lane;
+            bool keep = false;
+            if (j < lim && (total - 1 - (i * 256 + j)) < wmax) keep = bwd_block_may_touch(sA[j], sB[j].x, sB[j].y, blkx, blky);
+            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+            if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
+            cnt += __popc(mk);
+        }
+        __syncwarp();
+        for (uint32_t kk = 0; kk < cnt; kk++) {
+            const int j = wl[kk];
+            const int contributor = total - 1 - (i * 256 + j);
             float g[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) g[k] = 0.0f;
             bool hit = false;
-            if (inside) {
-                contributor--;
-                if ((int)contributor < last_contributor) {
-                    const float4 a = sA[j];
-                    const float4 b = sB[j];
-                    const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-                    const float power = gauss_power(a.z, a.w, b.x, dx, dy);
-                    if (!(power > 0.0f || power < -4.5f)) {
-                        const float G = expf(power);
-                        const float alpha = fminf(0.99f, FM(b.y, G));
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            hit = true;
-                            T = T / (1.f - alpha);
-                            const float dchannel_dcolor = alpha * T;
-                            float dL_dalpha = 0.0f;
-                            const float4 cc = sC[j];
-                            const float col[3] = {cc.x, cc.y, cc.z};
+            if (inside && contributor < last_contributor) {
+                const float4 a = sA[j];
+                const float4 b = sB[j];
+                const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
+                const float power = gauss_power(a.z, a.w, b.x, dx, dy);
+                if (!(power > 0.0f || power < -4.5f)) {
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, FM(b.y, G));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        hit = true;
+                        T = T / (1.f - alpha);
+                        const float dchannel_dcolor = alpha * T;
+                        float dL_dalpha = 0.0f;
+                        const float4 cc = sC[j];
+                        const float col[3] = {cc.x, cc.y, cc.z};
 #pragma unroll
-                            for (int ch = 0; ch < 3; ch++) {
-                                const float c = col[ch];
-                                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                                last_color[ch] = c;
-                                const float dL_dchannel = dL_dpixel[ch];
-                                dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
-                                g[ch] = dchannel_dcolor * dL_dchannel;
-                            }
-                            dL_dalpha *= T;
-                            last_alpha = alpha;
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                            const float dL_dG = b.y * dL_dalpha;
-                            const float gdx = G * dx;
-                            const float gdy = G * dy;
-                            const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                            const float dG_ddely = -gdy * b.x - gdx * a.w;
-                            g[3] = dL_dG * dG_ddelx * ddelx_dx;
-                            g[4] = dL_dG * dG_ddely * ddely_dy;
-                            g[5] = -0.5f * gdx * dx * dL_dG;
-                            g[6] = -0.5f * gdx * dy * dL_dG;
-                            g[7] = -0.5f * gdy * dy * dL_dG;
-                            g[8] = G * dL_dalpha;
+                        for (int ch = 0; ch < 3; ch++) {
+                            const float c = col[ch];
+                            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                            last_color[ch] = c;
+                            const float dL_dchannel = dL_dpixel[ch];
+                            dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
+                            g[ch] = dchannel_dcolor * dL_dchannel;
                         }
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                        const float dL_dG = b.y * dL_dalpha;
+                        const float gdx = G * dx;
+                        const float gdy = G * dy;
+                        const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                        const float dG_ddely = -gdy * b.x - gdx * a.w;
+                        g[3] = dL_dG * dG_ddelx * ddelx_dx;
+                        g[4] = dL_dG * dG_ddely * ddely_dy;
+                        g[5] = -0.5f * gdx * dx * dL_dG;
+                        g[6] = -0.5f * gdx * dy * dL_dG;
+                        g[7] = -0.5f * gdy * dy * dL_dG;
+                        g[8] = G * dL_dalpha;
                     }
                 }
             }
             if (__any_sync(0xffffffffu, hit)) {
+                // transposed reduction of g[0..7]: halve the value set at each of three exchange steps, then two
+                // butterfly steps over the remaining 4 lanes; g[8] takes the plain butterfly
+                float h[4];
 #pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    const float v = warp_sum(g[k]);
-                    if (lane == 0) atomicAdd(&acc[k][j], v);
+                for (int q = 0; q < 4; q++) {
+                    const float send = hi16 ? g[q] : g[q + 4];
+                    const float keepv = hi16 ? g[q + 4] : g[q];
+                    h[q] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
+                float h2[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const float send = hi8 ? h[q] : h[q + 2];
+                    const float keepv = hi8 ? h[q + 2] : h[q];
+                    h2[q] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                float h1;
+                {
+                    const float send = hi4 ? h2[0] : h2[1];
+                    const float keepv = hi4 ? h2[1] : h2[0];
+                    h1 = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                h1 += __shfl_xor_sync(0xffffffffu, h1, 2);
+                h1 += __shfl_xor_sync(0xffffffffu, h1, 1);
+                const float v8 = warp_sum(g[8]);
+                if ((lane & 3) == 0 && h1 != 0.0f) atomicAdd(&acc[j * ACC_STRIDE + myk], h1);
+                if (lane == 1 && v8 != 0.0f) atomicAdd(&acc[j * ACC_STRIDE + 8], v8);
             }
         }
         __syncthreads();
@@ -145,7 +224,7 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
             float v[9];
             bool nz = false;
 #pragma unroll
-            for (int k = 0; k < 9; k++) { v[k] = acc[k][tid]; nz = nz || (v[k] != 0.0f); }
+            for (int k = 0; k < 9; k++) { v[k] = acc[tid * ACC_STRIDE + k]; nz = nz || (v[k] != 0.0f); }
             if (nz) {
                 atomicAdd(&dL_dcolors[3 * (size_t)id + 0], v[0]);
                 atomicAdd(&dL_dcolors[3 * (size_t)id + 1], v[1]);

@@ -377,9 +377,9 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     prof_mark(3, st);
     launch_scatter(ws, num_sms, st);
     STAGE_CHECK();
-    // Inference variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the
-    // sorted lists; the training variant always needs complete lists (backward, batch-granular gaussians_count).
-    const bool lazy = (MODE != MODE_SUM) && in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
+    // All variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the complete sorted
+    // lists.  The training variant appends the sorted prefix it composites to point_list: exactly what its backward walks.
+    const bool lazy = in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
     prof_mark(4, st);
     if (!lazy) {
         launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);

@@ -396,14 +396,15 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
     return false;
 }
 
-template <int KIND, class PIX>
-__device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, const int tile, PIX& px, const float pixx,
-                                          const float pixy, const float blkx, const float blky, const int L1, const int L2) {
+// ---- front-to-back producer of sorted key groups for one tile --------------------------------------------------------
+// `consume(sk, m, last)` is called by the whole CTA with m sorted keys in shared memory, groups in depth order; `last` says
+// no key follows.  It returns true (uniformly) when the tile needs nothing more; the keys behind are then never sorted.
+template <class CONSUME>
+__device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspace& ws, const int tile, CONSUME&& consume) {
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t cap = ws.hdr->cap;
     const uint32_t sbeg = min(ws.tile_offset[tile], cap), send = min(ws.tile_offset[tile + 1], cap);
     const uint32_t n = send - sbeg;
-    uint32_t consumed = 0, kept = 0;
     if (n == 0) return;
     const uint64_t* __restrict__ gA = ws.keysA + sbeg;
     if (n <= (uint32_t)LCAP) {
@@ -411,104 +412,209 @@ __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, con
         for (uint32_t i = tid; i < n; i += 256) sm.keys[0][i] = gA[i];
         __syncthreads();
         const int cur = lazy_sort_group(sm, n);
-        lazy_blend_group<KIND>(sm, ws, sm.keys[cur], n, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
-    } else {
-        // ---- MSD partition of the tile's keys by their highest varying depth byte ----
-        uint64_t* gB = ws.keysB + sbeg;
-        if (tid == 0) sm.vary = 0ull;
-        sm.bucket_cur[tid] = 0;
-        __syncthreads();
-        constexpr int MU = 8;   // keys in flight per thread in the three partition passes (L2 round trips overlap)
-        {
-            const uint64_t k0 = gA[0];
-            uint64_t v = 0;
-            for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
-                uint64_t k[MU];
-#pragma unroll
-                for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : k0; }
-#pragma unroll
-                for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
-        }
-        __syncthreads();
-        const uint32_t vhi = (uint32_t)(sm.vary >> 32);
-        // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile)
-        const int shift = vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32;
+        consume(sm.keys[cur], n, true);
+        return;
+    }
+    // ---- MSD partition of the tile's keys by their highest varying depth byte ----
+    uint64_t* gB = ws.keysB + sbeg;
+    if (tid == 0) sm.vary = 0ull;
+    sm.bucket_cur[tid] = 0;
+    __syncthreads();
+    constexpr int MU = 8;   // keys in flight per thread in the three partition passes (L2 round trips overlap)
+    {
+        const uint64_t k0 = gA[0];
+        uint64_t v = 0;
         for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
             uint64_t k[MU];
 #pragma unroll
-            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
+            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : k0; }
 #pragma unroll
-            for (int u = 0; u < MU; u++) if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+            for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
+    }
+    __syncthreads();
+    const uint32_t vhi = (uint32_t)(sm.vary >> 32);
+    // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile)
+    const int shift = vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32;
+    for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
+        uint64_t k[MU];
+#pragma unroll
+        for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
+#pragma unroll
+        for (int u = 0; u < MU; u++) if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    {   // exclusive scan of the 256 bucket sizes
+        const uint32_t c = sm.bucket_cur[tid];
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) sm.wsum[tid >> 5] = x;
         __syncthreads();
-        {   // exclusive scan of the 256 bucket sizes
-            const uint32_t c = sm.bucket_cur[tid];
-            uint32_t x = c;
+        uint32_t base = x - c;
+        for (int w = 0; w < (tid >> 5); w++) base += sm.wsum[w];
+        sm.bucket_off[tid] = base;
+        if (tid == 255) sm.bucket_off[256] = base + c;
+        sm.bucket_cur[tid] = base;
+    }
+    __syncthreads();
+    for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
+        uint64_t k[MU];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) sm.wsum[tid >> 5] = x;
-            __syncthreads();
-            uint32_t base = x - c;
-            for (int w = 0; w < (tid >> 5); w++) base += sm.wsum[w];
-            sm.bucket_off[tid] = base;
-            if (tid == 255) sm.bucket_off[256] = base + c;
-            sm.bucket_cur[tid] = base;
-        }
-        __syncthreads();
-        for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
-            uint64_t k[MU];
+        for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
 #pragma unroll
-            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
-#pragma unroll
-            for (int u = 0; u < MU; u++) {
-                if (i0 + u * 256 < n) {
-                    const uint32_t pos = atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
-                    gB[pos] = k[u];
-                }
-            }
-        }
-        __syncthreads();   // gB is read below by this CTA only
-        // ---- front-to-back over groups of buckets ----
-        int b = 0;
-        bool all_done = false;
-        while (b < 256 && !all_done) {
-            const uint32_t g0 = sm.bucket_off[b];
-            int e = b;
-            while (e < 256 && sm.bucket_off[e + 1] - g0 <= (uint32_t)LCAP) e++;
-            if (e == b) {
-                // one bucket larger than the shared buffer (>= 2048 keys agreeing in all depth bits above `shift`):
-                // order it completely with the block radix sort on the global ping-pong ranges (this tile's slice of
-                // keysA is free scratch after the partition), then composite it in LCAP-sized slices.
-                const uint32_t bs = sm.bucket_off[b + 1] - g0;
-                const uint64_t* sorted = lazy_global_sort(sm, gB + g0, const_cast<uint64_t*>(gA) + g0, bs);
-                for (uint32_t c0 = 0; c0 < bs && !all_done; c0 += LCAP) {
-                    const uint32_t m = min((uint32_t)LCAP, bs - c0);
-                    for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = sorted[c0 + i];
-                    __syncthreads();
-                    all_done = lazy_blend_group<KIND>(sm, ws, sm.keys[0], m, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
-                    __syncthreads();
-                }
-                b = b + 1;
-            } else {
-                const uint32_t m = sm.bucket_off[e] - g0;
-                if (m) {
-#pragma unroll 4
-                    for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = gB[g0 + i];
-                    __syncthreads();
-                    const int cur = lazy_sort_group(sm, m);
-                    all_done = lazy_blend_group<KIND>(sm, ws, sm.keys[cur], m, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
-                    __syncthreads();
-                }
-                b = e;
+        for (int u = 0; u < MU; u++) {
+            if (i0 + u * 256 < n) {
+                const uint32_t pos = atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+                gB[pos] = k[u];
             }
         }
     }
-    if (tid == 0 && consumed) atomicAdd(&ws.hdr->stats.reserved[0], consumed);
-    if (lane == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);   // (warp, splat) pairs that passed block_may_touch
+    __syncthreads();   // gB is read below by this CTA only
+    // ---- front-to-back over groups of buckets ----
+    int b = 0;
+    bool all_done = false;
+    while (b < 256 && !all_done) {
+        const uint32_t g0 = sm.bucket_off[b];
+        int e = b;
+        while (e < 256 && sm.bucket_off[e + 1] - g0 <= (uint32_t)LCAP) e++;
+        if (e == b) {
+            // one bucket larger than the shared buffer (>= 2048 keys agreeing in all depth bits above `shift`):
+            // order it completely with the block radix sort on the global ping-pong ranges (this tile's slice of
+            // keysA is free scratch after the partition), then hand it over in LCAP-sized slices.
+            const uint32_t bs = sm.bucket_off[b + 1] - g0;
+            const uint64_t* sorted = lazy_global_sort(sm, gB + g0, const_cast<uint64_t*>(gA) + g0, bs);
+            for (uint32_t c0 = 0; c0 < bs && !all_done; c0 += LCAP) {
+                const uint32_t m = min((uint32_t)LCAP, bs - c0);
+                for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = sorted[c0 + i];
+                __syncthreads();
+                all_done = consume(sm.keys[0], m, g0 + c0 + m == n);
+                __syncthreads();
+            }
+            b = b + 1;
+        } else {
+            const uint32_t m = sm.bucket_off[e] - g0;
+            if (m) {
+#pragma unroll 4
+                for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = gB[g0 + i];
+                __syncthreads();
+                const int cur = lazy_sort_group(sm, m);
+                all_done = consume(sm.keys[cur], m, g0 + m == n);
+                __syncthreads();
+            }
+            b = e;
+        }
+    }
+}
+
+template <int KIND, class PIX>
+__device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, const int tile, PIX& px, const float pixx,
+                                          const float pixy, const float blkx, const float blky, const int L1, const int L2) {
+    uint32_t consumed = 0, kept = 0;
+    lazy_for_each_group(sm, ws, tile, [&](const uint64_t* sk, uint32_t m, bool) {
+        return lazy_blend_group<KIND>(sm, ws, sk, m, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
+    });
+    if (threadIdx.x == 0 && consumed) atomicAdd(&ws.hdr->stats.reserved[0], consumed);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);   // (warp, splat) pairs that passed block_may_touch
+}
+
+// ---- training variant (SUM/forward.cu:298-430) on the lazy producer ---------------------------------------------------
+// The reference defines three things by its 256-entry batches at ABSOLUTE list positions: a batch is staged iff some pixel
+// is still live when it starts; every entry of a staged batch gets `gaussians_count += 1`; `n_contrib` is the 1-based
+// position of a pixel's last contributing entry.  So the sorted ids are appended to `point_list` (the backward walks that
+// prefix) as groups arrive, and batches are composited from there once complete (or once the list has ended).
+// `contributions[id] += alpha*T` per hit (one fp32 atomic per pixel hit in the reference) is summed over the warp, then
+// over the tile in shared memory, and leaves as one atomic per staged entry.
+struct SumSmemExtra {
+    float acc[256];
+    int ids[256];
+};
+
+__device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, const Workspace& ws, const FrameInputs& in,
+                                              const int tile, const bool inside, const float pixx, const float pixy,
+                                              const float blkx, const float blky, float& T, float& C0, float& C1, float& C2,
+                                              uint32_t& last_contributor) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t cap = ws.hdr->cap;
+    const uint32_t rbeg = min(ws.tile_offset[tile], cap), rend = min(ws.tile_offset[tile + 1], cap);
+    const uint32_t n = rend - rbeg;
+    uint32_t* __restrict__ plist = ws.point_list + rbeg;
+    uint32_t sorted_count = 0, next = 0, kept = 0;   // next = index of the next 256-batch to composite
+    bool done = !inside;
+    uint8_t* __restrict__ wl = sm.widx[warp];
+    lazy_for_each_group(sm, ws, tile, [&](const uint64_t* sk, uint32_t m, bool last) {
+        for (uint32_t i = tid; i < m; i += 256) plist[sorted_count + i] = (uint32_t)sk[i];
+        sorted_count += m;
+        __syncthreads();   // ids visible to the CTA; sk / sort scratch no longer needed
+        while ((next + 1) * 256u <= sorted_count || (last && next * 256u < n)) {
+            if (__syncthreads_count(done) == 256) return true;
+            const uint32_t b0 = next * 256u;
+            const int lim = (int)min(256u, n - b0);
+            if (tid < lim) {
+                const uint32_t id = plist[b0 + tid];
+                const float4* __restrict__ rec = ws.rec + (size_t)REC_PS1 * id;
+                sm.bl.sA[tid] = rec[0]; sm.bl.sB[tid] = rec[1]; sm.bl.sC[tid] = rec[2];
+                sx.ids[tid] = (int)id;
+                atomicAdd(&in.gaussians_count[id], 1);   // counted when the batch is staged, as in the reference
+            }
+            sx.acc[tid] = 0.0f;
+            __syncthreads();
+            next++;
+            if (!__all_sync(0xffffffffu, done)) {
+                uint32_t cnt = 0;
+                for (int jb = 0; jb < lim; jb += 32) {
+                    const int j = jb + lane;
+                    bool keep = false;
+                    if (j < lim) keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, sm.bl.sB[j].y, blkx, blky);
+                    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                    if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
+                    cnt += __popc(mk);
+                }
+                __syncwarp();
+                kept += cnt;
+                for (uint32_t k = 0; k < cnt; k++) {
+                    if (__all_sync(0xffffffffu, done)) break;
+                    const int j = wl[k];
+                    float w = 0.0f;
+                    if (!done) {
+                        const float4 a = sm.bl.sA[j];
+                        const float4 bq = sm.bl.sB[j];
+                        const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
+                        const float power = gauss_power(a.z, a.w, bq.x, dx, dy);
+                        if (!(power > 0.0f || power < -4.5f)) {
+                            const float alpha = fminf(0.99f, FM(bq.y, expf(power)));
+                            if (!(alpha < 1.0f / 255.0f)) {
+                                const float test_T = FM(T, FS(1.0f, alpha));
+                                if (test_T < 0.0001f) {
+                                    done = true;
+                                } else {
+                                    // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
+                                    const float4 c = sm.bl.sC[j];
+                                    w = FM(alpha, T);
+                                    C0 = FF(T, FM(alpha, c.x), C0);
+                                    C1 = FF(T, FM(alpha, c.y), C1);
+                                    C2 = FF(T, FM(alpha, c.z), C2);
+                                    T = test_T;
+                                    last_contributor = b0 + (uint32_t)j + 1u;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                    if (lane == 0 && w != 0.0f) atomicAdd(&sx.acc[j], w);
+                }
+            }
+            __syncthreads();
+            if (tid < lim && sx.acc[tid] != 0.0f) atomicAdd(&in.contributions[sx.ids[tid]], sx.acc[tid]);
+        }
+        return false;
+    });
+    if (tid == 0 && next) atomicAdd(&ws.hdr->stats.reserved[0], min(n, next * 256u));
+    if (lane == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);
 }
 
 template <int MODE>
@@ -571,6 +677,18 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
                 in.out_color[2 * HW + pix_id] = FF(A2, w1, FM(B2, w2));
             }
         }
+    } else if (MODE == MODE_SUM) {
+        SumSmemExtra& sx = *reinterpret_cast<SumSmemExtra*>(lazy_smem_raw + sizeof(LazySmem));
+        float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+        uint32_t last_contributor = 0;
+        lazy_tile_sum(sm, sx, ws, in, tile, inside, pixx, pixy, blkx, blky, T, C0, C1, C2, last_contributor);
+        if (inside) {
+            ws.final_T[pix_id] = T;
+            ws.n_contrib[pix_id] = last_contributor;
+            in.out_color[pix_id] = FF(bg0, T, C0);
+            in.out_color[HW + pix_id] = FF(bg1, T, C1);
+            in.out_color[2 * HW + pix_id] = FF(bg2, T, C2);
+        }
     } else {
         PixPS1 px;
         px.init(inside);
@@ -584,16 +702,19 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
 }
 
 cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T, Mode mode, cudaStream_t st) {
-    const size_t smem = sizeof(LazySmem);
+    const size_t smem = sizeof(LazySmem), smem_sum = sizeof(LazySmem) + sizeof(SumSmemExtra);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_lazy_blend<MODE_FOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_OBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
+        if (e != cudaSuccess) return e;
         configured = true;
     }
     if (mode == MODE_FOV) k_lazy_blend<MODE_FOV><<<T, 256, smem, st>>>(ws, in);
+    else if (mode == MODE_SUM) k_lazy_blend<MODE_SUM><<<T, 256, smem_sum, st>>>(ws, in);
     else k_lazy_blend<MODE_OBB><<<T, 256, smem, st>>>(ws, in);
     return cudaGetLastError();
 }
