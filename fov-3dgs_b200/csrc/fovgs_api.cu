@@ -24,7 +24,7 @@ int fovgs_version(void) { return FOVGS_VERSION; }
 
 size_t fovgs_workspace_bytes(int32_t P, int32_t W, int32_t H, int64_t max_instances, int32_t foveated, int32_t ps1_mode) {
     if (P < 0 || W <= 0 || H <= 0 || max_instances < 0) return 0;
-    const Mode mode = foveated ? MODE_FOV : (ps1_mode == FOVGS_PS1_SUM ? MODE_SUM : MODE_OBB);
+    const Mode mode = foveated ? MODE_FOV : (ps1_mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB);
     return carve_workspace(nullptr, P, W, H, max_instances, mode).total_bytes;
 }
 
@@ -67,8 +67,10 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
-    if (a->mode != FOVGS_PS1_OBB && a->mode != FOVGS_PS1_SUM) return fail(FOVGS_ERR_INVALID_ARG, "bad ps1 mode%s");
-    const Mode mode = a->mode == FOVGS_PS1_SUM ? MODE_SUM : MODE_OBB;
+    if (a->mode < FOVGS_PS1_OBB || a->mode > FOVGS_PS1_LWMC) return fail(FOVGS_ERR_INVALID_ARG, "bad ps1 mode%s");
+    const Mode mode = a->mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB;
+    if (a->mode == FOVGS_PS1_LWMC && !a->loss_map && a->P > 0)
+        return fail(FOVGS_ERR_INVALID_ARG, "the loss-weighted variant needs loss_map [H,W]%s");
     if (a->P < 0) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3)%s");
     if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
     if (a->P == 0) return 0;
@@ -78,7 +80,7 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     if (!a->colors_precomp && !(a->shs && a->M > 0))
         return fail(FOVGS_ERR_INVALID_ARG, "provide either shs (M>0) or colors_precomp%s");
     if (mode == MODE_SUM && (!a->gaussians_count || !a->contributions))
-        return fail(FOVGS_ERR_INVALID_ARG, "SUM mode needs gaussians_count and contributions%s");
+        return fail(FOVGS_ERR_INVALID_ARG, "the training variants need gaussians_count and contributions%s");
     if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
     Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, mode);
     if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
@@ -89,6 +91,8 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     in.means3D = a->means3D; in.opacities = a->opacities; in.scales = a->scales; in.rotations = a->rotations;
     in.cov3D_precomp = a->cov3D_precomp; in.shs = a->colors_precomp ? nullptr : a->shs; in.colors_precomp = a->colors_precomp;
     in.radii = a->radii; in.gaussians_count = a->gaussians_count; in.contributions = a->contributions;
+    in.loss_map = a->loss_map;
+    in.stat = a->mode == FOVGS_PS1_MAX ? STAT_MAX : (a->mode == FOVGS_PS1_LWMC ? STAT_LWMC : STAT_SUM);
     in.out_color = a->out_color; in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
     e = launch_forward(ws, in, W, H, mode, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_ps1");
@@ -153,7 +157,7 @@ int fovgs_fov_tile_tables(const void* workspace, int32_t W, int32_t H, float* ti
 int fovgs_ps1_geometry(const void* workspace, int32_t P, int32_t W, int32_t H, int32_t ps1_mode, float* means2D, float* depths,
                        float* conic, float* cov3D, float* rgb, void* stream) {
     if (!workspace) return fail(FOVGS_ERR_INVALID_ARG, "geometry: null workspace%s");
-    const Mode mode = ps1_mode == FOVGS_PS1_SUM ? MODE_SUM : MODE_OBB;
+    const Mode mode = ps1_mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB;
     // tile tables and per-Gaussian arrays do not depend on the instance capacity
     Workspace ws = carve_workspace(const_cast<void*>(workspace), P, W, H, 0, mode);
     cudaError_t e = launch_export_geometry(ws, P, mode, means2D, depths, conic, cov3D, rgb, nullptr, (cudaStream_t)stream);

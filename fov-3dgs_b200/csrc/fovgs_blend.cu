@@ -191,13 +191,18 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     fetch(tid);
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t contributor = 0, last_contributor = 0;
+    // training family: which statistics (fovgs_lazy.cu explains the three reference variants); this full-sort path keeps
+    // the reference's per-hit atomics — it serves parity runs (`out_point_list`), the lazy kernel is the fast one
+    const int stat = (MODE == MODE_SUM) ? in.stat : STAT_SUM;
+    int max_idx = 0;
+    float max_contrib = 0.0f;
     for (int i = 0; i < rounds; i++, toDo -= 256) {
         if (__syncthreads_count(done) == 256) break;
         if (pf.valid) {
             sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2];
             if (MODE == MODE_SUM) {
                 sId[tid] = (int)pf.id;
-                atomicAdd(&in.gaussians_count[pf.id], 1);   // counted when the batch is staged, as in the reference
+                if (stat != STAT_MAX) atomicAdd(&in.gaussians_count[pf.id], 1);   // counted when the batch is staged, as in the reference
             }
         }
         batches_done = i + 1;
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
             const float power = gauss_power(a.z, a.w, b.x, dx, dy);
             if (power > 0.0f || power < -4.5f) continue;
+            if (MODE == MODE_SUM && stat == STAT_MAX) atomicAdd(&in.gaussians_count[sId[j]], 1);
             const float alpha = fminf(0.99f, FM(b.y, expf(power)));
             if (alpha < 1.0f / 255.0f) continue;
             const float test_T = FM(T, FS(1.0f, alpha));
@@ -218,7 +224,10 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             if (MODE == MODE_SUM) {
                 // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
                 const float4 c = sC[j];
-                atomicAdd(&in.contributions[sId[j]], FM(alpha, T));
+                const float contrib = FM(alpha, T);
+                if (stat == STAT_SUM) atomicAdd(&in.contributions[sId[j]], contrib);
+                else if (stat == STAT_MAX) atomicMax(reinterpret_cast<unsigned*>(&in.contributions[sId[j]]), __float_as_uint(contrib));
+                else if (contrib > max_contrib) { max_contrib = contrib; max_idx = sId[j]; }
                 C0 = FF(T, FM(alpha, c.x), C0);
                 C1 = FF(T, FM(alpha, c.y), C1);
                 C2 = FF(T, FM(alpha, c.z), C2);
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
     if (inside) {
         if (MODE == MODE_SUM) {
+            if (stat == STAT_LWMC) atomicAdd(&in.contributions[max_idx], in.loss_map[pix_id]);
             ws.final_T[pix_id] = T;
             ws.n_contrib[pix_id] = last_contributor;
         }

@@ -528,15 +528,27 @@ __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, con
 // prefix) as groups arrive, and batches are composited from there once complete (or once the list has ended).
 // `contributions[id] += alpha*T` per hit (one fp32 atomic per pixel hit in the reference) is summed over the warp, then
 // over the tile in shared memory, and leaves as one atomic per staged entry.
+//
+// The pruning-metric variants keep different statistics on the same traversal (STAT):
+//   STAT_MAX  (pcheck_obb_max/forward.cu:381,400): `gaussians_count += 1` per (live pixel, entry) that passes the falloff
+//             cut — BEFORE the alpha test, so the block footprint test may only use the -4.5 bound — and
+//             `contributions = max(contributions, alpha*T)`.  alpha*T > 0, so the float maximum is the maximum of the bit
+//             patterns: warp `redux.max`, shared atomicMax, one global atomicMax per staged entry; counts likewise
+//             (ballot+popc, shared add, one global add).  Both are exact, hence bit-identical to the reference.
+//   STAT_LWMC (pcheck_obb_loss_weighted_max_count/forward.cu:347-348,403-410,435): counts as SUM; every pixel remembers the
+//             entry with its largest alpha*T (strict >, so the first maximum wins) and finally adds loss_map[pixel] to it —
+//             to Gaussian 0 when nothing contributed, as the reference does.
 struct SumSmemExtra {
     float acc[256];
     int ids[256];
+    int cnt[256];
 };
 
+template <int STAT>
 __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, const Workspace& ws, const FrameInputs& in,
                                               const int tile, const bool inside, const float pixx, const float pixy,
                                               const float blkx, const float blky, float& T, float& C0, float& C1, float& C2,
-                                              uint32_t& last_contributor) {
+                                              uint32_t& last_contributor, int& max_idx) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cap = ws.hdr->cap;
     const uint32_t rbeg = min(ws.tile_offset[tile], cap), rend = min(ws.tile_offset[tile + 1], cap);
@@ -544,6 +556,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
     uint32_t* __restrict__ plist = ws.point_list + rbeg;
     uint32_t sorted_count = 0, next = 0, kept = 0;   // next = index of the next 256-batch to composite
     bool done = !inside;
+    float max_contrib = 0.0f;   // STAT_LWMC
     uint8_t* __restrict__ wl = sm.widx[warp];
     lazy_for_each_group(sm, ws, tile, [&](const uint64_t* sk, uint32_t m, bool last) {
         for (uint32_t i = tid; i < m; i += 256) plist[sorted_count + i] = (uint32_t)sk[i];
@@ -558,9 +571,10 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                 const float4* __restrict__ rec = ws.rec + (size_t)REC_PS1 * id;
                 sm.bl.sA[tid] = rec[0]; sm.bl.sB[tid] = rec[1]; sm.bl.sC[tid] = rec[2];
                 sx.ids[tid] = (int)id;
-                atomicAdd(&in.gaussians_count[id], 1);   // counted when the batch is staged, as in the reference
+                if (STAT != STAT_MAX) atomicAdd(&in.gaussians_count[id], 1);   // counted when the batch is staged, as in the reference
             }
             sx.acc[tid] = 0.0f;
+            if (STAT == STAT_MAX) sx.cnt[tid] = 0;
             __syncthreads();
             next++;
             if (!__all_sync(0xffffffffu, done)) {
@@ -568,7 +582,8 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                 for (int jb = 0; jb < lim; jb += 32) {
                     const int j = jb + lane;
                     bool keep = false;
-                    if (j < lim) keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, sm.bl.sB[j].y, blkx, blky);
+                    // MAX counts entries that pass the falloff cut whatever their alpha: opacity 1 leaves only the -4.5 bound
+                    if (j < lim) keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, STAT == STAT_MAX ? 1.0f : sm.bl.sB[j].y, blkx, blky);
                     const unsigned mk = __ballot_sync(0xffffffffu, keep);
                     if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
                     cnt += __popc(mk);
@@ -579,12 +594,14 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     if (__all_sync(0xffffffffu, done)) break;
                     const int j = wl[k];
                     float w = 0.0f;
+                    bool in_cut = false;
                     if (!done) {
                         const float4 a = sm.bl.sA[j];
                         const float4 bq = sm.bl.sB[j];
                         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
                         const float power = gauss_power(a.z, a.w, bq.x, dx, dy);
                         if (!(power > 0.0f || power < -4.5f)) {
+                            in_cut = true;
                             const float alpha = fminf(0.99f, FM(bq.y, expf(power)));
                             if (!(alpha < 1.0f / 255.0f)) {
                                 const float test_T = FM(T, FS(1.0f, alpha));
@@ -603,13 +620,32 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                             }
                         }
                     }
+                    if (STAT == STAT_SUM) {
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-                    if (lane == 0 && w != 0.0f) atomicAdd(&sx.acc[j], w);
+                        for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                        if (lane == 0 && w != 0.0f) atomicAdd(&sx.acc[j], w);
+                    } else if (STAT == STAT_MAX) {
+                        const unsigned hits = __ballot_sync(0xffffffffu, in_cut);
+                        const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(w));   // w >= 0: bit order = value order
+                        if (lane == 0) {
+                            if (hits) atomicAdd(&sx.cnt[j], __popc(hits));
+                            if (wmax) atomicMax(reinterpret_cast<unsigned*>(&sx.acc[j]), wmax);
+                        }
+                    } else {
+                        if (w > max_contrib) { max_contrib = w; max_idx = sx.ids[j]; }
+                    }
                 }
             }
             __syncthreads();
-            if (tid < lim && sx.acc[tid] != 0.0f) atomicAdd(&in.contributions[sx.ids[tid]], sx.acc[tid]);
+            if (STAT == STAT_SUM) {
+                if (tid < lim && sx.acc[tid] != 0.0f) atomicAdd(&in.contributions[sx.ids[tid]], sx.acc[tid]);
+            } else if (STAT == STAT_MAX) {
+                if (tid < lim) {
+                    if (sx.cnt[tid]) atomicAdd(&in.gaussians_count[sx.ids[tid]], sx.cnt[tid]);
+                    const unsigned m = __float_as_uint(sx.acc[tid]);
+                    if (m) atomicMax(reinterpret_cast<unsigned*>(&in.contributions[sx.ids[tid]]), m);
+                }
+            }
         }
         return false;
     });
@@ -617,7 +653,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
     if (lane == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);
 }
 
-template <int MODE>
+template <int MODE, int STAT = STAT_SUM>
 __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs in) {
     extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
     LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
@@ -681,8 +717,10 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
         SumSmemExtra& sx = *reinterpret_cast<SumSmemExtra*>(lazy_smem_raw + sizeof(LazySmem));
         float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
         uint32_t last_contributor = 0;
-        lazy_tile_sum(sm, sx, ws, in, tile, inside, pixx, pixy, blkx, blky, T, C0, C1, C2, last_contributor);
+        int max_idx = 0;
+        lazy_tile_sum<STAT>(sm, sx, ws, in, tile, inside, pixx, pixy, blkx, blky, T, C0, C1, C2, last_contributor, max_idx);
         if (inside) {
+            if (STAT == STAT_LWMC) atomicAdd(&in.contributions[max_idx], in.loss_map[pix_id]);
             ws.final_T[pix_id] = T;
             ws.n_contrib[pix_id] = last_contributor;
             in.out_color[pix_id] = FF(bg0, T, C0);
@@ -709,12 +747,18 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_OBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
+        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_LWMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (mode == MODE_FOV) k_lazy_blend<MODE_FOV><<<T, 256, smem, st>>>(ws, in);
-    else if (mode == MODE_SUM) k_lazy_blend<MODE_SUM><<<T, 256, smem_sum, st>>>(ws, in);
+    else if (mode == MODE_SUM && in.stat == STAT_MAX) k_lazy_blend<MODE_SUM, STAT_MAX><<<T, 256, smem_sum, st>>>(ws, in);
+    else if (mode == MODE_SUM && in.stat == STAT_LWMC) k_lazy_blend<MODE_SUM, STAT_LWMC><<<T, 256, smem_sum, st>>>(ws, in);
+    else if (mode == MODE_SUM) k_lazy_blend<MODE_SUM, STAT_SUM><<<T, 256, smem_sum, st>>>(ws, in);
     else k_lazy_blend<MODE_OBB><<<T, 256, smem, st>>>(ws, in);
     return cudaGetLastError();
 }

@@ -1,6 +1,8 @@
-"""Import-only stand-in: fov3dgs/gaussian_wrapper.py:2-7 imports this package at module import time, but it is a
-pruning-metric / vanilla variant outside the hot path of this round (SURVEY.md §8f "next")."""
-from fovgs.surface import make_unavailable_api as _make
+"""Drop-in for the reference package of the same name (PS=1 pruning metric "max": forward with per-(pixel, Gaussian) hit
+counts and the maximum alpha*T per Gaussian, SUM's backward; reference:
+fov3dgs/submodules/diff-gaussian-rasterization_pcheck_obb_max/diff_gaussian_rasterization_pcheck_obb_max/__init__.py,
+cuda_rasterizer/forward.cu:381,400)."""
+from fovgs.surface import make_max_api as _make
 
-globals().update(_make("diff_gaussian_rasterization_pcheck_obb_max", "pruning-metric / vanilla variants are scheduled after the hot path (SURVEY.md section 8f)"))
+globals().update(_make())
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]

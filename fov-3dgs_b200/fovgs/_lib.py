@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfovgs.so")
 
 FOVGS_PS1_OBB = 0
 FOVGS_PS1_SUM = 1
+FOVGS_PS1_MAX = 2
+FOVGS_PS1_LWMC = 3
 
 _f = C.c_void_p  # all device pointers travel as void*
 
@@ -91,6 +93,7 @@ class Ps1FwdArgs(C.Structure):
         ("max_instances", C.c_int64),
         ("out_point_list", _f),
         ("out_ranges", _f),
+        ("loss_map", _f),
     ]
 
 

@@ -21,6 +21,11 @@ from . import _lib
 from ._lib import Camera, FovFwdArgs, FrameStats, Ps1BwdArgs, Ps1FwdArgs, check, lib
 
 MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
+# pruning-metric variants of the training rasterizer: SUM's workspace layout and backward, other statistics
+MODE_MAX, MODE_LWMC = 3, 4
+_TRAIN_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC)
+_PS1_ABI_MODE = {MODE_OBB: _lib.FOVGS_PS1_OBB, MODE_SUM: _lib.FOVGS_PS1_SUM, MODE_MAX: _lib.FOVGS_PS1_MAX,
+                 MODE_LWMC: _lib.FOVGS_PS1_LWMC}
 _DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
 
 
@@ -122,7 +127,7 @@ def _initial_capacity(P):
 
 
 def _new_workspace(device, mode, P, W, H, cap):
-    nbytes = lib().fovgs_workspace_bytes(P, W, H, cap, 1 if mode == MODE_FOV else 0, 1 if mode == MODE_SUM else 0)
+    nbytes = lib().fovgs_workspace_bytes(P, W, H, cap, 1 if mode == MODE_FOV else 0, 1 if mode in _TRAIN_MODES else 0)
     if nbytes == 0:
         raise RuntimeError("fovgs_workspace_bytes rejected the frame configuration")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -261,8 +266,8 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
 
 
 def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs, colors_precomp, raster_settings,
-                want_lists=False):
-    """PS=1 forward (mode = MODE_OBB | MODE_SUM).
+                want_lists=False, loss_map=None):
+    """PS=1 forward (mode = MODE_OBB | MODE_SUM | MODE_MAX | MODE_LWMC; `loss_map` [H,W] for MODE_LWMC).
     Returns (num_rendered, color, radii, workspace_item[, gaussians_count, contributions][, point_list, ranges])."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -270,7 +275,7 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
     rs = raster_settings
     H, W = int(rs.image_height), int(rs.image_width)
     P = means3D.size(0)
-    sum_mode = mode == MODE_SUM
+    sum_mode = mode in _TRAIN_MODES
     if P == 0:
         z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
         r = torch.zeros((0,), dtype=torch.int32, device=device)
@@ -287,6 +292,10 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
     shs = _prep(shs, "shs", device, optional=True)
     colors_precomp = _prep(colors_precomp, "colors_precomp", device, optional=True)
     M = 0 if shs is None else int(shs.size(1))
+    if mode == MODE_LWMC:
+        loss_map = _prep(loss_map, "loss_map", device)
+        if loss_map.numel() != H * W:
+            raise RuntimeError("loss_map must have image_height * image_width elements")
     cam = _camera(rs, device, keep)
     color = torch.empty((3, H, W), dtype=torch.float32, device=device)
     radii = torch.empty((P,), dtype=torch.int32, device=device)
@@ -298,7 +307,8 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
     def launch(item, stream):
         a = Ps1FwdArgs()
         a.cam = cam
-        a.mode = _lib.FOVGS_PS1_SUM if sum_mode else _lib.FOVGS_PS1_OBB
+        a.mode = _PS1_ABI_MODE[mode]
+        a.loss_map = loss_map.data_ptr() if mode == MODE_LWMC else None
         a.P = P
         a.M = M
         a.means3D = means3D.data_ptr()
@@ -435,8 +445,8 @@ def geometry(item, mode, P, W, H):
         return {"means2D": means2D, "depths": depths, "conic": conic, "level_colors": lc}
     cov3D = torch.zeros((P, 6), **opts)
     rgb = torch.zeros((P, 3), **opts)
-    check(lib().fovgs_ps1_geometry(item["ws"].data_ptr(), P, W, H, 1 if mode == MODE_SUM else 0, means2D.data_ptr(),
-                                   depths.data_ptr(), conic.data_ptr(), cov3D.data_ptr() if mode == MODE_SUM else None,
+    check(lib().fovgs_ps1_geometry(item["ws"].data_ptr(), P, W, H, 1 if mode in _TRAIN_MODES else 0, means2D.data_ptr(),
+                                   depths.data_ptr(), conic.data_ptr(), cov3D.data_ptr() if mode in _TRAIN_MODES else None,
                                    rgb.data_ptr(), stream), "fovgs_ps1_geometry")
     return {"means2D": means2D, "depths": depths, "conic": conic, "cov3D": cov3D, "rgb": rgb}
 

@@ -132,22 +132,28 @@ def make_fov_api():
 # ------------------------------------------------------------------------------------------------------------
 # PS=1: inference (pcheck_obb) and training (pcheck_obb_sum)
 # ------------------------------------------------------------------------------------------------------------
-def _make_ps1_function(sum_mode: bool):
-    mode = ops.MODE_SUM if sum_mode else ops.MODE_OBB
+def _make_ps1_function(mode: int):
+    """mode: ops.MODE_OBB (inference) or one of the training family ops.MODE_SUM / MODE_MAX / MODE_LWMC.  The
+    loss-weighted variant takes one more argument, `loss_map`, after `raster_settings`
+    (.../pcheck_obb_loss_weighted_max_count/diff_gaussian_rasterization_pcheck_obb_loss_weighted_max_count/__init__.py:24-47)."""
+    sum_mode = mode != ops.MODE_OBB
+    with_loss_map = mode == ops.MODE_LWMC
 
     class _RasterizeGaussians(torch.autograd.Function):
         @staticmethod
         def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    raster_settings):
+                    raster_settings, *extra):
+            loss_map = extra[0] if with_loss_map else None
             args = (raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations,
                     raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
                     raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy,
                     raster_settings.image_height, raster_settings.image_width, sh, raster_settings.sh_degree,
-                    raster_settings.campos, raster_settings.prefiltered, raster_settings.debug)
+                    raster_settings.campos, raster_settings.prefiltered) + \
+                   ((loss_map,) if with_loss_map else ()) + (raster_settings.debug,)
 
             def run():
                 return ops.forward_ps1(mode, means3D, opacities, scales, rotations, cov3Ds_precomp, sh, colors_precomp,
-                                       raster_settings)
+                                       raster_settings, loss_map=loss_map)
 
             if raster_settings.debug:
                 cpu_args = cpu_deep_copy_tuple(args)
@@ -203,13 +209,42 @@ def _make_ps1_function(sum_mode: bool):
             (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
              grad_rotations) = res
             return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
-                    grad_rotations, grad_cov3Ds_precomp, None)
+                    grad_rotations, grad_cov3Ds_precomp, None) + ((None,) if with_loss_map else ())
 
     return _RasterizeGaussians
 
 
-def _make_ps1_api(sum_mode: bool):
-    Fn = _make_ps1_function(sum_mode)
+def _make_ps1_api(mode: int):
+    Fn = _make_ps1_function(mode)
+
+    if mode == ops.MODE_LWMC:
+        def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                raster_settings, loss_map):
+            return Fn.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                            raster_settings, loss_map)
+
+        class GaussianRasterizer(nn.Module):
+            def __init__(self, raster_settings):
+                super().__init__()
+                self.raster_settings = raster_settings
+
+            def markVisible(self, positions):
+                return _mark_visible(self.raster_settings, positions)
+
+            def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                        cov3D_precomp=None, loss_map=None):
+                _check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+                return rasterize_gaussians(means3D, means2D, _empty_if_none(shs), _empty_if_none(colors_precomp),
+                                           opacities, _empty_if_none(scales), _empty_if_none(rotations),
+                                           _empty_if_none(cov3D_precomp), self.raster_settings, loss_map)
+
+        return {
+            "GaussianRasterizationSettings": GaussianRasterizationSettings,
+            "GaussianRasterizer": GaussianRasterizer,
+            "rasterize_gaussians": rasterize_gaussians,
+            "_RasterizeGaussians": Fn,
+            "cpu_deep_copy_tuple": cpu_deep_copy_tuple,
+        }
 
     def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                             raster_settings):
@@ -241,11 +276,19 @@ def _make_ps1_api(sum_mode: bool):
 
 
 def make_obb_api():
-    return _make_ps1_api(False)
+    return _make_ps1_api(ops.MODE_OBB)
 
 
 def make_sum_api():
-    return _make_ps1_api(True)
+    return _make_ps1_api(ops.MODE_SUM)
+
+
+def make_max_api():
+    return _make_ps1_api(ops.MODE_MAX)
+
+
+def make_lwmc_api():
+    return _make_ps1_api(ops.MODE_LWMC)
 
 
 def make_unavailable_api(pkg, why):

@@ -10,6 +10,8 @@ The resulting modules are the reference's pybind ``_C`` modules:
   ref_fov_C : rasterize_gaussians(24 args), mark_visible      (FOV/rasterize_points.h:17-44, FOV/ext.cpp:15-18)
   ref_obb_C : rasterize_gaussians(19 args), rasterize_gaussians_backward, mark_visible
   ref_sum_C : rasterize_gaussians(19 args) -> 8-tuple, rasterize_gaussians_backward(21 args), mark_visible
+  ref_max_C / ref_lwmc_C : as ref_sum_C (lwmc: 20 args, loss_map before debug)
+  ref_naive_C / ref_mmfr_C : the SMFR / MMFR foveation baselines (23 args; mmfr takes cur_level instead of highest_levels)
 
 Nothing in the product path imports these.  Only tests/, bench.py --impl reference and tools/make_golden.py do.
 """
@@ -28,6 +30,11 @@ VARIANTS = {
     "ref_fov_C": ("diff-gaussian-rasterization_fov_pcheck_obb", False),
     "ref_obb_C": ("diff-gaussian-rasterization_pcheck_obb", True),
     "ref_sum_C": ("diff-gaussian-rasterization_pcheck_obb_sum", True),
+    # SURVEY.md §8f "next" rows: pruning-metric variants and the two foveation baselines
+    "ref_max_C": ("diff-gaussian-rasterization_pcheck_obb_max", True),
+    "ref_lwmc_C": ("diff-gaussian-rasterization_pcheck_obb_loss_weighted_max_count", True),
+    "ref_naive_C": ("diff-gaussian-rasterization_naive_pcheck_obb", False),
+    "ref_mmfr_C": ("diff-gaussian-rasterization_mmfr_pcheck_obb", False),
 }
 
 

@@ -440,6 +440,13 @@ static inline void atomic_add_f32(float* p, float v) {
     while (!__atomic_compare_exchange_n((uint32_t*)p, &old, neu, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
 }
 
+/* atomicMaxFloat of the MAX variant (pcheck_obb_max/cuda_rasterizer/auxiliary.h:41-50): CAS loop around fmaxf */
+static inline void atomic_max_f32(float* p, float v) {
+    uint32_t old = __atomic_load_n((uint32_t*)p, __ATOMIC_RELAXED), neu;
+    do { float f; memcpy(&f, &old, 4); f = fmaxf(v, f); memcpy(&neu, &f, 4); }
+    while (!__atomic_compare_exchange_n((uint32_t*)p, &old, neu, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+
 static inline float gauss_power(float conx, float cony, float conz, float dx, float dy) {
     const float a = dy * (dy * conz);
     const float s = fmaf(dx, dx * conx, a);
@@ -450,7 +457,7 @@ static inline float gauss_power(float conx, float cony, float conz, float dx, fl
 typedef struct {
     const orc_camera* cam; int mode, W, H, gx; const uint32_t* rng; const inst_t* inst; const splat_t* sp;
     const float* opacity; const float* rgb; int* gaussians_count; float* contributions; float* final_T; uint32_t* n_contrib;
-    float* out_color;
+    float* out_color; const float* loss_map;
 } ps1_blend_ctx;
 static void blend_tile_ps1(void* vctx, int tile) {
     const ps1_blend_ctx* c = (const ps1_blend_ctx*)vctx;
@@ -464,9 +471,14 @@ static void blend_tile_ps1(void* vctx, int tile) {
         const uint32_t r0 = rng[2 * tile], r1 = rng[2 * tile + 1];
         const int total = (int)(r1 - r0);
         float Tt[256], C[256][3]; uint8_t done[256]; uint32_t contributor[256], last[256];
+        /* LWMC: per pixel the Gaussian with the largest alpha*T so far (strict >, first wins), id 0 if none
+           (pcheck_obb_loss_weighted_max_count/cuda_rasterizer/forward.cu:347-348,403-408) */
+        int max_idx[256]; float max_contrib[256];
+        const float* loss_map = c->loss_map;
         int ndone = 0;
         for (int t = 0; t < 256; t++) {
             const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
+            max_idx[t] = 0; max_contrib[t] = 0.0f;
             Tt[t] = 1.0f; C[t][0] = C[t][1] = C[t][2] = 0; contributor[t] = last[t] = 0;
             done[t] = !(px < W && py < H); ndone += done[t];
         }
@@ -475,7 +487,7 @@ static void blend_tile_ps1(void* vctx, int tile) {
         for (int b = 0; b < rounds; b++, toDo -= 256) {
             if (ndone == 256) break;
             const int lim = toDo < 256 ? toDo : 256;
-            if (mode == 1)
+            if (mode == 1 || mode == 3)   /* SUM, LWMC: counted when the batch is staged (SUM/forward.cu:361) */
                 for (int j = 0; j < lim; j++) {
                     const uint32_t id = o.inst[r0 + (size_t)b * 256 + j].id;
                     __atomic_fetch_add(&gaussians_count[id], 1, __ATOMIC_RELAXED);
@@ -490,12 +502,17 @@ static void blend_tile_ps1(void* vctx, int tile) {
                     const float dx = s->px - pxf, dy = s->py - pyf;
                     const float power = gauss_power(s->conx, s->cony, s->conz, dx, dy);
                     if (power > 0.0f || power < -4.5f) continue;
+                    /* MAX: one count per (pixel, Gaussian) that passes the falloff cut (pcheck_obb_max/forward.cu:381) */
+                    if (mode == 2) __atomic_fetch_add(&gaussians_count[id], 1, __ATOMIC_RELAXED);
                     const float alpha = fminf(0.99f, opacity[id] * expf(power));
                     if (alpha < 1.0f / 255.0f) continue;
                     const float test_T = Tt[t] * (1 - alpha);
                     if (test_T < 0.0001f) { done[t] = 1; ndone++; continue; }
-                    if (mode == 1) {
-                        atomic_add_f32(&contributions[id], alpha * Tt[t]);
+                    if (mode >= 1) {
+                        const float contrib = alpha * Tt[t];
+                        if (mode == 1) atomic_add_f32(&contributions[id], contrib);
+                        else if (mode == 2) atomic_max_f32(&contributions[id], contrib);   /* pcheck_obb_max/forward.cu:400 */
+                        else if (contrib > max_contrib[t]) { max_contrib[t] = contrib; max_idx[t] = (int)id; }
                         for (int ch = 0; ch < 3; ch++) C[t][ch] = fmaf(Tt[t], alpha * rgb[3 * id + ch], C[t][ch]);
                     } else {
                         const float w = alpha * Tt[t];
@@ -510,6 +527,8 @@ static void blend_tile_ps1(void* vctx, int tile) {
             const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
             if (!(px < W && py < H)) continue;
             const size_t pid = (size_t)W * py + px;
+            /* LWMC: the pixel's loss goes to its max contributor — Gaussian 0 when nothing contributed (forward.cu:435) */
+            if (mode == 3 && loss_map) atomic_add_f32(&contributions[max_idx[t]], loss_map[pid]);
             if (final_T) final_T[pid] = Tt[t];
             if (n_contrib) n_contrib[pid] = last[t];
             for (int ch = 0; ch < 3; ch++) out_color[(size_t)ch * H * W + pid] = fmaf(cam->bg[ch], Tt[t], C[t][ch]);
@@ -517,17 +536,19 @@ static void blend_tile_ps1(void* vctx, int tile) {
 }
 
 /* =================================================================================================================
- * PS=1 forward (mode 0 = pcheck_obb, 1 = pcheck_obb_sum).  All pointers are host memory.  Optional outputs may be NULL.
+ * PS=1 forward (mode 0 = pcheck_obb, 1 = pcheck_obb_sum, 2 = pcheck_obb_max, 3 = pcheck_obb_loss_weighted_max_count;
+ * modes 1-3 share everything but the per-Gaussian statistics of the blend).  All pointers are host memory.  Optional
+ * outputs may be NULL; `loss_map` [H*W] is read by mode 3 only.
  * ================================================================================================================= */
 int64_t orc_forward_ps1(const orc_camera* cam, int mode, int P, int M, const float* means3D, const float* opacity,
                         const float* scales, const float* rot, const float* shs, float* out_color, int* radii,
                         int* gaussians_count, float* contributions, float* means2D, float* depths, float* conic,
                         float* cov3D, float* rgb_out, uint8_t* clamped_out, uint32_t* point_list, int64_t list_cap,
-                        uint32_t* ranges, float* final_T, uint32_t* n_contrib) {
+                        uint32_t* ranges, float* final_T, uint32_t* n_contrib, const float* loss_map) {
     const int W = cam->W, H = cam->H, gx = (W + 15) / 16, gy = (H + 15) / 16, T = gx * gy;
     const float fy = H / (2.0f * cam->tanfovy), fx = W / (2.0f * cam->tanfovx);
     bin_in_t in; memset(&in, 0, sizeof(in));
-    in.mode = mode; in.cam = cam; in.P = P; in.M = M; in.means3D = means3D; in.opacity = opacity; in.scales = scales; in.rot = rot; in.shs = shs;
+    in.mode = mode >= 1 ? 1 : 0; in.cam = cam; in.P = P; in.M = M; in.means3D = means3D; in.opacity = opacity; in.scales = scales; in.rot = rot; in.shs = shs;
     bin_out_t o; memset(&o, 0, sizeof(o));
     o.sp = (splat_t*)calloc((size_t)P + 1, sizeof(splat_t)); o.vis = (uint8_t*)calloc((size_t)P + 1, 1);
     o.radii = radii; o.cov3d = (float*)calloc((size_t)P * 6 + 6, sizeof(float));
@@ -560,7 +581,7 @@ int64_t orc_forward_ps1(const orc_camera* cam, int mode, int P, int M, const flo
     /* blend: one 16x16 tile per work item, 256-entry batches with the block-wide "all done" vote
        (OBB/forward.cu:251-384, SUM/forward.cu:298-430) */
     {
-        ps1_blend_ctx bc = {cam, mode, W, H, gx, rng, o.inst, o.sp, opacity, rgb, gaussians_count, contributions, final_T, n_contrib, out_color};
+        ps1_blend_ctx bc = {cam, mode, W, H, gx, rng, o.inst, o.sp, opacity, rgb, gaussians_count, contributions, final_T, n_contrib, out_color, loss_map};
         run_tiles(blend_tile_ps1, &bc, T);
     }
     free(o.sp); free(o.vis); free(o.cov3d); free(o.inst); free(rgb); free(clamped); free(rng);

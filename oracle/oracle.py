@@ -60,9 +60,13 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def forward_ps1(scene, cam, mode="obb", bg=(0.0, 0.0, 0.0), list_cap=None):
-    """mode: 'obb' | 'sum'.  Returns dict with color, radii, num_rendered, point_list, ranges, means2D, depths, conic,
-    cov3D, rgb, clamped (+ gaussians_count, contributions, final_T, n_contrib for 'sum')."""
+PS1_MODES = {"obb": 0, "sum": 1, "max": 2, "lwmc": 3}
+
+
+def forward_ps1(scene, cam, mode="obb", bg=(0.0, 0.0, 0.0), list_cap=None, loss_map=None):
+    """mode: 'obb' | 'sum' | 'max' | 'lwmc' (loss_map [H,W] required).  Returns dict with color, radii, num_rendered,
+    point_list, ranges, means2D, depths, conic, cov3D, rgb, clamped (+ gaussians_count, contributions, final_T,
+    n_contrib for the training-family modes)."""
     L = lib()
     P = scene["means3D"].shape[0]
     M = scene["shs"].shape[1]
@@ -79,10 +83,15 @@ def forward_ps1(scene, cam, mode="obb", bg=(0.0, 0.0, 0.0), list_cap=None):
         "final_T": np.zeros(H * W, np.float32), "n_contrib": np.zeros(H * W, np.uint32),
     }
     ins = [_f32(scene["means3D"]), _f32(scene["opacity"]), _f32(scene["scales"]), _f32(scene["rotations"]), _f32(scene["shs"])]
-    n = L.orc_forward_ps1(C.byref(c), 1 if mode == "sum" else 0, P, M, *[_p(a) for a in ins], _p(o["color"]), _p(o["radii"]),
+    if mode == "lwmc" and loss_map is None:
+        raise ValueError("mode 'lwmc' needs loss_map")
+    lm = None if loss_map is None else _f32(np.asarray(loss_map).reshape(-1))
+    if lm is not None and lm.size != H * W:
+        raise ValueError("loss_map must have H*W elements")
+    n = L.orc_forward_ps1(C.byref(c), PS1_MODES[mode], P, M, *[_p(a) for a in ins], _p(o["color"]), _p(o["radii"]),
                           _p(o["gaussians_count"]), _p(o["contributions"]), _p(o["means2D"]), _p(o["depths"]), _p(o["conic"]),
                           _p(o["cov3D"]), _p(o["rgb"]), _p(o["clamped"]), _p(o["point_list"]), C.c_int64(cap), _p(o["ranges"]),
-                          _p(o["final_T"]), _p(o["n_contrib"]))
+                          _p(o["final_T"]), _p(o["n_contrib"]), _p(lm))
     o["num_rendered"] = int(n)
     o["point_list"] = o["point_list"][: min(n, cap)]
     return o

@@ -45,12 +45,15 @@ def fov_forward(mod, sc, cam, gaze, alpha=0.05, blending=True, bg=None, debug=Fa
         cam["campos"], False, debug)
 
 
-def ps1_forward(mod, sc, cam, bg=None, debug=False):
+def ps1_forward(mod, sc, cam, bg=None, debug=False, loss_map=None):
+    """`loss_map` (CUDA [H,W]) only for ref_lwmc_C, whose pybind signature takes it between `prefiltered` and `debug`
+    (.../pcheck_obb_loss_weighted_max_count/rasterize_points.cu:35-57)."""
     bg = bg if bg is not None else torch.zeros(3, device="cuda")
+    tail = (False, debug) if loss_map is None else (False, loss_map, debug)
     return mod.rasterize_gaussians(
         bg, sc["means3D"], _empty(), sc["opacity"], sc["scales"], sc["rotations"], 1.0, _empty(), cam["viewmatrix"],
         cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], cam["image_height"], cam["image_width"], sc["shs"],
-        sc["sh_degree"], cam["campos"], False, debug)
+        sc["sh_degree"], cam["campos"], *tail)
 
 
 def ps1_backward(mod, sc, cam, radii, grad_out, geom, num_rendered, binning, img, bg=None, debug=False):

@@ -31,7 +31,8 @@ def test_fov_signatures_match_reference():
         "shs_dcs", "highest_levels", "gazeArray", "alpha", "blending"]
 
 
-@pytest.mark.parametrize("name", ["diff_gaussian_rasterization_pcheck_obb", "diff_gaussian_rasterization_pcheck_obb_sum"])
+@pytest.mark.parametrize("name", ["diff_gaussian_rasterization_pcheck_obb", "diff_gaussian_rasterization_pcheck_obb_sum",
+                                  "diff_gaussian_rasterization_pcheck_obb_max"])
 def test_ps1_signatures_match_reference(name):
     m = importlib.import_module(name)
     assert list(inspect.signature(m.rasterize_gaussians).parameters) == [
@@ -39,6 +40,16 @@ def test_ps1_signatures_match_reference(name):
     assert list(inspect.signature(m.GaussianRasterizer.forward).parameters) == [
         "self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp"]
     assert hasattr(m.GaussianRasterizer, "markVisible")
+
+
+def test_loss_weighted_signature_matches_reference():
+    """.../pcheck_obb_loss_weighted_max_count/.../__init__.py:24-36,198: `loss_map` is the last argument."""
+    m = importlib.import_module("diff_gaussian_rasterization_pcheck_obb_loss_weighted_max_count")
+    assert list(inspect.signature(m.rasterize_gaussians).parameters) == [
+        "means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp", "raster_settings",
+        "loss_map"]
+    assert list(inspect.signature(m.GaussianRasterizer.forward).parameters) == [
+        "self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp", "loss_map"]
 
 
 def _settings(m):
@@ -68,7 +79,7 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
 
 
 def test_non_hot_path_variants_explain_themselves():
-    m = importlib.import_module("diff_gaussian_rasterization_pcheck_obb_max")
+    m = importlib.import_module("diff_gaussian_rasterization")
     with pytest.raises(NotImplementedError):
         m.GaussianRasterizer(raster_settings=None)
 

@@ -139,26 +139,36 @@ def run_fov(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
         print(json.dumps({k: v for k, v in rep.items() if k != "trace"}), flush=True)
 
 
+PS1_VARIANTS = {"obb": ("ref_obb_C", ops.MODE_OBB), "sum": ("ref_sum_C", ops.MODE_SUM), "max": ("ref_max_C", ops.MODE_MAX),
+                "lwmc": ("ref_lwmc_C", ops.MODE_LWMC)}
+
+
 def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
-    sum_mode = variant == "sum"
-    mod = ref_api.ref_module("ref_sum_C" if sum_mode else "ref_obb_C")
+    sum_mode = variant != "obb"          # the training family: sum / max / lwmc
+    mod = ref_api.ref_module(PS1_VARIANTS[variant][0])
     sc = to_cuda(scn)
     c = to_cuda(cam)
     W, H = cam["image_width"], cam["image_height"]
     P = sc["means3D"].shape[0]
     bg = torch.zeros(3, device="cuda")
     rs = settings(c, sc["sh_degree"], bg)
-    mode = ops.MODE_SUM if sum_mode else ops.MODE_OBB
+    mode = PS1_VARIANTS[variant][1]
     rep = {"variant": variant, "tag": tag, "P": P, "W": W, "H": H}
+    loss_map = None
+    if variant == "lwmc":
+        loss_map = torch.from_numpy(np.random.default_rng(17).random((H, W)).astype(np.float32)).cuda()
     try:
-        res = ref_api.ps1_forward(mod, sc, c)
+        if mod is None:
+            raise RuntimeError(f"reference module {PS1_VARIANTS[variant][0]} is not built")
+        res = ref_api.ps1_forward(mod, sc, c, loss_map=loss_map)
         torch.cuda.synchronize()
         n_r, col_r, rad_r, geom, binning, img = res[:6]
         gr = ref_api.decode_geom(geom, P, "ps1")
         br = ref_api.decode_binning(binning, n_r)
         ir = ref_api.decode_img(img, W, H)
         ref = {"n": n_r, "color": col_r, "radii": rad_r, "point_list": br["point_list"], "ranges": ir["ranges"]}
-        out = ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs, want_lists=True)
+        out = ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs, want_lists=True,
+                              loss_map=loss_map)
         torch.cuda.synchronize()
         n_o, col_o, rad_o, item = out[:4]
         pl_o, rg_o = out[-2], out[-1]
@@ -177,22 +187,33 @@ def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
             rep["contrib_max_rel"] = float(((ct_r - ct_o).abs() / (ct_r.abs() + 1e-6)).max().item())
             rep["cov3D_bit_mismatch"] = mism(gr["cov3D"], go["cov3D"], vis)
             rep["n_contrib_mismatch"] = None
+            # the lazy (consumption-driven) training kernel: same statistics, same image, same saved state
+            lz = ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs,
+                                 loss_map=loss_map)
+            torch.cuda.synchronize()
+            rep["lazy_img_max_abs"] = float((lz[1] - col_r).abs().max().item())
+            rep["lazy_gaussians_count_mismatch"] = int((gc_r != lz[4]).sum().item())
+            rep["lazy_contrib_max_rel"] = float(((ct_r - lz[5]).abs() / (ct_r.abs() + 1e-6)).max().item())
+            rep["lazy_contrib_bit_mismatch"] = mism(ct_r, lz[5])
+            rep["contrib_bit_mismatch"] = mism(ct_r, ct_o)
             # backward
             grad_out = torch.from_numpy(np.random.default_rng(3).standard_normal((3, H, W)).astype(np.float32)).cuda()
             g_ref = ref_api.ps1_backward(mod, sc, c, rad_r, grad_out, geom, n_r, binning, img)
             g_our = ops.backward_ps1(item, sc["means3D"], rad_o, sc["scales"], sc["rotations"], None, sc["shs"], None, rs, grad_out)
+            g_lazy = ops.backward_ps1(lz[3], sc["means3D"], lz[2], sc["scales"], sc["rotations"], None, sc["shs"], None, rs, grad_out)
             torch.cuda.synchronize()
             names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
             gcmp = {}
-            for nm, a, b in zip(names, g_ref, g_our):
+            for nm, a, b, l in zip(names, g_ref, g_our, g_lazy):
                 num = (a - b).norm().item(); den = a.norm().item()
-                gcmp[nm] = {"rel_l2": num / (den + 1e-30), "max_abs": float((a - b).abs().max().item()), "ref_max": float(a.abs().max().item())}
+                gcmp[nm] = {"rel_l2": num / (den + 1e-30), "max_abs": float((a - b).abs().max().item()), "ref_max": float(a.abs().max().item()),
+                            "lazy_rel_l2": (a - l).norm().item() / (den + 1e-30)}
             rep["grads"] = gcmp
             if do_time:
                 rep["time_bwd_ref"] = time_fn(lambda: ref_api.ps1_backward(mod, sc, c, rad_r, grad_out, geom, n_r, binning, img), 3, 10)
                 rep["time_bwd_ours"] = time_fn(lambda: ops.backward_ps1(item, sc["means3D"], rad_o, sc["scales"], sc["rotations"], None, sc["shs"], None, rs, grad_out), 3, 10)
             if golden_dir:
-                np.savez_compressed(os.path.join(golden_dir, f"sum_{tag}_bwd.npz"), grad_seed=np.int64(3), numpy_grad=np.int64(1),
+                np.savez_compressed(os.path.join(golden_dir, f"{variant}_{tag}_bwd.npz"), grad_seed=np.int64(3), numpy_grad=np.int64(1),
                                     **{nm: a.cpu().numpy() for nm, a in zip(names, g_ref)})
         rep["stats"] = dict(ops.last_stats)
         if golden_dir:
@@ -200,13 +221,16 @@ def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
             if sum_mode:
                 extra = {"gaussians_count": res[6].cpu().numpy(), "contributions": res[7].cpu().numpy(),
                          "final_T": ir["accum_alpha"].cpu().numpy(), "n_contrib": ir["n_contrib"].cpu().numpy()}
+                if loss_map is not None:
+                    extra["loss_map_seed"] = np.int64(17)
             np.savez_compressed(os.path.join(golden_dir, f"{variant}_{tag}.npz"), color=col_r.cpu().numpy(), radii=rad_r.cpu().numpy(),
                                 num_rendered=np.int64(n_r), point_list=br["point_list"].cpu().numpy(),
                                 ranges=ir["ranges"][: ((W + 15) // 16) * ((H + 15) // 16)].cpu().numpy(),
                                 means2D=gr["means2D"].cpu().numpy(), depths=gr["depths"].cpu().numpy(), conic=gr["conic"].contiguous().cpu().numpy(), **extra)
         if do_time:
-            rep["time_ref"] = time_fn(lambda: ref_api.ps1_forward(mod, sc, c))
-            rep["time_ours"] = time_fn(lambda: ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs))
+            rep["time_ref"] = time_fn(lambda: ref_api.ps1_forward(mod, sc, c, loss_map=loss_map))
+            rep["time_ours"] = time_fn(lambda: ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs,
+                                                               loss_map=loss_map))
     except Exception as ex:
         rep["error"] = repr(ex); rep["trace"] = traceback.format_exc()[-1500:]
     rep_list.append(rep)
