@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         const uint32_t* src = (const uint32_t*)&ws.hdr->cam;
         uint32_t* dst = (uint32_t*)&sm.cam;
         for (int i = tid; i < n; i += PB) dst[i] = src[i];
-        if (MODE == MODE_FOV && tid < FOV_LEVELS * 4) (&sm.bbox[0][0])[tid] = (&ws.hdr->lvl_bbox[0][0])[tid];
+        if (is_foveated(MODE) && tid < FOV_LEVELS * 4) (&sm.bbox[0][0])[tid] = (&ws.hdr->lvl_bbox[0][0])[tid];
     }
     __syncthreads();   // the only block barrier: from here on warps never wait for each other
     const CamParams& cam = sm.cam;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         if (ok) {
             const bool single0 = ((uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0)) == 1u;
             int cx0 = s.x0, cy0 = s.y0, cx1 = s.x1, cy1 = s.y1;
-            if (MODE == MODE_FOV) {
+            if (is_foveated(MODE)) {
                 hl = in.highest_levels[idx];
                 // tiles outside the level's bounding box fail `tile_min < hl + 1` anyway: do not even enumerate them
                 const int li = (int)hl;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
             wm.dbits[lane] = __float_as_uint(s.depth);
             wm.x0[lane] = cx0; wm.y0[lane] = cy0; wm.w[lane] = cw; wm.rw[lane] = 1.0f / (float)max(cw, 1);
-            if (MODE == MODE_FOV) wm.hl1[lane] = FA(hl, 1.0f);
+            if (is_foveated(MODE)) wm.hl1[lane] = FA(hl, 1.0f);
         }
         wm.cnt[lane] = 0;
         // exclusive scan of the candidate counts over the warp; compact list of non-empty owners
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                 tile = (uint32_t)ty * gx + tx;
                 single = wm.single[owner] != 0;
                 pass = true;
-                if (MODE == MODE_FOV) pass = ws.tile_min[tile] < wm.hl1[owner];
+                if (is_foveated(MODE)) pass = ws.tile_min[tile] < wm.hl1[owner];
                 if (pass && !single) {
                     const float cx = wm.px[owner], cy = wm.py[owner];
                     const float e1x = wm.e1x[owner], e1y = wm.e1y[owner], e2x = wm.e2x[owner], e2y = wm.e2y[owner];
@@ -307,10 +307,10 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         visible_total += nv;
         uint32_t lv = 0;
         if (visible) {
-            constexpr int R = (MODE == MODE_FOV) ? REC_FOV : REC_PS1;
+            constexpr int R = rec_size(MODE);
             float4* rec = ws.rec + (size_t)R * idx;
             rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
-            if (MODE == MODE_FOV) {
+            if (is_foveated(MODE)) {
                 rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
                 lv = (uint32_t)(FOV_LEVELS - 1) << 8;   // all levels
             } else {
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(CW * 32) k_color(Workspace ws, FrameInputs in)
                     rec[2 + l] = o;
                 }
             } else {
-                float4* rec = ws.rec + (size_t)REC_PS1 * id;
+                float4* rec = ws.rec + (size_t)rec_size(MODE) * id;
                 float3 c;
                 bool cl0 = false, cl1 = false, cl2 = false;
                 if (in.colors_precomp != nullptr) {
@@ -453,7 +453,8 @@ __global__ void __launch_bounds__(CW * 32) k_color(Workspace ws, FrameInputs in)
                     cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
                     c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
                 }
-                rec[2] = make_float4(c.x, c.y, c.z, 0.f);
+                if (MODE == MODE_SMFR) rec[2] = make_float4(in.opacities[id], c.x, c.y, c.z);   // REC_SMFR
+                else rec[2] = make_float4(c.x, c.y, c.z, 0.f);
                 if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[id] = make_uchar4(cl0, cl1, cl2, 0);
             }
         }
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs
                     rec[2 + l] = o;
                 }
             } else {
-                float4* rec = ws.rec + (size_t)REC_PS1 * id;
+                float4* rec = ws.rec + (size_t)rec_size(MODE) * id;
                 float3 c;
                 bool cl0 = false, cl1 = false, cl2 = false;
                 if (in.colors_precomp != nullptr) {
@@ -603,7 +604,8 @@ __global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs
                     cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
                     c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
                 }
-                rec[2] = make_float4(c.x, c.y, c.z, 0.f);
+                if (MODE == MODE_SMFR) rec[2] = make_float4(in.opacities[id], c.x, c.y, c.z);   // REC_SMFR
+                else rec[2] = make_float4(c.x, c.y, c.z, 0.f);
                 if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[id] = make_uchar4(cl0, cl1, cl2, 0);
             }
         }
@@ -725,6 +727,7 @@ cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, in
     switch (mode) {
         case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, 0, st>>>(ws, in); break;
         case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, 0, st>>>(ws, in); break;
+        case MODE_SMFR: k_pre<MODE_SMFR><<<grid, PB, 0, st>>>(ws, in); break;
         default: k_pre<MODE_FOV><<<grid, PB, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();
@@ -740,6 +743,7 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
         switch (mode) {
             case MODE_OBB: k_color_tma<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
             case MODE_SUM: k_color_tma<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
+            case MODE_SMFR: k_color_tma<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
             default: k_color_tma<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
         }
         return cudaGetLastError();
@@ -747,6 +751,7 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
     switch (mode) {
         case MODE_OBB: k_color<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in); break;
         case MODE_SUM: k_color<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in); break;
+        case MODE_SMFR: k_color<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
         default: k_color<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();

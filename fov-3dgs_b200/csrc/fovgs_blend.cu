@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     __shared__ float4 sA[256];   // px, py, conx, cony
     __shared__ float4 sB[256];   // conz, opacity | highest_level, depth
     __shared__ float4 sC[256];   // PS1: (r, g, b, -) | FOV: level L1 (opacity, r, g, b)
-    __shared__ float4 sD[(MODE == MODE_FOV) ? 256 : 1];   // FOV blending tiles: level L2 (opacity, r, g, b)
+    __shared__ float4 sD[(MODE == MODE_FOV) ? 256 : 1];   // SMFR blending tiles reuse sC for both levels   // FOV blending tiles: level L2 (opacity, r, g, b)
     __shared__ int sId[(MODE == MODE_SUM) ? 256 : 1];
     const FrameHeader* __restrict__ hdr = ws.hdr;
     const int W = hdr->cam.W, H = hdr->cam.H, gx = hdr->cam.grid_x;
@@ -53,18 +53,21 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     const uint32_t* __restrict__ plist = ws.point_list + rbeg;
     int batches_done = 0;   // statistics: how much of the sorted list the tile actually consumed
 
-    if (MODE == MODE_FOV) {
+    if (is_foveated(MODE)) {
         const bool blending = ws.tile_blend[tile] != 0;
         const float tile_level_f = ws.tile_min[tile];   // Q2: the render kernels receive tile_level_min
         const int L1 = (int)tile_level_f;
+        constexpr int R = rec_size(MODE);
+        constexpr bool SMFR = MODE == MODE_SMFR;          // one shared (opacity, r, g, b) record in slot 2
+        const int S1 = SMFR ? 2 : 2 + L1;
         if (!blending) {
             Prefetch<3> pf;
             auto fetch = [&](int progress) {
                 pf.valid = progress < total;
                 if (pf.valid) {
                     const uint32_t id = plist[progress];
-                    const float4* __restrict__ rec = ws.rec + (size_t)REC_FOV * id;
-                    pf.r[0] = rec[0]; pf.r[1] = rec[1]; pf.r[2] = rec[2 + L1];
+                    const float4* __restrict__ rec = ws.rec + (size_t)R * id;
+                    pf.r[0] = rec[0]; pf.r[1] = rec[1]; pf.r[2] = rec[S1];
                 }
             };
             fetch(tid);
@@ -109,15 +112,16 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                 pf.valid = progress < total;
                 if (pf.valid) {
                     const uint32_t id = plist[progress];
-                    const float4* __restrict__ rec = ws.rec + (size_t)REC_FOV * id;
-                    pf.r[0] = rec[0]; pf.r[1] = rec[1]; pf.r[2] = rec[2 + L1]; pf.r[3] = rec[2 + L2];
+                    const float4* __restrict__ rec = ws.rec + (size_t)R * id;
+                    pf.r[0] = rec[0]; pf.r[1] = rec[1]; pf.r[2] = rec[S1];
+                    if (!SMFR) pf.r[3] = rec[S1 + 1];
                 }
             };
             fetch(tid);
             float T1 = 1.0f, T2 = 1.0f, A0 = 0.f, A1 = 0.f, A2 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
             for (int i = 0; i < rounds; i++, toDo -= 256) {
                 if (__syncthreads_count(done) == 256) break;
-                if (pf.valid) { sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2]; sD[tid] = pf.r[3]; }
+                if (pf.valid) { sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2]; if (!SMFR) sD[tid] = pf.r[3]; }
                 batches_done = i + 1;
                 __syncthreads();
                 if (i + 1 < rounds) fetch((i + 1) * 256 + tid);
@@ -129,6 +133,33 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                     const float power = gauss_power(a.z, a.w, b.x, dx, dy);
                     if (power > 0.0f || power < -4.5f) continue;
                     const float e = expf(power);
+                    if (SMFR) {
+                        // naive_pcheck_obb/cuda_rasterizer/forward.cu:383-430: one alpha for both levels; a live L1 drops
+                        // the entry for both when alpha < 1/255, a finished L1 lets it through to L2 untested
+                        const float4 c = sC[j];
+                        const float alpha1 = fminf(0.99f, FM(c.x, e));
+                        if (!L1_done) {
+                            if (alpha1 < 1.0f / 255.0f) continue;
+                            const float test_T1 = FM(T1, FS(1.0f, alpha1));
+                            L1_done = test_T1 < 0.0001f;
+                            if (!L1_done) {
+                                const float w = FM(alpha1, T1);
+                                A0 = FF(c.y, w, A0); A1 = FF(c.z, w, A1); A2 = FF(c.w, w, A2);
+                                T1 = test_T1;
+                            }
+                        }
+                        if (!L2_done && !(FA(b.y, 1.0f) < L2_f)) {
+                            const float test_T2 = FM(T2, FS(1.0f, alpha1));
+                            L2_done = test_T2 < 0.0001f;
+                            if (!L2_done) {
+                                const float w = FM(alpha1, T2);
+                                B0 = FF(c.y, w, B0); B1 = FF(c.z, w, B1); B2 = FF(c.w, w, B2);
+                                T2 = test_T2;
+                            }
+                        }
+                        if (L1_done && L2_done) done = true;
+                        continue;
+                    }
                     if (!L1_done) {
                         const float4 c = sC[j];
                         const float alpha1 = fminf(0.99f, FM(c.x, e));
@@ -257,6 +288,7 @@ cudaError_t launch_blend(const Workspace& ws, const FrameInputs& in, int T, Mode
     switch (mode) {
         case MODE_OBB: k_blend<MODE_OBB><<<T, 256, 0, st>>>(ws, in); break;
         case MODE_SUM: k_blend<MODE_SUM><<<T, 256, 0, st>>>(ws, in); break;
+        case MODE_SMFR: k_blend<MODE_SMFR><<<T, 256, 0, st>>>(ws, in); break;
         default: k_blend<MODE_FOV><<<T, 256, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();

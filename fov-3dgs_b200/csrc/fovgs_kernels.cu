@@ -240,14 +240,14 @@ __global__ void k_export_geometry(Workspace ws, int P, int mode, const int* __re
                                   float* conic, float* cov3D, float* rgb, float* level_colors) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
-    const int R = (mode == MODE_FOV) ? REC_FOV : REC_PS1;
+    const int R = rec_size(mode);
     const float4* rec = ws.rec + (size_t)R * idx;
     const float4 r0 = rec[0], r1 = rec[1];
     if (means2D) { means2D[2 * idx] = r0.x; means2D[2 * idx + 1] = r0.y; }
     if (depths) depths[idx] = r1.z;
     if (conic) { conic[3 * idx] = r0.z; conic[3 * idx + 1] = r0.w; conic[3 * idx + 2] = r1.x; }
     if (cov3D && mode == MODE_SUM) for (int k = 0; k < 6; k++) cov3D[6 * idx + k] = ws.cov3D[6 * (size_t)idx + k];
-    if (rgb && mode != MODE_FOV) { const float4 c = rec[2]; rgb[3 * idx] = c.x; rgb[3 * idx + 1] = c.y; rgb[3 * idx + 2] = c.z; }
+    if (rgb && !is_foveated(mode)) { const float4 c = rec[2]; rgb[3 * idx] = c.x; rgb[3 * idx + 1] = c.y; rgb[3 * idx + 2] = c.z; }
     if (level_colors && mode == MODE_FOV)
         for (int l = 0; l < FOV_LEVELS; l++) {
             const float4 c = rec[2 + l];
@@ -278,14 +278,14 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
     ws.tile_offset = (uint32_t*)take((T + 1) * 4);
     ws.tile_cursor = (uint32_t*)take(T * 4 * CSTRIDE);
     ws.tile_order = (uint32_t*)take(T * 4);
-    if (mode == MODE_FOV) {
+    if (is_foveated(mode)) {
         ws.tile_level = (float*)take(T * 4);
         ws.tile_min = (float*)take(T * 4);
         ws.tile_gx = (float*)take(T * 4);
         ws.tile_gy = (float*)take(T * 4);
         ws.tile_blend = (uint8_t*)take(T);
     }
-    ws.rec = (float4*)take((size_t)P * 16 * (mode == MODE_FOV ? REC_FOV : REC_PS1));
+    ws.rec = (float4*)take((size_t)P * 16 * rec_size(mode));
     ws.vis_cap = (uint32_t)((size_t)P + (size_t)P / 4 + (size_t)STAGE_MAX_BLOCKS * 8 * 128);
     ws.vis_list = (uint32_t*)take((size_t)ws.vis_cap * 4);
     ws.vis_lv = (uint32_t*)take((size_t)ws.vis_cap * 4);
@@ -337,7 +337,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     const int T = a.tiles;
     prof_mark(0, st);
     k_setup<<<(T + 255) / 256, 256, 0, st>>>(ws, a);
-    if (mode == MODE_FOV) {
+    if (is_foveated(mode)) {
         k_tile_levels<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, gaze, a.W, a.H, a.gx, alpha);
         k_tile_infos<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, a.gx, a.gy, ws.tile_gy, ws.tile_gx, ws.tile_min,
                                                      ws.tile_blend, ws.hdr);
@@ -397,6 +397,7 @@ cudaError_t launch_forward(const Workspace& ws, const FrameInputs& in, int W, in
     switch (mode) {
         case MODE_OBB: return forward_impl<MODE_OBB>(ws, in, W, H, debug, st);
         case MODE_SUM: return forward_impl<MODE_SUM>(ws, in, W, H, debug, st);
+        case MODE_SMFR: return forward_impl<MODE_SMFR>(ws, in, W, H, debug, st);
         default: return forward_impl<MODE_FOV>(ws, in, W, H, debug, st);
     }
 }

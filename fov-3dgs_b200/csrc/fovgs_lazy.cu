@@ -16,6 +16,7 @@
 // to the reference; only WHERE batch boundaries fall differs, which no pixel can observe (a pixel's `done` is its own).
 // The training variant (SUM) keeps the full sort: its backward needs the complete lists, and its
 // `gaussians_count` is defined by 256-entry batch boundaries.  `out_point_list` requests also use the full path.
+#include <type_traits>
 #include "fovgs_internal.cuh"
 #ifdef FOVGS_TILE_TIMING
 #include <cstdio>
@@ -150,6 +151,49 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
                 L2_done = test_T2 < 0.0001f;
                 if (!L2_done) {
                     const float w = FM(alpha2, T2);
+                    B0 = FF(c.y, w, B0); B1 = FF(c.z, w, B1); B2 = FF(c.w, w, B2);
+                    T2 = test_T2;
+                }
+            }
+        }
+        if (L1_done && L2_done) done = true;
+    }
+};
+
+struct PixSmfrBlend {  // naive_pcheck_obb/cuda_rasterizer/forward.cu:262-440: one alpha for both levels
+    float T1, T2, A0, A1, A2, B0, B1, B2, L2_f;
+    bool L1_done, L2_done, done;
+    __device__ __forceinline__ void init(bool inside, float est, int L2, float l2f) {
+        T1 = T2 = 1.0f; A0 = A1 = A2 = B0 = B1 = B2 = 0.f; L2_f = l2f;
+        L1_done = est > (float)L2; L2_done = false; done = !inside;
+    }
+    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
+        const float4 a = sm.bl.sA[j];
+        const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
+        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
+    }
+    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
+        if (power > 0.0f || power < -4.5f) return;
+        const float4 b = sm.bl.sB[j];
+        const float4 c = sm.bl.sC[j];
+        const float alpha1 = fminf(0.99f, FM(c.x, expf(power)));
+        if (!L1_done) {
+            // a live L1 drops the entry for BOTH levels (:403-405); once L1 is done the alpha test no longer applies
+            if (alpha1 < 1.0f / 255.0f) return;
+            const float test_T1 = FM(T1, FS(1.0f, alpha1));
+            L1_done = test_T1 < 0.0001f;
+            if (!L1_done) {
+                const float w = FM(alpha1, T1);
+                A0 = FF(c.y, w, A0); A1 = FF(c.z, w, A1); A2 = FF(c.w, w, A2);
+                T1 = test_T1;
+            }
+        }
+        if (!L2_done) {
+            if (!(FA(b.y, 1.0f) < L2_f)) {
+                const float test_T2 = FM(T2, FS(1.0f, alpha1));
+                L2_done = test_T2 < 0.0001f;
+                if (!L2_done) {
+                    const float w = FM(alpha1, T2);
                     B0 = FF(c.y, w, B0); B1 = FF(c.z, w, B1); B2 = FF(c.w, w, B2);
                     T2 = test_T2;
                 }
@@ -331,13 +375,14 @@ __device__ __forceinline__ const uint64_t* lazy_global_sort(LazySmem& sm, uint64
 // ---- composite the m sorted keys `sk` (shared memory) in 256-entry batches; returns true when every pixel is done ----
 // Thread layout: warp w owns the 8x4 pixel block at (8*(w&1), 4*(w>>1)) of the tile.  Per batch each warp first builds
 // the list of slots that can reach its block (block_may_touch, one slot per lane), then all lanes walk that list.
-template <int KIND, class PIX>
+// KIND: 0 PS=1, 1 foveated plain tile, 2 FOV blending tile (two level records), 3 SMFR blending tile (one record).
+// R = float4 per record; S1 / S2 = record slots of the level-L1 / level-L2 (opacity, r, g, b).
+template <int KIND, int R, class PIX>
 __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& ws, const uint64_t* sk, const uint32_t m,
                                                  PIX& px, const float pixx, const float pixy, const float blkx,
-                                                 const float blky, const int L1, const int L2, uint32_t& consumed,
+                                                 const float blky, const int S1, const int S2, uint32_t& consumed,
                                                  uint32_t& kept) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int R = (KIND == 0) ? REC_PS1 : REC_FOV;
     float4 r0, r1, r2, r3;
     bool valid;
     auto fetch = [&](uint32_t pos) {
@@ -346,8 +391,8 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
             const uint32_t id = (uint32_t)sk[pos];
             const float4* __restrict__ rec = ws.rec + (size_t)R * id;
             r0 = rec[0]; r1 = rec[1];
-            r2 = (KIND == 0) ? rec[2] : rec[2 + L1];
-            if (KIND == 2) r3 = rec[2 + L2];
+            r2 = (KIND == 0) ? rec[2] : rec[S1];
+            if (KIND == 2) r3 = rec[S2];
         }
     };
     fetch(tid);
@@ -369,7 +414,9 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
             const int j = jb + lane;
             bool keep = false;
             if (j < lim) {
-                const float op = (KIND == 0) ? sm.bl.sB[j].y : (KIND == 1) ? sm.bl.sC[j].x : fmaxf(sm.bl.sC[j].x, sm.bl.sD[j].x);
+                // SMFR blending tiles composite level L2 whatever the alpha once L1 is done: only the -4.5 bound holds
+                const float op = (KIND == 0) ? sm.bl.sB[j].y : (KIND == 1) ? sm.bl.sC[j].x :
+                                 (KIND == 2) ? fmaxf(sm.bl.sC[j].x, sm.bl.sD[j].x) : 1.0f;
                 keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, op, blkx, blky);
             }
             const unsigned mk = __ballot_sync(0xffffffffu, keep);
@@ -510,12 +557,12 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     }
 }
 
-template <int KIND, class PIX>
+template <int KIND, int R, class PIX>
 __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, const int tile, PIX& px, const float pixx,
-                                          const float pixy, const float blkx, const float blky, const int L1, const int L2) {
+                                          const float pixy, const float blkx, const float blky, const int S1, const int S2) {
     uint32_t consumed = 0, kept = 0;
     lazy_for_each_group(sm, ws, tile, [&](const uint64_t* sk, uint32_t m, bool) {
-        return lazy_blend_group<KIND>(sm, ws, sk, m, px, pixx, pixy, blkx, blky, L1, L2, consumed, kept);
+        return lazy_blend_group<KIND, R>(sm, ws, sk, m, px, pixx, pixy, blkx, blky, S1, S2, consumed, kept);
     });
     if (threadIdx.x == 0 && consumed) atomicAdd(&ws.hdr->stats.reserved[0], consumed);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);   // (warp, splat) pairs that passed block_may_touch
@@ -679,14 +726,16 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
     const float pixx = (float)pxi, pixy = (float)pyi;
     const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
     const size_t HW = (size_t)H * W;
-    if (MODE == MODE_FOV) {
+    if (is_foveated(MODE)) {
         const bool blending = ws.tile_blend[tile] != 0;
         const float tile_level_f = ws.tile_min[tile];
         const int L1 = (int)tile_level_f;
+        constexpr int R = rec_size(MODE);
+        const int S1 = (MODE == MODE_FOV) ? 2 + L1 : 2;   // SMFR: the one shared (opacity, r, g, b) record
         if (!blending) {
             PixFov px;
             px.init(inside);
-            lazy_tile<1>(sm, ws, tile, px, pixx, pixy, blkx, blky, L1, 0);
+            lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
             if (inside) {
                 in.out_color[pix_id] = FF(bg0, px.T, px.C0);
                 in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);
@@ -696,9 +745,9 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
             const int L2 = L1 + 1;
             const float dxl = (float)lxi, dyl = (float)lyi;
             const float est = FF(FF(dxl, ws.tile_gx[tile], FM(dyl, ws.tile_gy[tile])), 0.0625f, tile_level_f);
-            PixFovBlend px;
+            typename std::conditional<MODE == MODE_FOV, PixFovBlend, PixSmfrBlend>::type px;
             px.init(inside, est, L2, FA(tile_level_f, 1.0f));
-            lazy_tile<2>(sm, ws, tile, px, pixx, pixy, blkx, blky, L1, L2);
+            lazy_tile<(MODE == MODE_FOV) ? 2 : 3, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, S1 + 1);
             if (inside) {
                 const float A0 = FF(bg0, px.T1, px.A0), A1 = FF(bg1, px.T1, px.A1), A2 = FF(bg2, px.T1, px.A2);
                 const float B0 = FF(bg0, px.T2, px.B0), B1 = FF(bg1, px.T2, px.B1), B2 = FF(bg2, px.T2, px.B2);
@@ -730,7 +779,7 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
     } else {
         PixPS1 px;
         px.init(inside);
-        lazy_tile<0>(sm, ws, tile, px, pixx, pixy, blkx, blky, 0, 0);
+        lazy_tile<0, REC_PS1>(sm, ws, tile, px, pixx, pixy, blkx, blky, 0, 0);
         if (inside) {
             in.out_color[pix_id] = FF(bg0, px.T, px.C0);
             in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);
@@ -747,6 +796,8 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_OBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SMFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
@@ -756,6 +807,7 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
         configured = true;
     }
     if (mode == MODE_FOV) k_lazy_blend<MODE_FOV><<<T, 256, smem, st>>>(ws, in);
+    else if (mode == MODE_SMFR) k_lazy_blend<MODE_SMFR><<<T, 256, smem, st>>>(ws, in);
     else if (mode == MODE_SUM && in.stat == STAT_MAX) k_lazy_blend<MODE_SUM, STAT_MAX><<<T, 256, smem_sum, st>>>(ws, in);
     else if (mode == MODE_SUM && in.stat == STAT_LWMC) k_lazy_blend<MODE_SUM, STAT_LWMC><<<T, 256, smem_sum, st>>>(ws, in);
     else if (mode == MODE_SUM) k_lazy_blend<MODE_SUM, STAT_SUM><<<T, 256, smem_sum, st>>>(ws, in);

@@ -592,6 +592,7 @@ typedef struct {
     const orc_camera* cam; int W, H, gx; const uint32_t* rng; const inst_t* inst; const splat_t* sp;
     const float* tm; const float* tgx; const float* tgy; const uint8_t* tb; const float* opacities4; const float* fc;
     const float* highest_levels; float* out_color;
+    int naive;   /* SMFR baseline (naive_pcheck_obb/cuda_rasterizer/forward.cu:383-430): one opacity/colour for all levels */
 } fov_blend_ctx;
 static void blend_tile_fov(void* vctx, int tile) {
     const fov_blend_ctx* c = (const fov_blend_ctx*)vctx;
@@ -638,6 +639,32 @@ static void blend_tile_fov(void* vctx, int tile) {
                         const float w = a * T1[t];
                         for (int ch = 0; ch < 3; ch++) C1[t][ch] = fmaf(fc[(size_t)id * 12 + L1 * 3 + ch], w, C1[t][ch]);
                         T1[t] = tt;
+                    } else if (c->naive) {
+                        /* the shared-model baseline tests alpha once: a live L1 drops the entry for both levels when
+                           alpha < 1/255, but once L1 is done the entry still reaches L2 whatever its alpha */
+                        const float a = fminf(0.99f, opacities4[(size_t)id * 4 + L1] * e);
+                        if (!d1[t]) {
+                            if (a < 1.0f / 255.0f) continue;
+                            const float tt = T1[t] * (1 - a);
+                            d1[t] = tt < 0.0001f;
+                            if (!d1[t]) {
+                                const float w = a * T1[t];
+                                for (int ch = 0; ch < 3; ch++) C1[t][ch] = fmaf(fc[(size_t)id * 12 + L1 * 3 + ch], w, C1[t][ch]);
+                                T1[t] = tt;
+                            }
+                        }
+                        if (!d2[t]) {
+                            if (!((highest_levels[id] + 1) < L2f)) {
+                                const float tt = T2[t] * (1 - a);
+                                d2[t] = tt < 0.0001f;
+                                if (!d2[t]) {
+                                    const float w = a * T2[t];
+                                    for (int ch = 0; ch < 3; ch++) C2[t][ch] = fmaf(fc[(size_t)id * 12 + L1 * 3 + ch], w, C2[t][ch]);
+                                    T2[t] = tt;
+                                }
+                            }
+                        }
+                        if (d1[t] && d2[t]) { done[t] = 1; ndone++; }
                     } else {
                         if (!d1[t]) {
                             const float a = fminf(0.99f, opacities4[(size_t)id * 4 + L1] * e);
@@ -692,12 +719,20 @@ static void blend_tile_fov(void* vctx, int tile) {
 /* =================================================================================================================
  * Foveated forward (diff_gaussian_rasterization_fov_pcheck_obb).
  * ================================================================================================================= */
-int64_t orc_forward_fov(const orc_camera* cam, int P, int M_rest, const float* means3D, const float* opacities4,
+static int64_t forward_fov_impl(int naive, const orc_camera* cam, int P, int M_rest, const float* means3D, const float* opacities4_in,
                         const float* scales, const float* rot, const float* shs_rest, const float* shs_dcs,
                         const float* highest_levels, const float* gaze, float alpha_pool, float* out_color, int* radii,
                         float* means2D, float* depths, float* conic, uint32_t* point_list, int64_t list_cap,
                         uint32_t* ranges, float* tile_level_out, float* tile_min_out, uint8_t* tile_blend_out,
                         int32_t* level_ranges_out) {
+    /* naive (SMFR): `shs_rest` is the full [P,M,3] SH tensor (DC first), `opacities4_in` is [P]; shs_dcs unused */
+    const float* opacities4 = opacities4_in;
+    float* op_rep = NULL;
+    if (naive) {
+        op_rep = (float*)malloc(sizeof(float) * 4 * ((size_t)P + 1));
+        for (size_t i = 0; i < (size_t)P; i++) for (int l = 0; l < 4; l++) op_rep[4 * i + l] = opacities4_in[i];
+        opacities4 = op_rep;
+    }
     const int W = cam->W, H = cam->H, gx = (W + 15) / 16, gy = (H + 15) / 16, T = gx * gy;
     const float fy = H / (2.0f * cam->tanfovy), fx = W / (2.0f * cam->tanfovx);
     float* tl = (float*)malloc(sizeof(float) * T); float* tm = (float*)malloc(sizeof(float) * T);
@@ -725,23 +760,55 @@ int64_t orc_forward_fov(const orc_camera* cam, int P, int M_rest, const float* m
         if (radii[i] <= 0) continue;
         float d[3]; view_dir(cam, means3D + 3 * i, d);
         float res[3] = {0, 0, 0};
+        if (naive) {
+            /* computeColorFromSH of the shared model (naive_pcheck_obb/cuda_rasterizer/rasterizer_impl.cu:34-82) */
+            const float* sh = shs_rest + (size_t)3 * M_rest * i;
+            for (int ch = 0; ch < 3; ch++) res[ch] = SH_C0 * sh[ch];
+            sh_accumulate(sh, 1, cam->sh_degree, d[0], d[1], d[2], res);
+            for (int l = 0; l < 4; l++)
+                for (int ch = 0; ch < 3; ch++) fc[(size_t)i * 12 + l * 3 + ch] = fmaxf(res[ch] + 0.5f, 0.0f);
+        } else {
         if (M_rest > 0) sh_accumulate(shs_rest + (size_t)3 * M_rest * i, 0, cam->sh_degree, d[0], d[1], d[2], res);
         for (int ch = 0; ch < 3; ch++) res[ch] += 0.5f;
         for (int l = o.lvl_lo[i]; l <= o.lvl_hi[i]; l++)
             for (int ch = 0; ch < 3; ch++)
                 fc[(size_t)i * 12 + l * 3 + ch] = fmaxf(SH_C0 * shs_dcs[(size_t)i * 12 + l * 3 + ch] + res[ch], 0.0f);
+        }
         if (means2D) { means2D[2 * i] = o.sp[i].px; means2D[2 * i + 1] = o.sp[i].py; }
         if (depths) depths[i] = o.sp[i].depth;
         if (conic) { conic[3 * i] = o.sp[i].conx; conic[3 * i + 1] = o.sp[i].cony; conic[3 * i + 2] = o.sp[i].conz; }
         if (level_ranges_out) { level_ranges_out[2 * i] = o.lvl_lo[i]; level_ranges_out[2 * i + 1] = o.lvl_hi[i]; }
     }
     {
-        fov_blend_ctx bc = {cam, W, H, gx, rng, o.inst, o.sp, tm, tgx, tgy, tb, opacities4, fc, highest_levels, out_color};
+        fov_blend_ctx bc = {cam, W, H, gx, rng, o.inst, o.sp, tm, tgx, tgy, tb, opacities4, fc, highest_levels, out_color, naive};
         run_tiles(blend_tile_fov, &bc, T);
     }
     free(tl); free(tm); free(tgx); free(tgy); free(tb); free(o.sp); free(o.vis); free(o.cov3d); free(o.lvl_lo); free(o.lvl_hi);
-    free(o.inst); free(rng); free(fc);
+    free(o.inst); free(rng); free(fc); free(op_rep);
     return n;
+}
+
+int64_t orc_forward_fov(const orc_camera* cam, int P, int M_rest, const float* means3D, const float* opacities4,
+                        const float* scales, const float* rot, const float* shs_rest, const float* shs_dcs,
+                        const float* highest_levels, const float* gaze, float alpha_pool, float* out_color, int* radii,
+                        float* means2D, float* depths, float* conic, uint32_t* point_list, int64_t list_cap,
+                        uint32_t* ranges, float* tile_level_out, float* tile_min_out, uint8_t* tile_blend_out,
+                        int32_t* level_ranges_out) {
+    return forward_fov_impl(0, cam, P, M_rest, means3D, opacities4, scales, rot, shs_rest, shs_dcs, highest_levels, gaze, alpha_pool,
+                            out_color, radii, means2D, depths, conic, point_list, list_cap, ranges, tile_level_out, tile_min_out,
+                            tile_blend_out, level_ranges_out);
+}
+
+/* =================================================================================================================
+ * SMFR baseline (diff_gaussian_rasterization_naive_pcheck_obb): the foveated pipeline with ONE shared model — `shs` is
+ * the full [P,M,3] tensor, `opacity` [P]; levels only subset the Gaussians (highest_levels) and pick the blending path.
+ * ================================================================================================================= */
+int64_t orc_forward_smfr(const orc_camera* cam, int P, int M, const float* means3D, const float* opacity,
+                         const float* scales, const float* rot, const float* shs, const float* highest_levels,
+                         const float* gaze, float alpha_pool, float* out_color, int* radii, uint32_t* point_list,
+                         int64_t list_cap, uint32_t* ranges) {
+    return forward_fov_impl(1, cam, P, M, means3D, opacity, scales, rot, shs, NULL, highest_levels, gaze, alpha_pool, out_color,
+                            radii, NULL, NULL, NULL, point_list, list_cap, ranges, NULL, NULL, NULL, NULL);
 }
 
 /* =================================================================================================================

@@ -45,6 +45,16 @@ def fov_forward(mod, sc, cam, gaze, alpha=0.05, blending=True, bg=None, debug=Fa
         cam["campos"], False, debug)
 
 
+def smfr_forward(mod, sc, cam, gaze, alpha=0.05, blending=True, bg=None, debug=False):
+    """ref_naive_C (SMFR baseline): 23 args, naive_pcheck_obb/rasterize_points.h:17-43.  sc carries shs [P,M,3],
+    opacity [P,1], highest_levels [P,1]."""
+    bg = bg if bg is not None else torch.zeros(3, device="cuda")
+    return mod.rasterize_gaussians(
+        sc["highest_levels"], gaze, float(alpha), bool(blending), bg, sc["means3D"], _empty(), sc["opacity"], sc["scales"],
+        sc["rotations"], 1.0, _empty(), cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"],
+        cam["image_height"], cam["image_width"], sc["shs"], sc["sh_degree"], cam["campos"], False, debug)
+
+
 def ps1_forward(mod, sc, cam, bg=None, debug=False, loss_map=None):
     """`loss_map` (CUDA [H,W]) only for ref_lwmc_C, whose pybind signature takes it between `prefiltered` and `debug`
     (.../pcheck_obb_loss_weighted_max_count/rasterize_points.cu:35-57)."""

@@ -149,6 +149,32 @@ def test_fov_vs_oracle(gaze):
     assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
 
 
+@pytest.mark.parametrize("gaze", [(0.5, 0.5), (0.2, 0.8)])
+def test_smfr_baseline_vs_oracle_full_and_lazy(gaze):
+    """SMFR baseline (naive_pcheck_obb, SURVEY §8f rank 2): lists exact, image within tolerance, lazy == full-sort bits;
+    its blending tiles follow the shared-alpha rule of naive_pcheck_obb/cuda_rasterizer/forward.cu:383-430."""
+    import oracle
+    s = synth.add_foveation(synth.make_scene_cube(5000, 23))
+    c = _small_cam(400, 240)
+    o = oracle.forward_smfr(s, c, gaze)
+    sc = _cuda(s)
+    import diff_gaussian_rasterization_naive_pcheck_obb as m
+    rs = _settings(m, c, s["sh_degree"])
+    g = torch.tensor(np.asarray(gaze, np.float32)).cuda()
+    n, color, radii, pl, rg, item = ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                     sc["highest_levels"], g, 0.05, True, rs, want_lists=True)
+    assert n == o["num_rendered"]
+    assert np.array_equal(radii.cpu().numpy(), o["radii"])
+    assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
+    assert np.array_equal(rg.cpu().numpy().astype(np.uint32), o["ranges"])
+    assert int(ops.last_stats["num_blend_tiles"]) > 0
+    assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
+    r = m.GaussianRasterizer(raster_settings=rs)
+    col_l, radii_l = r(means3D=sc["means3D"], means2D=None, opacities=sc["opacity"], shs=sc["shs"], scales=sc["scales"],
+                       rotations=sc["rotations"], highest_levels=sc["highest_levels"], gazeArray=g, alpha=0.05, blending=True)
+    assert torch.equal(col_l, color) and torch.equal(radii_l, radii)
+
+
 def test_sum_backward_vs_oracle():
     import oracle
     s = synth.make_scene_cube(3000, 33)

@@ -139,6 +139,52 @@ def run_fov(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
         print(json.dumps({k: v for k, v in rep.items() if k != "trace"}), flush=True)
 
 
+def run_smfr(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
+    """SMFR baseline (naive_pcheck_obb) vs ref_naive_C."""
+    mod = ref_api.ref_module("ref_naive_C")
+    sc = to_cuda(synth.add_foveation(scn))
+    c = to_cuda(cam)
+    W, H = cam["image_width"], cam["image_height"]
+    P = sc["means3D"].shape[0]
+    bg = torch.zeros(3, device="cuda")
+    rs = settings(c, sc["sh_degree"], bg)
+    for gi, g in enumerate(gazes):
+        rep = {"variant": "smfr", "tag": tag, "P": P, "W": W, "H": H, "gaze": list(g)}
+        try:
+            if mod is None:
+                raise RuntimeError("reference module ref_naive_C is not built")
+            gaze = torch.tensor(g, dtype=torch.float32, device="cuda")
+            n_r, col_r, rad_r, geom, binning, img = ref_api.smfr_forward(mod, sc, c, gaze)
+            torch.cuda.synchronize()
+            br = ref_api.decode_binning(binning, n_r)
+            ir = ref_api.decode_img(img, W, H)
+            n_o, col_o, rad_o, pl_o, rg_o, item = ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                                   sc["highest_levels"], gaze, 0.05, True, rs, want_lists=True)
+            torch.cuda.synchronize()
+            rep["num_rendered_ref"] = int(n_r); rep["num_rendered_ours"] = int(n_o)
+            rep["radii_mismatch"] = int((rad_r != rad_o).sum().item())
+            rep["point_list_mismatch"] = int((br["point_list"][:n_r] != pl_o[:n_r]).sum().item()) if n_r == n_o else -1
+            T = ((W + 15) // 16) * ((H + 15) // 16)
+            rep["ranges_mismatch"] = int((ir["ranges"][:T] != rg_o[:T]).sum().item())
+            d = (col_r - col_o).abs()
+            rep["img_max_abs"] = float(d.max().item()); rep["img_n_gt_1e-6"] = int((d > 1e-6).sum().item())
+            _, col_l, _ = ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"], sc["highest_levels"],
+                                           gaze, 0.05, True, rs)
+            rep["lazy_img_max_abs"] = float((col_l - col_r).abs().max().item()); rep["lazy_stats"] = dict(ops.last_stats)
+            if golden_dir and gi < 2:
+                np.savez_compressed(os.path.join(golden_dir, f"smfr_{tag}_g{gi}.npz"), gaze=np.array(g, np.float32),
+                                    color=col_r.cpu().numpy(), radii=rad_r.cpu().numpy(), num_rendered=np.int64(n_r),
+                                    point_list=br["point_list"].cpu().numpy(), ranges=ir["ranges"][:T].cpu().numpy())
+            if do_time and gi == 0:
+                rep["time_ref"] = time_fn(lambda: ref_api.smfr_forward(mod, sc, c, gaze))
+                rep["time_ours"] = time_fn(lambda: ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                                    sc["highest_levels"], gaze, 0.05, True, rs))
+        except Exception as ex:
+            rep["error"] = repr(ex); rep["trace"] = traceback.format_exc()[-1500:]
+        rep_list.append(rep)
+        print(json.dumps({k: v for k, v in rep.items() if k != "trace"}), flush=True)
+
+
 PS1_VARIANTS = {"obb": ("ref_obb_C", ops.MODE_OBB), "sum": ("ref_sum_C", ops.MODE_SUM), "max": ("ref_max_C", ops.MODE_MAX),
                 "lwmc": ("ref_lwmc_C", ops.MODE_LWMC)}
 
@@ -269,6 +315,8 @@ def main():
             for v in a.variants.split(","):
                 if v == "fov":
                     run_fov(scn, cam, synth.GAZES_9[: a.gazes], reports, a.time, gd, tag)
+                elif v == "smfr":
+                    run_smfr(scn, cam, synth.GAZES_9[: a.gazes], reports, a.time, gd, tag)
                 else:
                     run_ps1(v, scn, cam, reports, a.time, gd, tag)
         json.dump(reports, open(a.out, "w"), indent=1)
