@@ -96,6 +96,49 @@ def test_sum_forward_and_backward_match_reference_golden(scene_small, golden_dir
         assert np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30) <= 1e-4, nm
 
 
+@pytest.mark.parametrize("variant", ["max", "lwmc"])
+def test_pruning_variants_match_reference_golden(scene_small, golden_dir, variant):
+    g = _g(golden_dir, f"{variant}_small_c0.npz")
+    s, c = scene_small
+    sc = _cuda(s)
+    import diff_gaussian_rasterization_pcheck_obb_sum as m
+    rs = _settings(m, c, s["sh_degree"])
+    H, W = c["image_height"], c["image_width"]
+    lm = None
+    if variant == "lwmc":
+        lm = torch.from_numpy(np.random.default_rng(int(g["loss_map_seed"])).random((H, W)).astype(np.float32)).cuda()
+    mode = ops.MODE_MAX if variant == "max" else ops.MODE_LWMC
+    for lazy in (False, True):
+        r = ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs,
+                            want_lists=not lazy, loss_map=lm)
+        n, color, radii, item, gcount, contrib = r[:6]
+        assert n == int(g["num_rendered"])
+        assert np.array_equal(gcount.cpu().numpy(), g["gaussians_count"])
+        assert np.array_equal(color.cpu().numpy(), g["color"])          # measured: bit-identical to the reference binary
+        if variant == "max":
+            assert np.array_equal(contrib.cpu().numpy(), g["contributions"])   # exact maximum, exact counts
+        else:
+            a, b = contrib.cpu().numpy().astype(np.float64), g["contributions"].astype(np.float64)
+            assert (np.abs(a - b) / (np.abs(b) + 1e-3)).max() <= 1e-4
+
+
+@pytest.mark.parametrize("gi", [0, 1])
+def test_smfr_matches_reference_golden(scene_small, golden_dir, gi):
+    g = _g(golden_dir, f"smfr_small_c0_g{gi}.npz")
+    s, c = scene_small
+    sc = _cuda(synth.add_foveation(s))
+    import diff_gaussian_rasterization_naive_pcheck_obb as m
+    rs = _settings(m, c, s["sh_degree"])
+    gz = torch.from_numpy(np.asarray(g["gaze"], np.float32)).cuda()
+    n, color, radii, pl, rg, item = ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                     sc["highest_levels"], gz, 0.05, True, rs, want_lists=True)
+    assert n == int(g["num_rendered"])
+    assert np.array_equal(radii.cpu().numpy(), g["radii"])
+    assert np.array_equal(pl.cpu().numpy(), g["point_list"])
+    assert np.array_equal(rg.cpu().numpy(), g["ranges"])
+    assert np.array_equal(color.cpu().numpy(), g["color"])
+
+
 @pytest.mark.parametrize("gi", [0, 1])
 def test_fov_matches_reference_golden(scene_small, golden_dir, gi):
     g = _g(golden_dir, f"fov_small_c0_g{gi}.npz")

@@ -101,6 +101,47 @@ def test_fov_matches_reference(scene_small, golden_dir, gi):
     assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
 
 
+def test_max_statistics_match_reference(scene_small, golden_dir):
+    """pcheck_obb_max: per-(pixel, Gaussian) hit counts and the maximum alpha*T.  Counts are bit-exact where libm and
+    libdevice expf agree on every alpha >= 1/255 and T >= 1e-4 decision (they do on this fixture); the maximum is an
+    exact selection, equal up to the expf ulp."""
+    g = _g(golden_dir, "max_small_c0.npz")
+    s, c = scene_small
+    o = oracle.forward_ps1(s, c, "max")
+    assert o["num_rendered"] == int(g["num_rendered"])
+    assert np.array_equal(o["gaussians_count"], g["gaussians_count"])
+    assert np.array_equal(o["n_contrib"], g["n_contrib"].astype(np.uint32))
+    assert np.abs(o["contributions"] - g["contributions"]).max() <= 1e-6
+    assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
+
+
+def test_loss_weighted_statistics_match_reference(scene_small, golden_dir):
+    """pcheck_obb_loss_weighted_max_count with the seeded loss map the fixture was made with (tools/parity_gpu.py)."""
+    g = _g(golden_dir, "lwmc_small_c0.npz")
+    s, c = scene_small
+    H, W = c["image_height"], c["image_width"]
+    lm = np.random.default_rng(int(g["loss_map_seed"])).random((H, W)).astype(np.float32)
+    o = oracle.forward_ps1(s, c, "lwmc", loss_map=lm)
+    assert np.array_equal(o["gaussians_count"], g["gaussians_count"])
+    a, b = o["contributions"].astype(np.float64), g["contributions"].astype(np.float64)
+    assert abs(a.sum() - b.sum()) <= 1e-4 * b.sum()
+    assert (np.abs(a - b) / (np.abs(b) + 1e-3)).max() <= 1e-3      # fp32 atomics in arbitrary order on both sides
+    assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
+
+
+@pytest.mark.parametrize("gi", [0, 1])
+def test_smfr_baseline_matches_reference(scene_small, golden_dir, gi):
+    """naive_pcheck_obb (SMFR): one shared model, levels subset the Gaussians."""
+    g = _g(golden_dir, f"smfr_small_c0_g{gi}.npz")
+    s, c = scene_small
+    o = oracle.forward_smfr(synth.add_foveation(s), c, g["gaze"])
+    assert o["num_rendered"] == int(g["num_rendered"])
+    assert np.array_equal(o["radii"], g["radii"])
+    assert np.array_equal(o["point_list"], g["point_list"].astype(np.uint32))
+    assert np.array_equal(o["ranges"], g["ranges"].astype(np.uint32))
+    assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
+
+
 def test_tile_tables_shape_and_monotone_eccentricity():
     t = oracle.tile_tables(1920, 1080, (0.5, 0.5))
     lvl = t["tile_level"].reshape(68, 120)
