@@ -329,11 +329,12 @@ def roofline(res, wl, steps):
     T = ((wl.W + 15) // 16) * ((wl.H + 15) // 16)
     P, pix = wl.P, wl.W * wl.H
     blend_share = Tb / T
+    color_bytes = V * (4 + 12 + 180 + 48 + 16) + V * 64      # visible list + xyz + SH rest + 4 dc + 4 opacity; 4 level records
     bytes_model = {
-        # reads xyz+scale+rot+level for all P, SH-rest + 4 dc + 4 opacity for visible; writes radii, records, staged instances
-        "preprocess": P * (12 + 12 + 16 + 4) + V * (180 + 48 + 16) + P * 4 + V * 96 + N * (12 + 4),
-        "tile_scan": T * 8,
-        "scatter": N * (12 + 4 + 8),
+        # k_pre: reads xyz+scale+rot+level of all P; writes radii, 2 geometry records per visible, 16 B per staged instance
+        "preprocess": P * (12 + 12 + 16 + 4) + P * 4 + V * (32 + 4) + N * 12 + T * 8,
+        "color": color_bytes,
+        "scatter": N * (12 + 8),                                # staged (tile, key) in, binned key out
         "tile_sort": N * (8 + 4),
         "blend": N * (4 + 48 + 16 * blend_share) + pix * 12,
         "setup": T * 24,

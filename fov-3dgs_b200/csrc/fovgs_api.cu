@@ -28,6 +28,8 @@ size_t fovgs_workspace_bytes(int32_t P, int32_t W, int32_t H, int64_t max_instan
     return carve_workspace(nullptr, P, W, H, max_instances, mode).total_bytes;
 }
 
+static const int32_t kMaxP = 1 << 30;   // Gaussian ids travel in 32 bits next to the depth bits; loop counters are int
+
 static int check_cam(const fovgs_camera& c) {
     if (c.image_width <= 0 || c.image_height <= 0) return fail(FOVGS_ERR_INVALID_ARG, "image size must be positive%s");
     if (!c.bg || !c.viewmatrix || !c.projmatrix || !c.campos)
@@ -40,7 +42,7 @@ int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
-    if (a->P < 0) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3)%s");
+    if (a->P < 0 || a->P > kMaxP) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3), num_points <= 2^30%s");
     if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
     if (a->P == 0) return 0;  // reference: outputs stay at their initial value (rasterize_points.cu:103)
     if (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->shs_dcs || !a->highest_levels || !a->gaze)
@@ -67,7 +69,7 @@ int fovgs_forward_smfr(const fovgs_smfr_fwd_args* a, void* stream) {
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
-    if (a->P < 0) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3)%s");
+    if (a->P < 0 || a->P > kMaxP) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3), num_points <= 2^30%s");
     if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
     if (a->P == 0) return 0;
     if (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->shs || !a->highest_levels || !a->gaze)
@@ -98,7 +100,7 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     const Mode mode = a->mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB;
     if (a->mode == FOVGS_PS1_LWMC && !a->loss_map && a->P > 0)
         return fail(FOVGS_ERR_INVALID_ARG, "the loss-weighted variant needs loss_map [H,W]%s");
-    if (a->P < 0) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3)%s");
+    if (a->P < 0 || a->P > kMaxP) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3), num_points <= 2^30%s");
     if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
     if (a->P == 0) return 0;
     if (!a->means3D || !a->opacities) return fail(FOVGS_ERR_INVALID_ARG, "null input pointer (means3D/opacities)%s");

@@ -11,8 +11,10 @@
 //              Surviving (tile, depth|id) instances are staged densely (block-granular allocation, one global
 //              atomic per 4096 slots) and counted per tile; colours of visible Gaussians are evaluated in the same
 //              kernel.  Replaces preprocessCUDA + InclusiveSum x2 + filter + duplicateWithKeys + compute_fov_colors.
-//   k_tile_scan  one-block exclusive scan of the tile histogram (= the reference's `ranges`, no identifyTileRanges).
-//   k_scatter  staged instances -> tile-binned key array (trivially balanced: one thread per instance).
+//   tile scan  exclusive scan of the tile histogram (= the reference's `ranges`, no identifyTileRanges), run by the LAST
+//              CTA of k_pre to finish (ticket counter), so it costs no launch and no idle GPU.
+//   k_color_tma  SH colours of the visible Gaussians (TMA bulk gathers).
+//   k_scatter  staged instances -> their tiles' segments (cursor atomics; trivially balanced: one thread per instance).
 #include "fovgs_internal.cuh"
 
 namespace fovgs {
@@ -116,16 +118,38 @@ struct WarpSmem {
     uint32_t dbits[32];
     int x0[32], y0[32], w[32];
     uint32_t pref[33];
+    uint32_t gid[32];            // Gaussian id handled by each lane in phases A-C
+    uint32_t queue[64];          // ids that survived the conservative screen cull, waiting for a full warp of work
     uint32_t nzlist[32];         // lane of the k-th Gaussian with a non-empty candidate rectangle
     uint32_t cnt[32];            // != 0: at least one candidate tile survived (the Gaussian is visible)
+    uint32_t hcode[32];          // FOV: highest_level + 1 when it is one of 1..4 (level-code fast path), else 0
     uint32_t single[32];         // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
 };
 
+struct ScanSmem {
+    uint32_t warp_sums[32];
+    uint32_t carry, maxv;
+    uint32_t bucket_cnt[33], bucket_base[33];
+    int is_last;
+};
+
+constexpr int LC_MAX = 16384;      // tiles whose level code fits the shared table (1080p: 8160)
+constexpr int PRE_CHUNK = 128;     // Gaussians per work ticket of k_pre
+
 struct PreSmem {
     CamParams cam;
+    float cull_k;                // bound on |T row| * tz for the conservative screen cull (see k_pre phase 0)
     int bbox[FOV_LEVELS][4];
+    // FOV: per tile the smallest h in {1,2,3,4} with tile_min < h (5: none).  A Gaussian with integral highest_level passes
+    // `tile_min < highest_level + 1` (rasterizer_impl.cu:307,344) iff highest_level + 1 >= code: the per-candidate level
+    // test reads one shared byte instead of gathering a float through L1.
+    uint8_t lvl_code[LC_MAX];
     WarpSmem w[WPB];
+    ScanSmem scan;
 };
+
+template <int NT>
+__device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s);
 
 template <int MODE>
 __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
@@ -137,6 +161,25 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         uint32_t* dst = (uint32_t*)&sm.cam;
         for (int i = tid; i < n; i += PB) dst[i] = src[i];
         if (is_foveated(MODE) && tid < FOV_LEVELS * 4) (&sm.bbox[0][0])[tid] = (&ws.hdr->lvl_bbox[0][0])[tid];
+        if (tid == 32) {
+            // |row i of T| <= Wn * f * (1 + 1.3 tanfov) / tz  (cov2d_from_cov3d: T_i = J_ii * view_axis_i + J_i2 * view_axis_z,
+            // |J_i2| <= f * 1.3 tanfov / tz); Wn = largest norm of the three view axes (1 for a rigid camera, not assumed)
+            const float* v = ws.hdr->cam.view;
+            const float n0 = sqrtf(v[0] * v[0] + v[4] * v[4] + v[8] * v[8]);
+            const float n1 = sqrtf(v[1] * v[1] + v[5] * v[5] + v[9] * v[9]);
+            const float n2 = sqrtf(v[2] * v[2] + v[6] * v[6] + v[10] * v[10]);
+            const float fxk = ws.hdr->cam.focal_x * (1.0f + 1.3f * ws.hdr->cam.tanfovx);
+            const float fyk = ws.hdr->cam.focal_y * (1.0f + 1.3f * ws.hdr->cam.tanfovy);
+            sm.cull_k = fmaxf(n0, fmaxf(n1, n2)) * fmaxf(fxk, fyk) * 1.001f;
+        }
+        if (is_foveated(MODE)) {
+            const int T = ws.hdr->tiles;
+            if (T <= LC_MAX)
+                for (int i = tid; i < T; i += PB) {
+                    const float tm = ws.tile_min[i];
+                    sm.lvl_code[i] = (uint8_t)((tm < 1.0f) ? 1 : (tm < 2.0f) ? 2 : (tm < 3.0f) ? 3 : (tm < 4.0f) ? 4 : 5);
+                }
+        }
     }
     __syncthreads();   // the only block barrier: from here on warps never wait for each other
     const CamParams& cam = sm.cam;
@@ -152,9 +195,103 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
     bool has_vchunk = false;
     unsigned visible_total = 0, cand_total = 0;
 
-    const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
-    for (int base = gwarp * 32; base < in.P; base += nwarps * 32) {
-        const int idx = base + lane;
+    uint32_t qn = 0;   // entries waiting in this warp's queue (warp-uniform)
+    const float cull_k = sm.cull_k;
+    const float scr_w = (float)(16 * cam.grid_x), scr_h = (float)(16 * cam.grid_y);
+    const bool use_codes = is_foveated(MODE) && ws.hdr->tiles <= LC_MAX;
+    // Dynamic work distribution: warps draw 128-Gaussian chunks from a global ticket counter (splats that cover hundreds
+    // of tiles are rare and random, a static partition leaves a 12 % tail).  The next ticket is requested one chunk ahead;
+    // its value is only looked at when the current chunk is used up.
+    const uint32_t nchunks = ((uint32_t)in.P + PRE_CHUNK - 1) / PRE_CHUNK;
+    auto request_ticket = [&]() -> uint32_t { return lane == 0 ? atomicAdd(&ws.hdr->pre_chunk, 1u) : 0u; };
+    uint32_t cur = __shfl_sync(0xffffffffu, request_ticket(), 0);
+    uint32_t nxt_raw = request_ticket();
+    int batch = 0;
+    for (;;) {
+        const bool have_input = cur < nchunks;
+        const int base0 = have_input ? (int)(cur * PRE_CHUNK + batch * 32) : in.P;
+        // ---------------- phase 0: conservative screen cull + compaction (lane = Gaussian) ----------------
+        // Four in five Gaussians of a frame end with an empty tile rectangle.  The reference finds that out at the end of
+        // the full projection; here a bound on the radius decides it first:  lambda_max(Sigma2D) <= 2 (k/tz)^2
+        // lambda_max(Sigma3D) + 0.62  (|T row| <= k/tz; lambda_1 = mid + sqrt(max(0.1, ((cxx-cyy)/2)^2 + cxy^2)) <=
+        // max(cxx,cyy) + |cxy| + 0.317), lambda_max(Sigma3D) <= (mod * s_max * (|1-|q|^2| + |q|^2))^2  (R(q) = (1-|q|^2) I +
+        // |q|^2 R(q/|q|)).  A Gaussian whose mean lies further outside the tile grid than that radius (plus slack for every
+        // rounding involved) has an empty rectangle in the exact code as well — it is dropped here, radii = 0, exactly
+        // the reference's outcome; everything else (and anything non-finite) goes on to the exact projection.  Survivors
+        // are compacted through a per-warp queue, so phases A-C always run on a full warp of live Gaussians.
+        if (base0 < in.P) {
+            const int idx0 = base0 + lane;
+            bool keep = false;
+            if (idx0 < in.P) {
+                // all inputs of the bound are requested before the first one is used: one memory round trip, not two
+                const float mx = in.means3D[3 * (size_t)idx0], my = in.means3D[3 * (size_t)idx0 + 1], mz = in.means3D[3 * (size_t)idx0 + 2];
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+                if (in.cov3D_precomp == nullptr) {
+                    sx = in.scales[3 * (size_t)idx0]; sy = in.scales[3 * (size_t)idx0 + 1]; sz = in.scales[3 * (size_t)idx0 + 2];
+                    q = *reinterpret_cast<const float4*>(in.rotations + 4 * (size_t)idx0);
+                }
+                const float tz = xform_row(cam.view, 2, mx, my, mz);
+                if (!(tz <= 0.2f)) {                  // same expression, same bits as the exact near-plane test (NaN passes)
+                    float lam3;                       // bound on the largest eigenvalue of Sigma3D
+                    if (in.cov3D_precomp != nullptr) {
+                        const float* c = in.cov3D_precomp + 6 * (size_t)idx0;
+                        lam3 = sqrtf(c[0] * c[0] + c[3] * c[3] + c[5] * c[5] + 2.0f * (c[1] * c[1] + c[2] * c[2] + c[4] * c[4]));
+                    } else {
+                        const float qn2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+                        const float rn = fabsf(1.0f - qn2) + qn2;
+                        const float sm_ = fmaxf(fabsf(sx), fmaxf(fabsf(sy), fabsf(sz))) * fabsf(cam.scale_modifier) * rn;
+                        lam3 = sm_ * sm_;
+                    }
+                    const float kt = cull_k / tz;
+                    const float lam2 = 2.0f * kt * kt * lam3 * 1.01f + 0.62f;
+                    const float rb = 3.01f * sqrtf(lam2) + 2.0f;
+                    const float hx = xform_row(cam.proj, 0, mx, my, mz);
+                    const float hy = xform_row(cam.proj, 1, mx, my, mz);
+                    const float hw = xform_row(cam.proj, 3, mx, my, mz);
+                    const float pw = __frcp_rn(FA(hw, 0.0000001f));
+                    const float px = ((FM(hx, pw) + 1.0f) * (float)cam.W - 1.0f) * 0.5f;
+                    const float py = ((FM(hy, pw) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
+                    const float ex = rb + 1.0f + 1e-5f * fabsf(px), ey = rb + 1.0f + 1e-5f * fabsf(py);
+                    // exact rect: x1 = clamp(trunc((px + r + 15)/16)), x0 = clamp(trunc((px - r)/16)); empty iff x1 <= x0 or y1 <= y0
+                    const bool out = (px + ex + 16.0f < 0.0f) || (px - ex > scr_w + 1.0f) || (py + ey + 16.0f < 0.0f) || (py - ey > scr_h + 1.0f);
+                    keep = !out;                      // NaN anywhere: comparisons are false -> keep
+                }
+                if (!keep) in.radii[idx0] = 0;
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (keep) wm.queue[qn + __popc(km & lt_mask)] = (uint32_t)idx0;
+            qn += __popc(km);
+            __syncwarp();
+        }
+        if (have_input && ++batch == PRE_CHUNK / 32) {
+            batch = 0;
+            cur = __shfl_sync(0xffffffffu, nxt_raw, 0);
+            nxt_raw = request_ticket();
+            if (cur + 1 < nchunks) {   // full chunks only: the prefetched lines must lie inside the tensors
+                // the new chunk's inputs start their way up from HBM now (means 12 lines, scales 12, rotations 16)
+                const size_t g0 = (size_t)cur * PRE_CHUNK;
+                const char* pm = (const char*)(in.means3D + 3 * g0) + 128 * lane;
+                if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
+                if (in.cov3D_precomp == nullptr) {
+                    const char* ps = (const char*)(in.scales + 3 * g0) + 128 * lane;
+                    const char* pr = (const char*)(in.rotations + 4 * g0) + 128 * lane;
+                    if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps));
+                    if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+                }
+            }
+        }
+        const bool input_done = !(cur < nchunks);
+        if (qn < 32 && !(input_done && qn > 0)) {
+            if (input_done) break;
+            continue;
+        }
+        const bool valid_lane = (uint32_t)lane < qn;
+        const int idx = valid_lane ? (int)wm.queue[lane] : in.P;
+        __syncwarp();
+        if (qn > 32) { const uint32_t v = (32 + lane < (int)qn) ? wm.queue[32 + lane] : 0u; __syncwarp(); wm.queue[lane] = v; }
+        qn = qn > 32 ? qn - 32 : 0;
+        wm.gid[lane] = (uint32_t)idx;
         // ---------------- phase A: projection (lane = Gaussian) ----------------
         Splat s;
         float c3[6];
@@ -162,6 +299,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         float hl = 0.0f;
         if (idx < in.P) {
             const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
+            if (is_foveated(MODE)) hl = in.highest_levels[idx];
             if (in.cov3D_precomp != nullptr) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) c3[k] = in.cov3D_precomp[6 * (size_t)idx + k];
@@ -176,13 +314,14 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         if (ok) {
             const bool single0 = ((uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0)) == 1u;
             int cx0 = s.x0, cy0 = s.y0, cx1 = s.x1, cy1 = s.y1;
+            uint32_t hcode = 0;
             if (is_foveated(MODE)) {
-                hl = in.highest_levels[idx];
                 // tiles outside the level's bounding box fail `tile_min < hl + 1` anyway: do not even enumerate them
                 const int li = (int)hl;
                 if (hl >= 0.0f && hl <= (float)(FOV_LEVELS - 1) && (float)li == hl) {
                     cx0 = max(cx0, sm.bbox[li][0]); cy0 = max(cy0, sm.bbox[li][1]);
                     cx1 = min(cx1, sm.bbox[li][2]); cy1 = min(cy1, sm.bbox[li][3]);
+                    if (use_codes) hcode = (uint32_t)li + 1u;
                 }
             }
             if (!single0 && true) {
@@ -215,7 +354,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
             wm.dbits[lane] = __float_as_uint(s.depth);
             wm.x0[lane] = cx0; wm.y0[lane] = cy0; wm.w[lane] = cw; wm.rw[lane] = 1.0f / (float)max(cw, 1);
-            if (is_foveated(MODE)) wm.hl1[lane] = FA(hl, 1.0f);
+            if (is_foveated(MODE)) { wm.hl1[lane] = FA(hl, 1.0f); wm.hcode[lane] = hcode; }
         }
         wm.cnt[lane] = 0;
         // exclusive scan of the candidate counts over the warp; compact list of non-empty owners
@@ -253,7 +392,10 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                 tile = (uint32_t)ty * gx + tx;
                 single = wm.single[owner] != 0;
                 pass = true;
-                if (is_foveated(MODE)) pass = ws.tile_min[tile] < wm.hl1[owner];
+                if (is_foveated(MODE)) {
+                    const uint32_t hc = wm.hcode[owner];
+                    pass = hc ? (hc >= (uint32_t)sm.lvl_code[tile]) : (ws.tile_min[tile] < wm.hl1[owner]);
+                }
                 if (pass && !single) {
                     const float cx = wm.px[owner], cy = wm.py[owner];
                     const float e1x = wm.e1x[owner], e1y = wm.e1y[owner], e2x = wm.e2x[owner], e2y = wm.e2y[owner];
@@ -263,6 +405,9 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                     const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
                     pass = obb_hits_tile(oc, cx, cy, e1x, e1y, e2x, e2y, l1, l2, tcx, tcy);
                 }
+                // RED (no return value).  Measured alternative: taking the returned rank here so that the scatter needs no
+                // atomics costs k_pre +0.05 ms (even with the dependent store deferred by a round) and saves the scatter
+                // 0.02 ms — the scatter is bound by its 8-byte scattered stores, not by its cursor atomics.
                 if (pass) atomicAdd(&ws.tile_count[(size_t)tile * CSTRIDE], 1u);
             }
             // per-owner bookkeeping: a Gaussian is visible iff any of its candidate tiles survives (benign same-value race).
@@ -288,7 +433,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                     const uint32_t pos = chunk_base + chunk_used + __popc(passmask & lt_mask);
                     if (pos < stage_cap) {
                         ws.stage_tile[pos] = tile;
-                        ws.stage_key[pos] = ((uint64_t)wm.dbits[owner] << 32) | (uint32_t)(base + (int)owner);
+                        ws.stage_key[pos] = ((uint64_t)wm.dbits[owner] << 32) | wm.gid[owner];
                     }
                 }
                 chunk_used += np;
@@ -351,6 +496,15 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
     }
     if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
     if (lane == 0 && cand_total) atomicAdd(&ws.hdr->stats.reserved[2], cand_total);   // candidate tiles enumerated
+    // ---- the last CTA to get here scans the tile histogram (threadFenceReduction pattern) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sm.scan.is_last = (atomicAdd(&ws.hdr->pre_done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (sm.scan.is_last) {
+        __threadfence();
+        tile_scan_block<PB>(ws, ws.hdr->tiles, sm.scan);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -499,38 +653,76 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Scatter: staged instance -> its tile's segment of the key array (cursor allocation inside the segment).  12 B in, one
+// L2 fetch-and-add and one scattered 8-byte store per instance; the next batch's loads are in flight while this batch is
+// placed.  Bound by the scattered stores (61 G/s measured with or without the atomics).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scatter_role(const Workspace& ws, const uint32_t t, const uint32_t nthreads) {
+    const uint32_t n = min(ws.hdr->stage_cursor, ws.stage_cap);
+    const uint32_t cap = ws.hdr->cap;
+    constexpr int U = 4;
+    uint32_t tl[U], ntl[U];
+    unsigned long long k[U], nk[U];
+    auto load = [&](uint32_t i0, uint32_t* T, unsigned long long* K) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * nthreads;
+            const bool in = i < n;
+            T[u] = in ? __ldcs(&ws.stage_tile[i]) : TILE_INVALID;
+            K[u] = in ? __ldcs(reinterpret_cast<const unsigned long long*>(&ws.stage_key[i])) : 0ull;
+        }
+    };
+    if (t < n) load(t, tl, k);
+    for (uint32_t i0 = t; i0 < n; i0 += nthreads * U) {
+        const uint32_t nx = i0 + nthreads * U;
+        if (nx < n) load(nx, ntl, nk);
+        uint32_t off[U], r[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (tl[u] != TILE_INVALID) {
+                off[u] = ws.tile_offset[tl[u]];
+                r[u] = atomicAdd(&ws.tile_cursor[(size_t)tl[u] * CSTRIDE], 1u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (tl[u] != TILE_INVALID) {
+                const uint32_t slot = off[u] + r[u];
+                if (slot < cap) ws.keysA[slot] = k[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { tl[u] = ntl[u]; k[u] = nk[u]; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(Workspace ws) {
+    scatter_role(ws, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
 constexpr int TSLOT_FOV = 72;   // floats per slot: [0,56) SH-rest window, [56,68) 4 dc triplets, [68,72) 4 opacities
 constexpr int TSLOT_PS1 = 56;   // floats per slot: [0,56) SH window (192 B when aligned)
 
+// Colour role of one warp: `slots` = this warp's [32][SLOT] floats of shared memory, `bar` its mbarrier (count 32),
+// gw / nw = index of the warp among / number of all colour warps of the grid.
 template <int MODE>
-__global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs in, size_t shs_floats) {
+__device__ __forceinline__ void color_tma_role(const Workspace& ws, const FrameInputs& in, const size_t shs_floats,
+                                               float* slots, uint64_t* bar, const uint32_t gw, const uint32_t nw,
+                                               const float* campos_s, const int deg, const int M) {
     constexpr int SLOT = (MODE == MODE_FOV) ? TSLOT_FOV : TSLOT_PS1;
-    __shared__ __align__(16) float tbuf[CW][32][SLOT];
-    __shared__ __align__(8) uint64_t bars[CW];
-    __shared__ float campos_s[3];
-    __shared__ int deg_s, M_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 3) campos_s[tid] = ws.hdr->cam.campos[tid];
-    if (tid == 0) { deg_s = ws.hdr->cam.sh_degree; M_s = ws.hdr->cam.M; }
-    if (lane == 0) {
-        mbar_init(&bars[warp], 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int deg = deg_s, M = M_s;
+    const int lane = threadIdx.x & 31;
     const int nsh = (in.shs != nullptr) ? 3 * M : 0;
     const uint32_t nslots = min(ws.hdr->vis_cursor, ws.vis_cap);
-    uint64_t* bar = &bars[warp];
     uint32_t parity = 0;
     const uintptr_t shs_beg = (uintptr_t)in.shs, shs_end = shs_beg + shs_floats * 4;
-    const uint32_t gw = blockIdx.x * CW + warp, nw = gridDim.x * CW;
     for (uint32_t s0 = gw * 32; s0 < nslots; s0 += nw * 32) {
         const uint32_t slot = s0 + lane;
         uint32_t id = TILE_INVALID, lv = 0;
         if (slot < nslots) { id = ws.vis_list[slot]; lv = ws.vis_lv[slot]; }
         const bool valid = id != TILE_INVALID;
         if (__ballot_sync(0xffffffffu, valid) == 0) continue;
-        float* b = tbuf[warp][lane];
+        float* b = slots + lane * SLOT;
         int sh_off = 0;          // float offset of this Gaussian's SH block inside its window
         bool sh_direct = false;  // window would leave the tensor: plain loads instead
         uint32_t tx = 0;
@@ -613,111 +805,100 @@ __global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs
     }
 }
 
+// Measured and dropped: running the colour gathers and the scatter as two warp roles of ONE launch.  Alone they take
+// 0.159 ms and 0.155 ms, fused 0.328 ms — both are bound by the same thing (random 32-byte sectors through L2/HBM), so
+// there is nothing to overlap.  They stay two back-to-back launches, each at its own best occupancy.
+template <int MODE>
+__global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs in, size_t shs_floats) {
+    constexpr int SLOT = (MODE == MODE_FOV) ? TSLOT_FOV : TSLOT_PS1;
+    __shared__ __align__(16) float tbuf[CW][32][SLOT];
+    __shared__ __align__(8) uint64_t bars[CW];
+    __shared__ float campos_s[3];
+    __shared__ int deg_s, M_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 3) campos_s[tid] = ws.hdr->cam.campos[tid];
+    if (tid == 0) { deg_s = ws.hdr->cam.sh_degree; M_s = ws.hdr->cam.M; }
+    if (lane == 0) {
+        mbar_init(&bars[warp], 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    color_tma_role<MODE>(ws, in, shs_floats, &tbuf[warp][0][0], &bars[warp], blockIdx.x * CW + warp, gridDim.x * CW, campos_s,
+                         deg_s, M_s);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// Tile scan: exclusive prefix sum of the per-tile histogram (one block); publishes N and the overflow flag.
+// Tile scan: exclusive prefix sum of the per-tile histogram by ONE CTA of NT threads (the last CTA of k_pre); publishes N,
+// the overflow flag and the heavy-first tile order.  Counters are read with ld.cg: they were only ever touched by L2 atomics.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_tile_scan(Workspace ws, int T) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    __shared__ uint32_t max_s;
-    __shared__ uint32_t bucket_cnt[33], bucket_base[33];
+template <int NT>
+__device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s) {
+    constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { carry_s = 0; max_s = 0; }
-    if (threadIdx.x < 33) bucket_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s.carry = 0; s.maxv = 0; }
+    if (threadIdx.x < 33) s.bucket_cnt[threadIdx.x] = 0;
     __syncthreads();
     uint32_t local_max = 0;
-    for (int base = 0; base < T; base += 1024) {
+    for (int base = 0; base < T; base += NT) {
         const int i = base + threadIdx.x;
-        const uint32_t v = (i < T) ? ws.tile_count[(size_t)i * CSTRIDE] : 0u;
+        const uint32_t v = (i < T) ? __ldcg(&ws.tile_count[(size_t)i * CSTRIDE]) : 0u;
         local_max = max(local_max, v);
+        {   // size-class histogram, one shared atomic per distinct class in the warp (a few classes hold most tiles)
+            const int cls = (i < T) ? (v ? 32 - __clz(v) : 0) : 33 + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, cls);
+            if (i < T && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s.bucket_cnt[cls], (uint32_t)__popc(peers));
+        }
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
+        if (lane == 31) s.warp_sums[wid] = x;
         __syncthreads();
         if (wid == 0) {
-            uint32_t w = warp_sums[lane];
+            uint32_t w = (lane < NW) ? s.warp_sums[lane] : 0u;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += y;
             }
-            warp_sums[lane] = w;
+            if (lane < NW) s.warp_sums[lane] = w;
         }
         __syncthreads();
-        const uint32_t carry = carry_s;
-        const uint32_t incl = x + (wid ? warp_sums[wid - 1] : 0u) + carry;
+        const uint32_t carry = s.carry;
+        const uint32_t incl = x + (wid ? s.warp_sums[wid - 1] : 0u) + carry;
         if (i < T) ws.tile_offset[i] = incl - v;
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
+        if (threadIdx.x == NT - 1) s.carry = incl;
         __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if (lane == 0) atomicMax(&max_s, local_max);
+    if (lane == 0) atomicMax(&s.maxv, local_max);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t total = carry_s;
+        const uint32_t total = s.carry;
         ws.tile_offset[T] = total;
         ws.hdr->stats.num_rendered = total;
         ws.hdr->stats.overflow = (total > ws.hdr->cap || ws.hdr->stage_cursor > ws.stage_cap) ? 1u : 0u;
-        ws.hdr->stats.max_tile_instances = max_s;
-    }
-    // tile order for the per-tile kernels: descending power-of-two size class (longest-processing-time-first)
-    for (int i = threadIdx.x; i < T; i += 1024) {
-        const uint32_t c = ws.tile_count[(size_t)i * CSTRIDE];
-        atomicAdd(&bucket_cnt[c ? 32 - __clz(c) : 0], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+        ws.hdr->stats.max_tile_instances = s.maxv;
+        // tile order for the per-tile kernels: descending power-of-two size class (longest-processing-time-first)
         uint32_t run = 0;
-        for (int b = 32; b >= 0; b--) { bucket_base[b] = run; run += bucket_cnt[b]; ws.hdr->cum_class[b] = run; }
+        for (int b = 32; b >= 0; b--) { s.bucket_base[b] = run; run += s.bucket_cnt[b]; ws.hdr->cum_class[b] = run; }
         ws.hdr->cum_class[33] = 0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < T; i += 1024) {
-        const uint32_t c = ws.tile_count[(size_t)i * CSTRIDE];
-        const uint32_t pos = atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u);
-        ws.tile_order[pos] = (uint32_t)i;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Scatter: staged instance -> its tile's segment of the key array (cursor allocation inside the segment).
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(Workspace ws) {
-    const uint32_t n = min(ws.hdr->stage_cursor, ws.stage_cap);
-    const uint32_t cap = ws.hdr->cap;
-    // each instance is a chain load(tile) -> atomic(cursor) -> store(key); four chains per thread are kept in flight
-    constexpr int U = 4;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
-        uint32_t t[U];
-        uint64_t k[U];
-        uint32_t off[U], r[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + u * stride;
-            t[u] = (i < n) ? ws.stage_tile[i] : TILE_INVALID;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (t[u] != TILE_INVALID) {
-                k[u] = ws.stage_key[i0 + u * stride];
-                off[u] = ws.tile_offset[t[u]];
-                r[u] = atomicAdd(&ws.tile_cursor[(size_t)t[u] * CSTRIDE], 1u);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (t[u] != TILE_INVALID) {
-                const uint32_t slot = off[u] + r[u];
-                if (slot < cap) ws.keysA[slot] = k[u];
-            }
-        }
+    for (int base = 0; base < T; base += NT) {
+        const int i = base + threadIdx.x;
+        const uint32_t c = (i < T) ? __ldcg(&ws.tile_count[(size_t)i * CSTRIDE]) : 0u;
+        const int cls = (i < T) ? (c ? 32 - __clz(c) : 0) : 33 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, cls);
+        const unsigned lower = peers & ((1u << lane) - 1u);
+        uint32_t pos = 0;
+        if (i < T && lower == 0) pos = atomicAdd(&s.bucket_base[cls], (uint32_t)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1) + __popc(lower);
+        if (i < T) ws.tile_order[pos] = (uint32_t)i;
     }
 }
 
@@ -754,11 +935,6 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
         case MODE_SMFR: k_color<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
         default: k_color<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in); break;
     }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tile_scan(const Workspace& ws, int T, cudaStream_t st) {
-    k_tile_scan<<<1, 1024, 0, st>>>(ws, T);
     return cudaGetLastError();
 }
 

@@ -211,6 +211,8 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->tiles = a.tiles;
             h->cap = a.cap;
             h->stage_cursor = 0;
+            h->pre_done = 0;
+            h->pre_chunk = 0;
             h->vis_cursor = 0;
         }
         if (i < FOV_LEVELS * 4) (&h->lvl_bbox[0][0])[i] = ((i & 3) < 2) ? 0x7fffffff : -1;
@@ -367,12 +369,10 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
         if (num_sms <= 0) num_sms = 148;
     }
     prof_mark(1, st);
-    launch_pre(ws, in, (Mode)MODE, num_sms, st);
-    STAGE_CHECK();
-    launch_color(ws, in, (Mode)MODE, num_sms, st);
+    launch_pre(ws, in, (Mode)MODE, num_sms, st);      // + tile scan, by the last CTA to finish
     STAGE_CHECK();
     prof_mark(2, st);
-    launch_tile_scan(ws, T, st);
+    launch_color(ws, in, (Mode)MODE, num_sms, st);
     STAGE_CHECK();
     prof_mark(3, st);
     launch_scatter(ws, num_sms, st);

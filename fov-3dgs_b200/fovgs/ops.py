@@ -523,7 +523,7 @@ def geometry(item, mode, P, W, H):
     return {"means2D": means2D, "depths": depths, "conic": conic, "cov3D": cov3D, "rgb": rgb}
 
 
-STAGE_NAMES = ("setup", "preprocess", "tile_scan", "scatter", "tile_sort", "blend")
+STAGE_NAMES = ("setup", "preprocess", "color", "scatter", "tile_sort", "blend")
 
 
 def profile_enable(on=True):

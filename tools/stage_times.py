@@ -14,17 +14,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", default="sum"); ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--size", default="big"); ap.add_argument("--backward", action="store_true")
+    ap.add_argument("--split", default="0", help="comma list of FOVGS_OPT_SPLIT_STAGES settings to run, e.g. 0,1")
     a = ap.parse_args()
     if a.size == "big": scn = synth.make_scene_bicycle(6000000, 1); cams = synth.ring_cameras(30)
     else: scn = synth.make_scene_bicycle(300000, 1, log_scale_mu=-3.6); cams = synth.ring_cameras(30, 800, 600)
     bg = torch.zeros(3, device="cuda")
-    ops.profile_enable(True)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    fwd_ms, bwd_ms = [], []
-    if a.variant == "fov":
+    if a.variant in ("fov", "smfr"):
         sc = to_cuda(synth.add_foveation(scn))
     else:
         sc = to_cuda(scn)
+    ops.profile_enable(True)
+    run(a, sc, cams, bg, ev, 0)
+
+
+def run(a, sc, cams, bg, ev, split):
+    fwd_ms, bwd_ms = [], []
     for f in range(a.frames + 2):
         c = to_cuda(cams[f % 30]); rs = settings(c, sc["sh_degree"], bg)
         e0, e1, e2 = ev(), ev(), ev()
@@ -32,6 +37,9 @@ def main():
         if a.variant == "fov":
             gaze = torch.tensor(synth.GAZES_9[f % 9], dtype=torch.float32, device="cuda")
             out = ops.forward_fov(sc["means3D"], sc["opacities4"], sc["scales"], sc["rotations"], sc["shs_rest"], sc["shs_dcs"], sc["highest_levels"], gaze, 0.05, True, rs)
+        elif a.variant == "smfr":
+            gaze = torch.tensor(synth.GAZES_9[f % 9], dtype=torch.float32, device="cuda")
+            out = ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"], sc["highest_levels"], gaze, 0.05, True, rs)
         else:
             mode = ops.MODE_SUM if a.variant == "sum" else ops.MODE_OBB
             out = ops.forward_ps1(mode, sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], None, sc["shs"], None, rs)
@@ -44,7 +52,7 @@ def main():
         if f >= 2: fwd_ms.append(e0.elapsed_time(e1)); bwd_ms.append(e1.elapsed_time(e2))
     st = ops.profile_read_all()[2:]
     mean = {k: float(np.mean([s[k] for s in st])) for k in ops.STAGE_NAMES}
-    print("variant", a.variant, "fwd_ms_mean", np.mean(fwd_ms), "bwd_ms_mean", np.mean(bwd_ms), "stages", {k: round(v, 4) for k, v in mean.items()}, "stats", ops.last_stats)
+    print("split", split, "variant", a.variant, "fwd_ms_mean", np.mean(fwd_ms), "bwd_ms_mean", np.mean(bwd_ms), "stages", {k: round(v, 4) for k, v in mean.items()}, "stats", ops.last_stats)
 
 
 if __name__ == "__main__":
