@@ -15,7 +15,9 @@ value  : whole-job frames/s with every input resident in HBM, timed on the devic
 e2e    : the same frames/s through the public API with HOST inputs: per frame the camera matrices + gaze are copied
          from pinned host memory and the [3,H,W] image is copied back to pinned host memory (copy of frame i overlaps
          the rendering of frame i+1 on a copy stream, two host buffers; all copies finish inside the timed region), wall
-         clock with a synchronize on both sides.
+         clock with a synchronize on both sides.  The library runs in its pipelined serving mode
+         (ops.set_deferred_check: the 64-byte frame statistics of frame i are inspected when frame i+1 is queued instead
+         of blocking on them); `e2e.sync_value` is the same loop with the default blocking check after every frame.
 roofline: the dominant kernel (largest mean stage time from CUDA events recorded by the library between its stages
          over the timed region) against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
 cpu_baseline: the CPU oracle (oracle/fovgs_oracle.c, a port: the reference ships no CPU path) on ONE frame of the same
@@ -224,22 +226,34 @@ def run_ours(args, wl, rank, world, dev):
             img, _ = render(settings(cd), g)      # public API; reads the 64-byte frame statistics (host sync per frame)
             readback.push(img)
 
-        for f in frames[: args.warmup]:
-            e2e_frame(f)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for f in frames[args.warmup:]:
-            e2e_frame(f)
-        readback.drain()
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            dist.barrier()
+        def e2e_loop():
+            for f in frames[: args.warmup]:
+                e2e_frame(f)
+            readback.drain()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for f in frames[args.warmup:]:
+                e2e_frame(f)
+            readback.drain()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                dist.barrier()
+            return dt
 
-    return {"ms": ms, "e2e_s": e2e_s, "stages": stage_frames, "stats": stats, "clocks": clocks_summary(clk), "h2d": h2d, "d2h": d2h,
-            "launches_per_frame": 11}
+        e2e_sync_s = e2e_loop()                 # default API behaviour: one blocking 64-byte read per frame
+        ops.set_deferred_check(True)            # pipelined serving mode
+        try:
+            e2e_s = e2e_loop()
+            ops.check_pending(dev)
+        finally:
+            ops.set_deferred_check(False)
+
+    # kernels per frame: k_setup, k_tile_levels, k_tile_infos, k_pre (+ tile scan), k_color_tma, k_scatter, k_lazy_blend
+    return {"ms": ms, "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s, "stages": stage_frames, "stats": stats, "clocks": clocks_summary(clk),
+            "h2d": h2d, "d2h": d2h, "launches_per_frame": 7}
 
 
 def run_reference(args, wl, rank, world, dev):
@@ -393,10 +407,10 @@ def main():
         res = run_ours(args, wl, rank, world, dev)
 
     # max over ranks (device time and wall time)
-    t = torch.tensor([res["ms"], res["e2e_s"]], dtype=torch.float64, device=dev)
+    t = torch.tensor([res["ms"], res["e2e_s"], res.get("e2e_sync_s", 0.0)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_max = float(t[0]), float(t[1])
+    ms_max, e2e_max, e2e_sync_max = float(t[0]), float(t[1]), float(t[2])
     total_frames = args.steps * world
     value = total_frames / (ms_max * 1e-3)
     e2e_v = total_frames / e2e_max
@@ -420,6 +434,8 @@ def main():
             line["gpu_launches"] = 0
         else:
             line["gpu_launches"] = res["launches_per_frame"] * args.steps
+            line["e2e"]["mode"] = "pipelined (deferred statistics check); sync_value = blocking check per frame"
+            line["e2e"]["sync_value"] = total_frames / e2e_sync_max
             line["roofline"] = roofline(res, wl, args.steps)
             if not args.no_cpu_baseline and world == 1:
                 try:

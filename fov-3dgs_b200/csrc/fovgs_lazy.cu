@@ -464,36 +464,50 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     }
     // ---- MSD partition of the tile's keys by their highest varying depth byte ----
     uint64_t* gB = ws.keysB + sbeg;
+    constexpr int MU = 8;   // keys in flight per thread in the partition passes (L2 round trips overlap)
+    // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile).  The position is
+    // guessed from the first 2048 keys (the scatter left them in arbitrary order) and verified for free by the histogram
+    // pass, which ORs the differences of ALL keys; a wrong guess (never seen in practice) repeats the histogram.
+    const uint64_t k0 = gA[0];
+    auto digit_shift = [](uint32_t vhi) { return vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32; };
     if (tid == 0) sm.vary = 0ull;
-    sm.bucket_cur[tid] = 0;
     __syncthreads();
-    constexpr int MU = 8;   // keys in flight per thread in the three partition passes (L2 round trips overlap)
     {
-        const uint64_t k0 = gA[0];
+        uint64_t v = 0;
+        uint64_t k[MU];
+#pragma unroll
+        for (int u = 0; u < MU; u++) { const uint32_t i = tid + u * 256; k[u] = (i < n) ? gA[i] : k0; }
+#pragma unroll
+        for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
+    }
+    __syncthreads();
+    int shift = digit_shift((uint32_t)(sm.vary >> 32));
+    for (;;) {
+        sm.bucket_cur[tid] = 0;
+        __syncthreads();
         uint64_t v = 0;
         for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
             uint64_t k[MU];
 #pragma unroll
             for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : k0; }
 #pragma unroll
-            for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
+            for (int u = 0; u < MU; u++) {
+                v |= (k[u] ^ k0);
+                if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+            }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
+        __syncthreads();
+        const int exact = digit_shift((uint32_t)(sm.vary >> 32));
+        if (exact == shift) break;
+        shift = exact;          // uniform over the CTA: sm.vary is complete after the barrier
+        __syncthreads();
     }
-    __syncthreads();
-    const uint32_t vhi = (uint32_t)(sm.vary >> 32);
-    // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile)
-    const int shift = vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32;
-    for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
-        uint64_t k[MU];
-#pragma unroll
-        for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
-#pragma unroll
-        for (int u = 0; u < MU; u++) if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
-    }
-    __syncthreads();
     {   // exclusive scan of the 256 bucket sizes
         const uint32_t c = sm.bucket_cur[tid];
         uint32_t x = c;
@@ -526,8 +540,8 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     bool all_done = false;
     while (b < 256 && !all_done) {
         const uint32_t g0 = sm.bucket_off[b];
-        int e = b;
-        while (e < 256 && sm.bucket_off[e + 1] - g0 <= (uint32_t)LCAP) e++;
+        // buckets [b, e) fit the shared buffer together: bucket_off is monotone, so the fitting ones form a prefix — count them
+        const int e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= (uint32_t)LCAP);
         if (e == b) {
             // one bucket larger than the shared buffer (>= 2048 keys agreeing in all depth bits above `shift`):
             // order it completely with the block radix sort on the global ping-pong ranges (this tile's slice of
