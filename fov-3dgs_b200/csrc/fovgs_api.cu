@@ -24,7 +24,7 @@ int fovgs_version(void) { return FOVGS_VERSION; }
 
 size_t fovgs_workspace_bytes(int32_t P, int32_t W, int32_t H, int64_t max_instances, int32_t foveated, int32_t ps1_mode) {
     if (P < 0 || W <= 0 || H <= 0 || max_instances < 0) return 0;
-    const Mode mode = foveated == 2 ? MODE_SMFR : foveated ? MODE_FOV : (ps1_mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB);
+    const Mode mode = foveated == 3 ? MODE_MMFR : foveated == 2 ? MODE_SMFR : foveated ? MODE_FOV : (ps1_mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB);
     return carve_workspace(nullptr, P, W, H, max_instances, mode).total_bytes;
 }
 
@@ -51,7 +51,7 @@ int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
     Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, MODE_FOV);
     if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
-    cudaError_t e = launch_setup(ws, a->cam, a->P, a->M_rest, MODE_FOV, a->gaze, a->alpha, (uint32_t)a->max_instances, st);
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->M_rest, MODE_FOV, a->gaze, a->alpha, 0.0f, (uint32_t)a->max_instances, st);
     if (e != cudaSuccess) return fail_cuda(e, "setup");
     FrameInputs in{};
     in.P = a->P; in.M = a->M_rest;
@@ -78,7 +78,7 @@ int fovgs_forward_smfr(const fovgs_smfr_fwd_args* a, void* stream) {
     if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
     Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, MODE_SMFR);
     if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
-    cudaError_t e = launch_setup(ws, a->cam, a->P, a->M, MODE_SMFR, a->gaze, a->alpha, (uint32_t)a->max_instances, st);
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->M, MODE_SMFR, a->gaze, a->alpha, 0.0f, (uint32_t)a->max_instances, st);
     if (e != cudaSuccess) return fail_cuda(e, "setup");
     FrameInputs in{};
     in.P = a->P; in.M = a->M;
@@ -88,6 +88,33 @@ int fovgs_forward_smfr(const fovgs_smfr_fwd_args* a, void* stream) {
     in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
     e = launch_forward(ws, in, W, H, MODE_SMFR, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_smfr");
+    return 0;
+}
+
+int fovgs_forward_mmfr(const fovgs_mmfr_fwd_args* a, void* stream) {
+    if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_cam(a->cam)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = a->cam.image_width, H = a->cam.image_height;
+    if (a->P < 0 || a->P > kMaxP) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3), num_points <= 2^30%s");
+    if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
+    if (a->P == 0) return 0;
+    if (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->shs || !a->gaze)
+        return fail(FOVGS_ERR_INVALID_ARG, "null input pointer (means3D/opacities/scales/rotations/shs/gaze)%s");
+    if (a->M <= 0) return fail(FOVGS_ERR_INVALID_ARG, "shs must hold at least the DC coefficient (M >= 1)%s");
+    if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
+    Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, MODE_MMFR);
+    if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->M, MODE_MMFR, a->gaze, a->alpha, a->cur_level, (uint32_t)a->max_instances, st);
+    if (e != cudaSuccess) return fail_cuda(e, "setup");
+    FrameInputs in{};
+    in.P = a->P; in.M = a->M;
+    in.means3D = a->means3D; in.opacities = a->opacities; in.scales = a->scales; in.rotations = a->rotations;
+    in.shs = a->shs;
+    in.radii = a->radii; in.out_color = a->out_color;
+    in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    e = launch_forward(ws, in, W, H, MODE_MMFR, a->cam.debug != 0, st);
+    if (e != cudaSuccess) return fail_cuda(e, "forward_mmfr");
     return 0;
 }
 
@@ -113,7 +140,7 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
     Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, mode);
     if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
-    cudaError_t e = launch_setup(ws, a->cam, a->P, a->colors_precomp ? 0 : a->M, mode, nullptr, 0.0f, (uint32_t)a->max_instances, st);
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->colors_precomp ? 0 : a->M, mode, nullptr, 0.0f, 0.0f, (uint32_t)a->max_instances, st);
     if (e != cudaSuccess) return fail_cuda(e, "setup");
     FrameInputs in{};
     in.P = a->P; in.M = a->M;

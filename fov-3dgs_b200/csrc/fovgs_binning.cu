@@ -176,8 +176,12 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             const int T = ws.hdr->tiles;
             if (T <= LC_MAX)
                 for (int i = tid; i < T; i += PB) {
-                    const float tm = ws.tile_min[i];
-                    sm.lvl_code[i] = (uint8_t)((tm < 1.0f) ? 1 : (tm < 2.0f) ? 2 : (tm < 3.0f) ? 3 : (tm < 4.0f) ? 4 : 5);
+                    if (MODE == MODE_MMFR) {
+                        sm.lvl_code[i] = ws.tile_skip[i] ? 5 : 1;      // every Gaussian carries code 1: passes iff not skipped
+                    } else {
+                        const float tm = ws.tile_min[i];
+                        sm.lvl_code[i] = (uint8_t)((tm < 1.0f) ? 1 : (tm < 2.0f) ? 2 : (tm < 3.0f) ? 3 : (tm < 4.0f) ? 4 : 5);
+                    }
                 }
         }
     }
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
         float hl = 0.0f;
         if (idx < in.P) {
             const float mx = in.means3D[3 * (size_t)idx], my = in.means3D[3 * (size_t)idx + 1], mz = in.means3D[3 * (size_t)idx + 2];
-            if (is_foveated(MODE)) hl = in.highest_levels[idx];
+            if (has_level_mask(MODE)) hl = in.highest_levels[idx];
             if (in.cov3D_precomp != nullptr) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) c3[k] = in.cov3D_precomp[6 * (size_t)idx + k];
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
             uint32_t hcode = 0;
             if (is_foveated(MODE)) {
                 // tiles outside the level's bounding box fail `tile_min < hl + 1` anyway: do not even enumerate them
-                const int li = (int)hl;
+                const int li = (int)hl;   // MMFR: hl stays 0 -> box 0 = the tiles of this level's call, code 1
                 if (hl >= 0.0f && hl <= (float)(FOV_LEVELS - 1) && (float)li == hl) {
                     cx0 = max(cx0, sm.bbox[li][0]); cy0 = max(cy0, sm.bbox[li][1]);
                     cx1 = min(cx1, sm.bbox[li][2]); cy1 = min(cy1, sm.bbox[li][3]);
@@ -394,7 +398,8 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                 pass = true;
                 if (is_foveated(MODE)) {
                     const uint32_t hc = wm.hcode[owner];
-                    pass = hc ? (hc >= (uint32_t)sm.lvl_code[tile]) : (ws.tile_min[tile] < wm.hl1[owner]);
+                    if (MODE == MODE_MMFR) pass = hc ? (sm.lvl_code[tile] == 1) : (ws.tile_skip[tile] == 0);
+                    else pass = hc ? (hc >= (uint32_t)sm.lvl_code[tile]) : (ws.tile_min[tile] < wm.hl1[owner]);
                 }
                 if (pass && !single) {
                     const float cx = wm.px[owner], cy = wm.py[owner];
@@ -607,7 +612,7 @@ __global__ void __launch_bounds__(CW * 32) k_color(Workspace ws, FrameInputs in)
                     cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
                     c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
                 }
-                if (MODE == MODE_SMFR) rec[2] = make_float4(in.opacities[id], c.x, c.y, c.z);   // REC_SMFR
+                if (shared_model(MODE)) rec[2] = make_float4(in.opacities[id], c.x, c.y, c.z);   // REC_SMFR
                 else rec[2] = make_float4(c.x, c.y, c.z, 0.f);
                 if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[id] = make_uchar4(cl0, cl1, cl2, 0);
             }
@@ -796,7 +801,7 @@ __device__ __forceinline__ void color_tma_role(const Workspace& ws, const FrameI
                     cl0 = c.x < 0; cl1 = c.y < 0; cl2 = c.z < 0;
                     c.x = fmaxf(c.x, 0.0f); c.y = fmaxf(c.y, 0.0f); c.z = fmaxf(c.z, 0.0f);
                 }
-                if (MODE == MODE_SMFR) rec[2] = make_float4(in.opacities[id], c.x, c.y, c.z);   // REC_SMFR
+                if (shared_model(MODE)) rec[2] = make_float4(in.opacities[id], c.x, c.y, c.z);   // REC_SMFR
                 else rec[2] = make_float4(c.x, c.y, c.z, 0.f);
                 if (MODE == MODE_SUM) reinterpret_cast<uchar4*>(ws.clamped)[id] = make_uchar4(cl0, cl1, cl2, 0);
             }
@@ -909,6 +914,7 @@ cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, in
         case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, 0, st>>>(ws, in); break;
         case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, 0, st>>>(ws, in); break;
         case MODE_SMFR: k_pre<MODE_SMFR><<<grid, PB, 0, st>>>(ws, in); break;
+        case MODE_MMFR: k_pre<MODE_MMFR><<<grid, PB, 0, st>>>(ws, in); break;
         default: k_pre<MODE_FOV><<<grid, PB, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();
@@ -925,6 +931,7 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
             case MODE_OBB: k_color_tma<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
             case MODE_SUM: k_color_tma<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
             case MODE_SMFR: k_color_tma<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
+            case MODE_MMFR: k_color_tma<MODE_MMFR><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
             default: k_color_tma<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
         }
         return cudaGetLastError();
@@ -933,6 +940,7 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
         case MODE_OBB: k_color<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in); break;
         case MODE_SUM: k_color<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in); break;
         case MODE_SMFR: k_color<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
+        case MODE_MMFR: k_color<MODE_MMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
         default: k_color<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();

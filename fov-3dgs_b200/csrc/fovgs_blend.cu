@@ -59,8 +59,23 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
         const int L1 = (int)tile_level_f;
         constexpr int R = rec_size(MODE);
         constexpr bool SMFR = MODE == MODE_SMFR;          // one shared (opacity, r, g, b) record in slot 2
-        const int S1 = SMFR ? 2 : 2 + L1;
-        if (!blending) {
+        const int S1 = shared_model(MODE) ? 2 : 2 + L1;
+        if (MODE == MODE_MMFR && ws.tile_skip[tile]) {
+            if (inside) { in.out_color[pix_id] = 0.f; in.out_color[HW + pix_id] = 0.f; in.out_color[2 * HW + pix_id] = 0.f; }
+            return;
+        }
+        // MMFR blending tiles (mmfr_pcheck_obb/cuda_rasterizer/forward.cu:255-418) run the plain loop with two changes:
+        // pixels that belong to the other level of the pair start out done, and the result is weighted at the end
+        float mm_x = 0.0f;
+        int mm_L1 = 0;
+        const bool mm_blend = MODE == MODE_MMFR && blending;
+        if (mm_blend) {
+            const float est = FF(FF((float)(tid & 15), ws.tile_gx[tile], FM((float)(tid >> 4), ws.tile_gy[tile])), 0.0625f, tile_level_f);
+            mm_L1 = (int)est;
+            mm_x = FM(FS(est, FA((float)mm_L1, kStartBlend)), 2.0f);
+            if (mm_x < 0.0f && (float)mm_L1 != hdr->cur_level) done = true;
+        }
+        if (!blending || mm_blend) {
             Prefetch<3> pf;
             auto fetch = [&](int progress) {
                 pf.valid = progress < total;
@@ -95,9 +110,18 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                 }
             }
             if (inside) {
-                in.out_color[pix_id] = FF(bg0, T, C0);
-                in.out_color[HW + pix_id] = FF(bg1, T, C1);
-                in.out_color[2 * HW + pix_id] = FF(bg2, T, C2);
+                float used = 1.0f;
+                if (mm_blend) {
+                    const float x = fmaxf(0.0f, fminf(1.0f, mm_x));
+                    const float m3 = FM(x, FM(x, -3.0f));
+                    const float nb = FF(x, FM(x, FA(x, x)), m3);
+                    const float w1 = FA(nb, 1.0f);
+                    used = ((float)mm_L1 == hdr->cur_level) ? w1 : FS(1.0f, w1);
+                }
+                const float o0 = FF(bg0, T, C0), o1 = FF(bg1, T, C1), o2 = FF(bg2, T, C2);
+                in.out_color[pix_id] = mm_blend ? FM(o0, used) : o0;
+                in.out_color[HW + pix_id] = mm_blend ? FM(o1, used) : o1;
+                in.out_color[2 * HW + pix_id] = mm_blend ? FM(o2, used) : o2;
             }
             if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
         } else {
@@ -114,14 +138,14 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                     const uint32_t id = plist[progress];
                     const float4* __restrict__ rec = ws.rec + (size_t)R * id;
                     pf.r[0] = rec[0]; pf.r[1] = rec[1]; pf.r[2] = rec[S1];
-                    if (!SMFR) pf.r[3] = rec[S1 + 1];
+                    if (MODE == MODE_FOV) pf.r[3] = rec[S1 + 1];
                 }
             };
             fetch(tid);
             float T1 = 1.0f, T2 = 1.0f, A0 = 0.f, A1 = 0.f, A2 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
             for (int i = 0; i < rounds; i++, toDo -= 256) {
                 if (__syncthreads_count(done) == 256) break;
-                if (pf.valid) { sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2]; if (!SMFR) sD[tid] = pf.r[3]; }
+                if (pf.valid) { sA[tid] = pf.r[0]; sB[tid] = pf.r[1]; sC[tid] = pf.r[2]; if (MODE == MODE_FOV) sD[tid] = pf.r[3]; }
                 batches_done = i + 1;
                 __syncthreads();
                 if (i + 1 < rounds) fetch((i + 1) * 256 + tid);
@@ -289,6 +313,7 @@ cudaError_t launch_blend(const Workspace& ws, const FrameInputs& in, int T, Mode
         case MODE_OBB: k_blend<MODE_OBB><<<T, 256, 0, st>>>(ws, in); break;
         case MODE_SUM: k_blend<MODE_SUM><<<T, 256, 0, st>>>(ws, in); break;
         case MODE_SMFR: k_blend<MODE_SMFR><<<T, 256, 0, st>>>(ws, in); break;
+        case MODE_MMFR: k_blend<MODE_MMFR><<<T, 256, 0, st>>>(ws, in); break;
         default: k_blend<MODE_FOV><<<T, 256, 0, st>>>(ws, in); break;
     }
     return cudaGetLastError();

@@ -104,12 +104,16 @@ __global__ void k_tile_levels(int T, float* __restrict__ tile_levels, const floa
     tile_levels[idx] = level;
 }
 
+// `mmfr` != 0: the multi-model baseline's variant — tile_min clamped at 0 before it is stored and classified
+// (mmfr_pcheck_obb/cuda_rasterizer/rasterizer_impl.cu:249-251) and the per-level tile selection of
+// compute_tile_skips_cuda (:277-304): skip unless cur_level - blend_width < tile_min < cur_level + 1.
 __global__ void k_tile_infos(int T, const float* __restrict__ tile_levels, const int tile_width_num,
                              const int tile_height_num, float* __restrict__ grad_y, float* __restrict__ grad_x,
                              float* __restrict__ tile_level_min, uint8_t* __restrict__ tile_blendings,
-                             FrameHeader* __restrict__ hdr) {
+                             FrameHeader* __restrict__ hdr, const int mmfr, const float cur_level,
+                             uint8_t* __restrict__ tile_skips) {
     auto idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool blend = false;
+    bool blend = false, skip = false;
     if (idx < (uint64_t)T) {
         int tile_y = idx / tile_width_num;
         int tile_x = idx % tile_width_num;
@@ -130,6 +134,15 @@ __global__ void k_tile_infos(int T, const float* __restrict__ tile_levels, const
 
         float max_delta = 0.5 * (fabsf(gx) + fabsf(gy));
         float tile_min = tile_level_f - max_delta;
+        if (mmfr) {
+            if (tile_min < 0) tile_min = 0;
+            float lb, hb;
+            lb = cur_level - kBlendWidth;
+            hb = cur_level + 1;
+            bool min_in = tile_min > lb && tile_min < hb;
+            skip = !min_in;
+            tile_skips[idx] = skip ? 1 : 0;
+        }
         tile_level_min[idx] = tile_min;
         float tile_min_i = float(int(tile_min));
         blend = ((tile_min - tile_min_i) > kStartBlend && (tile_min_i < (FOV_LEVELS - 1)));
@@ -146,7 +159,8 @@ __global__ void k_tile_infos(int T, const float* __restrict__ tile_levels, const
         const int tx = in_range ? (int)(idx % tile_width_num) : 0, ty = in_range ? (int)(idx / tile_width_num) : 0;
 #pragma unroll
         for (int l = 0; l < FOV_LEVELS; l++) {
-            const bool inl = in_range && (tm < (float)(l + 1));
+            // MMFR: one box (slot 0) around the tiles this level's call renders
+            const bool inl = in_range && (mmfr ? (l == 0 && !skip) : (tm < (float)(l + 1)));
             const int x0 = __reduce_min_sync(0xffffffffu, inl ? tx : 0x7fffffff);
             const int y0 = __reduce_min_sync(0xffffffffu, inl ? ty : 0x7fffffff);
             const int x1 = __reduce_max_sync(0xffffffffu, inl ? tx + 1 : -1);
@@ -170,7 +184,7 @@ struct SetupArgs {
     const float* campos;
     const float* bg;
     const float* gaze;
-    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier, alpha;
+    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier, alpha, cur_level;
     int W, H, gx, gy, sh_degree, M, P, tiles;
     uint32_t cap;
 };
@@ -207,6 +221,7 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->cam.sh_degree = a.sh_degree;
             h->cam.M = a.M;
             h->alpha = a.alpha;
+            h->cur_level = a.cur_level;
             h->P = a.P;
             h->tiles = a.tiles;
             h->cap = a.cap;
@@ -286,6 +301,7 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
         ws.tile_gx = (float*)take(T * 4);
         ws.tile_gy = (float*)take(T * 4);
         ws.tile_blend = (uint8_t*)take(T);
+        if (mode == MODE_MMFR) ws.tile_skip = (uint8_t*)take(T);   // after the tables every foveated layout shares
     }
     ws.rec = (float4*)take((size_t)P * 16 * rec_size(mode));
     ws.vis_cap = (uint32_t)((size_t)P + (size_t)P / 4 + (size_t)STAGE_MAX_BLOCKS * 8 * 128);
@@ -325,14 +341,14 @@ static inline void prof_mark(int i, cudaStream_t st) {
 }
 
 cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, int M, Mode mode, const float* gaze,
-                         float alpha, uint32_t cap, cudaStream_t st) {
+                         float alpha, float cur_level, uint32_t cap, cudaStream_t st) {
     SetupArgs a;
     a.view = cam.viewmatrix; a.proj = cam.projmatrix; a.campos = cam.campos; a.bg = cam.bg; a.gaze = gaze;
     a.tanfovx = cam.tanfovx; a.tanfovy = cam.tanfovy;
     // reference: focal = dim / (2.0f * tanfov)   (FOV/rasterizer_impl.cu:656-657)
     a.focal_y = cam.image_height / (2.0f * cam.tanfovy);
     a.focal_x = cam.image_width / (2.0f * cam.tanfovx);
-    a.scale_modifier = cam.scale_modifier; a.alpha = alpha;
+    a.scale_modifier = cam.scale_modifier; a.alpha = alpha; a.cur_level = cur_level;
     a.W = cam.image_width; a.H = cam.image_height;
     a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
     a.sh_degree = cam.sh_degree; a.M = M; a.P = P; a.tiles = a.gx * a.gy; a.cap = cap;
@@ -342,7 +358,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     if (is_foveated(mode)) {
         k_tile_levels<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, gaze, a.W, a.H, a.gx, alpha);
         k_tile_infos<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, a.gx, a.gy, ws.tile_gy, ws.tile_gx, ws.tile_min,
-                                                     ws.tile_blend, ws.hdr);
+                                                     ws.tile_blend, ws.hdr, mode == MODE_MMFR ? 1 : 0, cur_level, ws.tile_skip);
     }
     return cudaGetLastError();
 }
@@ -398,6 +414,7 @@ cudaError_t launch_forward(const Workspace& ws, const FrameInputs& in, int W, in
         case MODE_OBB: return forward_impl<MODE_OBB>(ws, in, W, H, debug, st);
         case MODE_SUM: return forward_impl<MODE_SUM>(ws, in, W, H, debug, st);
         case MODE_SMFR: return forward_impl<MODE_SMFR>(ws, in, W, H, debug, st);
+        case MODE_MMFR: return forward_impl<MODE_MMFR>(ws, in, W, H, debug, st);
         default: return forward_impl<MODE_FOV>(ws, in, W, H, debug, st);
     }
 }

@@ -741,11 +741,39 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
     const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
     const size_t HW = (size_t)H * W;
     if (is_foveated(MODE)) {
+        if (MODE == MODE_MMFR && ws.tile_skip[tile]) {
+            // not a tile of this level's call: the reference leaves its zero-initialised image untouched here
+            if (inside) { in.out_color[pix_id] = 0.f; in.out_color[HW + pix_id] = 0.f; in.out_color[2 * HW + pix_id] = 0.f; }
+            return;
+        }
         const bool blending = ws.tile_blend[tile] != 0;
         const float tile_level_f = ws.tile_min[tile];
         const int L1 = (int)tile_level_f;
         constexpr int R = rec_size(MODE);
-        const int S1 = (MODE == MODE_FOV) ? 2 + L1 : 2;   // SMFR: the one shared (opacity, r, g, b) record
+        const int S1 = (MODE == MODE_FOV) ? 2 + L1 : 2;   // SMFR / MMFR: the one shared (opacity, r, g, b) record
+        if (MODE == MODE_MMFR && blending) {
+            // mmfr_pcheck_obb/cuda_rasterizer/forward.cu:255-418: one composite, weighted by this level's share of the
+            // smoothstep; pixels whose level estimate belongs to the other level of the pair do nothing at all
+            const float cur_level = hdr->cur_level;
+            const float est = FF(FF((float)lxi, ws.tile_gx[tile], FM((float)lyi, ws.tile_gy[tile])), 0.0625f, tile_level_f);
+            const int L1i = (int)est;
+            const float xr = FM(FS(est, FA((float)L1i, kStartBlendL)), 2.0f);   // (est - (L1 + start_blend)) / blend_width
+            PixFov px;
+            px.init(inside);
+            if (xr < 0.0f && (float)L1i != cur_level) px.done = true;
+            lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
+            if (inside) {
+                const float x = fmaxf(0.0f, fminf(1.0f, xr));
+                const float m3 = FM(x, FM(x, -3.0f));
+                const float nb = FF(x, FM(x, FA(x, x)), m3);
+                const float w1 = FA(nb, 1.0f);
+                const float used = ((float)L1i == cur_level) ? w1 : FS(1.0f, w1);
+                in.out_color[pix_id] = FM(FF(bg0, px.T, px.C0), used);
+                in.out_color[HW + pix_id] = FM(FF(bg1, px.T, px.C1), used);
+                in.out_color[2 * HW + pix_id] = FM(FF(bg2, px.T, px.C2), used);
+            }
+            return;
+        }
         if (!blending) {
             PixFov px;
             px.init(inside);
@@ -759,9 +787,9 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
             const int L2 = L1 + 1;
             const float dxl = (float)lxi, dyl = (float)lyi;
             const float est = FF(FF(dxl, ws.tile_gx[tile], FM(dyl, ws.tile_gy[tile])), 0.0625f, tile_level_f);
-            typename std::conditional<MODE == MODE_FOV, PixFovBlend, PixSmfrBlend>::type px;
+            typename std::conditional<MODE == MODE_SMFR, PixSmfrBlend, PixFovBlend>::type px;
             px.init(inside, est, L2, FA(tile_level_f, 1.0f));
-            lazy_tile<(MODE == MODE_FOV) ? 2 : 3, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, S1 + 1);
+            lazy_tile<(MODE == MODE_SMFR) ? 3 : 2, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, (MODE == MODE_FOV) ? S1 + 1 : S1);
             if (inside) {
                 const float A0 = FF(bg0, px.T1, px.A0), A1 = FF(bg1, px.T1, px.A1), A2 = FF(bg2, px.T1, px.A2);
                 const float B0 = FF(bg0, px.T2, px.B0), B1 = FF(bg1, px.T2, px.B1), B2 = FF(bg2, px.T2, px.B2);
@@ -812,6 +840,8 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_SMFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_lazy_blend<MODE_MMFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
@@ -822,6 +852,7 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
     }
     if (mode == MODE_FOV) k_lazy_blend<MODE_FOV><<<T, 256, smem, st>>>(ws, in);
     else if (mode == MODE_SMFR) k_lazy_blend<MODE_SMFR><<<T, 256, smem, st>>>(ws, in);
+    else if (mode == MODE_MMFR) k_lazy_blend<MODE_MMFR><<<T, 256, smem, st>>>(ws, in);
     else if (mode == MODE_SUM && in.stat == STAT_MAX) k_lazy_blend<MODE_SUM, STAT_MAX><<<T, 256, smem_sum, st>>>(ws, in);
     else if (mode == MODE_SUM && in.stat == STAT_LWMC) k_lazy_blend<MODE_SUM, STAT_LWMC><<<T, 256, smem_sum, st>>>(ws, in);
     else if (mode == MODE_SUM) k_lazy_blend<MODE_SUM, STAT_SUM><<<T, 256, smem_sum, st>>>(ws, in);

@@ -95,6 +95,30 @@ class SmfrFwdArgs(C.Structure):
     ]
 
 
+class MmfrFwdArgs(C.Structure):
+    _fields_ = [
+        ("cam", Camera),
+        ("P", C.c_int32),
+        ("M", C.c_int32),
+        ("means3D", _f),
+        ("opacities", _f),
+        ("scales", _f),
+        ("rotations", _f),
+        ("shs", _f),
+        ("cur_level", C.c_float),
+        ("gaze", _f),
+        ("alpha", C.c_float),
+        ("blending", C.c_int32),
+        ("out_color", _f),
+        ("radii", _f),
+        ("workspace", _f),
+        ("workspace_bytes", C.c_size_t),
+        ("max_instances", C.c_int64),
+        ("out_point_list", _f),
+        ("out_ranges", _f),
+    ]
+
+
 class Ps1FwdArgs(C.Structure):
     _fields_ = [
         ("cam", Camera),
@@ -154,6 +178,7 @@ EXPORTS = (
     "fovgs_workspace_bytes",
     "fovgs_forward_fov",
     "fovgs_forward_smfr",
+    "fovgs_forward_mmfr",
     "fovgs_forward_ps1",
     "fovgs_backward_ps1",
     "fovgs_mark_visible",
@@ -190,6 +215,7 @@ def lib():
     L.fovgs_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     L.fovgs_forward_fov.argtypes = [C.POINTER(FovFwdArgs), C.c_void_p]
     L.fovgs_forward_smfr.argtypes = [C.POINTER(SmfrFwdArgs), C.c_void_p]
+    L.fovgs_forward_mmfr.argtypes = [C.POINTER(MmfrFwdArgs), C.c_void_p]
     L.fovgs_forward_ps1.argtypes = [C.POINTER(Ps1FwdArgs), C.c_void_p]
     L.fovgs_backward_ps1.argtypes = [C.POINTER(Ps1BwdArgs), C.c_void_p]
     L.fovgs_mark_visible.argtypes = [C.c_int32, _f, _f, _f, _f, C.c_void_p]
@@ -206,7 +232,7 @@ def lib():
     L.fovgs_profile_count.restype = C.c_int
     L.fovgs_profile_read_frame.argtypes = [C.c_int32, C.POINTER(C.c_float), C.c_int32]
     L.fovgs_profile_read_frame.restype = C.c_int
-    for fn in ("fovgs_forward_fov", "fovgs_forward_smfr", "fovgs_forward_ps1", "fovgs_backward_ps1", "fovgs_mark_visible",
+    for fn in ("fovgs_forward_fov", "fovgs_forward_smfr", "fovgs_forward_mmfr", "fovgs_forward_ps1", "fovgs_backward_ps1", "fovgs_mark_visible",
                "fovgs_read_stats_async", "fovgs_fov_tile_tables", "fovgs_ps1_geometry", "fovgs_fov_geometry"):
         getattr(L, fn).restype = C.c_int
     _lib = L

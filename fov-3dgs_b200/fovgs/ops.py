@@ -18,12 +18,13 @@ import os
 import torch
 
 from . import _lib
-from ._lib import Camera, FovFwdArgs, FrameStats, Ps1BwdArgs, Ps1FwdArgs, SmfrFwdArgs, check, lib
+from ._lib import Camera, FovFwdArgs, FrameStats, MmfrFwdArgs, Ps1BwdArgs, Ps1FwdArgs, SmfrFwdArgs, check, lib
 
 MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
 # pruning-metric variants of the training rasterizer: SUM's workspace layout and backward, other statistics
 MODE_MAX, MODE_LWMC = 3, 4
 MODE_SMFR = 5   # shared-model foveation baseline (naive_pcheck_obb)
+MODE_MMFR = 6   # multi-model foveation baseline (mmfr_pcheck_obb), one call per level
 _TRAIN_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC)
 _PS1_ABI_MODE = {MODE_OBB: _lib.FOVGS_PS1_OBB, MODE_SUM: _lib.FOVGS_PS1_SUM, MODE_MAX: _lib.FOVGS_PS1_MAX,
                  MODE_LWMC: _lib.FOVGS_PS1_LWMC}
@@ -128,7 +129,7 @@ def _initial_capacity(P):
 
 
 def _new_workspace(device, mode, P, W, H, cap):
-    nbytes = lib().fovgs_workspace_bytes(P, W, H, cap, 1 if mode == MODE_FOV else (2 if mode == MODE_SMFR else 0),
+    nbytes = lib().fovgs_workspace_bytes(P, W, H, cap, {MODE_FOV: 1, MODE_SMFR: 2, MODE_MMFR: 3}.get(mode, 0),
                                          1 if mode in _TRAIN_MODES else 0)
     if nbytes == 0:
         raise RuntimeError("fovgs_workspace_bytes rejected the frame configuration")
@@ -331,6 +332,75 @@ def forward_smfr(means3D, opacities, scales, rotations, shs, highest_levels, gaz
         check(lib().fovgs_forward_smfr(C.byref(a), stream), "fovgs_forward_smfr")
 
     item, st = _run_with_capacity(launch, device, MODE_SMFR, P, W, H, fresh_workspace=False)
+    n = st["num_rendered"] if st is not None else -1
+    if want_lists:
+        return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item
+    return n, color, radii
+
+
+def forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArray, alpha, blending, raster_settings,
+                 want_lists=False):
+    """MMFR baseline forward for ONE level model (replaces RasterizeGaussiansCUDA of mmfr_pcheck_obb/rasterize_points.cu).
+    Returns (num_rendered, color[3,H,W], radii[P]) (+ point_list, ranges, workspace item when want_lists)."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    device = means3D.device
+    rs = raster_settings
+    H, W = int(rs.image_height), int(rs.image_width)
+    P = means3D.size(0)
+    if P == 0:
+        z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
+        return 0, z, torch.zeros((0,), dtype=torch.int32, device=device)
+    if cur_level is None:
+        raise RuntimeError("cur_level must be given (0..3)")
+    keep = []
+    means3D = _prep(means3D, "means3D", device)
+    opacities = _prep(opacities, "opacities", device)
+    if opacities.numel() != P:
+        raise RuntimeError("opacities must have dimensions (num_points, 1)")
+    scales = _prep(scales, "scales", device)
+    rotations = _prep(rotations, "rotations", device)
+    shs = _prep(shs, "shs", device)
+    gaze = gazeArray
+    if not isinstance(gaze, torch.Tensor):
+        gaze = torch.tensor([float(gaze[0]), float(gaze[1])], dtype=torch.float32)
+    if not gaze.is_cuda:
+        gaze = gaze.to(device, non_blocking=True)
+    gaze = _prep(gaze, "gazeArray", device)
+    M = int(shs.size(1))
+    cam = _camera(rs, device, keep)
+    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    lists = {}
+
+    def launch(item, stream):
+        a = MmfrFwdArgs()
+        a.cam = cam
+        a.P = P
+        a.M = M
+        a.means3D = means3D.data_ptr()
+        a.opacities = opacities.data_ptr()
+        a.scales = scales.data_ptr()
+        a.rotations = rotations.data_ptr()
+        a.shs = shs.data_ptr()
+        a.cur_level = float(cur_level)
+        a.gaze = gaze.data_ptr()
+        a.alpha = float(alpha) if alpha is not None else 0.0
+        a.blending = int(bool(blending))
+        a.out_color = color.data_ptr()
+        a.radii = radii.data_ptr()
+        a.workspace = item["ws"].data_ptr()
+        a.workspace_bytes = item["bytes"]
+        a.max_instances = item["cap"]
+        if want_lists:
+            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
+            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
+            a.out_point_list = lists["point_list"].data_ptr()
+            a.out_ranges = lists["ranges"].data_ptr()
+        check(lib().fovgs_forward_mmfr(C.byref(a), stream), "fovgs_forward_mmfr")
+
+    item, st = _run_with_capacity(launch, device, MODE_MMFR, P, W, H, fresh_workspace=False)
     n = st["num_rendered"] if st is not None else -1
     if want_lists:
         return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item

@@ -206,6 +206,81 @@ def make_smfr_api():
 
 
 # ------------------------------------------------------------------------------------------------------------
+# MMFR baseline: one call per level model (diff_gaussian_rasterization_mmfr_pcheck_obb)
+# ------------------------------------------------------------------------------------------------------------
+class _RasterizeGaussiansMmfr(torch.autograd.Function):
+    """mmfr_pcheck_obb/diff_gaussian_rasterization_mmfr_pcheck_obb/__init__.py:56-131 (forward-only)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                cur_level, gazeArray, alpha, blending):
+        if colors_precomp is not None and colors_precomp.numel() != 0:
+            raise RuntimeError("the multi-model foveated rasterizer renders from SH coefficients; colors_precomp is not supported")
+        if cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0:
+            raise RuntimeError("the multi-model foveated rasterizer takes scales/rotations, not cov3D_precomp")
+        args = (cur_level, gazeArray, alpha, blending, raster_settings.bg, means3D, colors_precomp, opacities, scales,
+                rotations, raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
+                raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy, raster_settings.image_height,
+                raster_settings.image_width, shs, raster_settings.sh_degree, raster_settings.campos,
+                raster_settings.prefiltered, raster_settings.debug)
+
+        def run():
+            return ops.forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArray, alpha, blending,
+                                    raster_settings)
+
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                num_rendered, color, radii = run()
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            num_rendered, color, radii = run()
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        return (None,) * 13
+
+
+def _mmfr_rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                              raster_settings, cur_level, gazeArray, alpha: float, blending: bool):
+    return _RasterizeGaussiansMmfr.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                         raster_settings, cur_level, gazeArray, alpha, blending)
+
+
+class _MmfrGaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        return _mark_visible(self.raster_settings, positions)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, shs_dcs=None, cur_level=None, gazeArray=None, alpha=None, blending=None):
+        _check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        return _mmfr_rasterize_gaussians(means3D, means2D, _empty_if_none(shs), _empty_if_none(colors_precomp), opacities,
+                                         _empty_if_none(scales), _empty_if_none(rotations), _empty_if_none(cov3D_precomp),
+                                         self.raster_settings, cur_level, gazeArray, alpha, blending)
+
+
+def make_mmfr_api():
+    return {
+        "GaussianRasterizationSettings": GaussianRasterizationSettings,
+        "GaussianRasterizer": _MmfrGaussianRasterizer,
+        "rasterize_gaussians": _mmfr_rasterize_gaussians,
+        "_RasterizeGaussians": _RasterizeGaussiansMmfr,
+        "cpu_deep_copy_tuple": cpu_deep_copy_tuple,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
 # PS=1: inference (pcheck_obb) and training (pcheck_obb_sum)
 # ------------------------------------------------------------------------------------------------------------
 def _make_ps1_function(mode: int):

@@ -215,14 +215,15 @@ static int obb_check(const splat_t* s, const corners_t* o, float tcx, float tcy)
 /* ---- tile levels (FOV/rasterizer_impl.cu:86-177, auxiliary.h:26-66) ---------------------------------------- */
 static const float real_image_width = 2.0f, real_viewing_distance = 1.0f, sqrt_max_ps = 3.4641016151377544f;
 static const float start_blend = 0.5f;
+static const float blend_width = 0.5f;   /* auxiliary.h:32 */
 
 static void ncd2dir(float nx, float ny, float rw, float rh, float* d) {
     float x = (nx - 0.5f) * rw, y = (ny - 0.5f) * rh, z = real_viewing_distance;
     float n = sqrtf(fmaf(y, y, x * x) + z * z);
     d[0] = x / n; d[1] = y / n; d[2] = z / n;
 }
-void orc_tile_tables(int W, int H, const float* gaze, float alpha, float* tile_level, float* tile_min, float* gxs,
-                     float* gys, uint8_t* blending) {
+static void tile_tables_impl(int W, int H, const float* gaze, float alpha, float* tile_level, float* tile_min, float* gxs,
+                     float* gys, uint8_t* blending, int clamp0) {
     const int tw = (W + 15) / 16, th = (H + 15) / 16, T = tw * th;
     const float step = (float)((sqrt_max_ps - 1.) / (float)(FOV_NUM - 1));
     for (int idx = 0; idx < T; idx++) {
@@ -262,12 +263,18 @@ void orc_tile_tables(int W, int H, const float* gaze, float alpha, float* tile_l
         if (r != -1 && l != -1) gx = (r - l) / 2.0f; else if (r != -1) gx = r - lv; else if (l != -1) gx = lv - l;
         if (u != -1 && d != -1) gy = (u - d) / 2.0f; else if (u != -1) gy = u - lv; else if (d != -1) gy = lv - d;
         const float md = (float)(0.5 * (fabsf(gx) + fabsf(gy)));
-        const float tm = lv - md;
+        float tm = lv - md;
+        if (clamp0 && tm < 0) tm = 0;   /* MMFR only: mmfr_pcheck_obb/cuda_rasterizer/rasterizer_impl.cu:249-251 */
         tile_min[idx] = tm;
         const float tmi = (float)f2i_rz(tm);
         blending[idx] = ((tm - tmi) > start_blend && (tmi < (FOV_NUM - 1))) ? 1 : 0;
         gys[idx] = gy; gxs[idx] = gx;
     }
+}
+
+void orc_tile_tables(int W, int H, const float* gaze, float alpha, float* tile_level, float* tile_min, float* gxs,
+                     float* gys, uint8_t* blending) {
+    tile_tables_impl(W, H, gaze, alpha, tile_level, tile_min, gxs, gys, blending, 0);
 }
 
 /* ---- SH colour ----------------------------------------------------------------------------------------------- */
@@ -309,7 +316,8 @@ static int inst_cmp(const void* a, const void* b) {
 }
 
 typedef struct {
-    int mode;  /* 0 obb, 1 sum, 2 fov */
+    int mode;  /* 0 obb, 1 sum, 2 fov, 3 mmfr (tile_skip instead of the level test) */
+    const uint8_t* tile_skip;
     const orc_camera* cam;
     int P, M;
     const float *means3D, *opacity, *scales, *rot, *shs;
@@ -358,6 +366,7 @@ static int64_t run_binning(const bin_in_t* in, bin_out_t* o, float fx, float fy,
                 pass = level < (hl + 1);
                 if (pass) { lo = level; hi = level; be_blend = in->tile_blend[tile] || be_blend; }
             }
+            if (in->mode == 3) pass = !in->tile_skip[tile];
             if (pass) { count = 1; inst[n].key = ((uint64_t)tile << 32) | dbits; inst[n].id = i; inst[n].seq = n; n++; }
         } else {
             corners_t oc; obb_corners(s, &oc);
@@ -366,6 +375,7 @@ static int64_t run_binning(const bin_in_t* in, bin_out_t* o, float fx, float fy,
                     const uint32_t tile = (uint32_t)y * gx + x;
                     float level = 0;
                     if (in->mode == 2) { level = in->tile_min[tile]; if (!(level < (hl + 1))) continue; }
+                    if (in->mode == 3 && in->tile_skip[tile]) continue;
                     const float tcx = (float)x * (float)BLOCK_X + (float)BLOCK_X / 2.0f;
                     const float tcy = (float)y * (float)BLOCK_Y + (float)BLOCK_Y / 2.0f;
                     if (!obb_check(s, &oc, tcx, tcy)) continue;
@@ -809,6 +819,124 @@ int64_t orc_forward_smfr(const orc_camera* cam, int P, int M, const float* means
                          int64_t list_cap, uint32_t* ranges) {
     return forward_fov_impl(1, cam, P, M, means3D, opacity, scales, rot, shs, NULL, highest_levels, gaze, alpha_pool, out_color,
                             radii, NULL, NULL, NULL, point_list, list_cap, ranges, NULL, NULL, NULL, NULL);
+}
+
+/* =================================================================================================================
+ * MMFR baseline (diff_gaussian_rasterization_mmfr_pcheck_obb): one call per level model.  `cur_level` selects the tiles
+ * (compute_tile_skips_cuda, rasterizer_impl.cu:277-304); plain tiles composite normally, blending tiles composite the one
+ * model and weight it (forward.cu:255-418), skipped tiles stay 0; the caller sums the four level images.
+ * The reference refreshes its (process-static) tile tables only when cur_level == 0; this restatement computes them
+ * on every call, which is the same thing for the four calls of one frame (same gaze, alpha, size).
+ * ================================================================================================================= */
+typedef struct {
+    const orc_camera* cam; int W, H, gx; const uint32_t* rng; const inst_t* inst; const splat_t* sp;
+    const float* tm; const float* tgx; const float* tgy; const uint8_t* tb; const uint8_t* tskip; const float* opacity;
+    const float* rgb; float cur_level; float* out_color;
+} mmfr_blend_ctx;
+static void blend_tile_mmfr(void* vctx, int tile) {
+    const mmfr_blend_ctx* c = (const mmfr_blend_ctx*)vctx;
+    const int W = c->W, H = c->H, gx = c->gx;
+    const int tx = tile % gx, ty = tile / gx;
+    if (c->tskip[tile]) return;                       /* out_color keeps its initial 0 */
+    const int blending = c->tb[tile];
+    const uint32_t r0 = c->rng[2 * tile], r1 = c->rng[2 * tile + 1];
+    const int total = (int)(r1 - r0), rounds = (total + 255) / 256;
+    const float tlf = c->tm[tile];
+    float T1[256], C1[256][3], xs[256]; int L1s[256]; uint8_t done[256];
+    int ndone = 0;
+    for (int t = 0; t < 256; t++) {
+        const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
+        T1[t] = 1.0f; C1[t][0] = C1[t][1] = C1[t][2] = 0;
+        done[t] = !(px < W && py < H);
+        if (blending) {
+            const float est = fmaf(fmaf((float)(t & 15), c->tgx[tile], (float)(t >> 4) * c->tgy[tile]), 0.0625f, tlf);
+            L1s[t] = f2i_rz(est);
+            xs[t] = (est - ((float)L1s[t] + start_blend)) / blend_width;
+            if (xs[t] < 0 && (float)L1s[t] != c->cur_level) done[t] = 1;
+        }
+        ndone += done[t];
+    }
+    int toDo = total;
+    for (int b = 0; b < rounds; b++, toDo -= 256) {
+        if (ndone == 256) break;
+        const int lim = toDo < 256 ? toDo : 256;
+        for (int t = 0; t < 256; t++) {
+            if (done[t]) continue;
+            const float pxf = (float)(tx * 16 + (t & 15)), pyf = (float)(ty * 16 + (t >> 4));
+            for (int j = 0; j < lim && !done[t]; j++) {
+                const uint32_t id = c->inst[r0 + (size_t)b * 256 + j].id;
+                const splat_t* s = &c->sp[id];
+                const float dx = s->px - pxf, dy = s->py - pyf;
+                const float power = gauss_power(s->conx, s->cony, s->conz, dx, dy);
+                if (power > 0.0f || power < -4.5f) continue;
+                const float a = fminf(0.99f, c->opacity[id] * expf(power));
+                if (a < 1.0f / 255.0f) continue;
+                const float tt = T1[t] * (1 - a);
+                if (tt < 0.0001f) { done[t] = 1; ndone++; continue; }
+                const float w = a * T1[t];
+                for (int ch = 0; ch < 3; ch++) C1[t][ch] = fmaf(c->rgb[3 * id + ch], w, C1[t][ch]);
+                T1[t] = tt;
+            }
+        }
+    }
+    for (int t = 0; t < 256; t++) {
+        const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
+        if (!(px < W && py < H)) continue;
+        const size_t pid = (size_t)W * py + px;
+        for (int ch = 0; ch < 3; ch++) {
+            const float v = fmaf(c->cam->bg[ch], T1[t], C1[t][ch]);
+            if (!blending) { c->out_color[(size_t)ch * H * W + pid] = v; continue; }
+            const float x = fmaxf(0.0f, fminf(1.0f, xs[t]));
+            const float nb = fmaf(x, x * (x + x), x * (x * -3.0f));     /* -(3x^2 - 2x^3), as the FOV kernel's binary */
+            const float w1 = nb + 1.0f;
+            const float used = ((float)L1s[t] == c->cur_level) ? w1 : 1.0f - w1;
+            c->out_color[(size_t)ch * H * W + pid] = v * used;
+        }
+    }
+}
+
+int64_t orc_forward_mmfr(const orc_camera* cam, int P, int M, const float* means3D, const float* opacity,
+                         const float* scales, const float* rot, const float* shs, float cur_level, const float* gaze,
+                         float alpha_pool, float* out_color, int* radii, uint32_t* point_list, int64_t list_cap,
+                         uint32_t* ranges, uint8_t* tile_skip_out) {
+    const int W = cam->W, H = cam->H, gx = (W + 15) / 16, gy = (H + 15) / 16, T = gx * gy;
+    const float fy = H / (2.0f * cam->tanfovy), fx = W / (2.0f * cam->tanfovx);
+    float* tl = (float*)malloc(sizeof(float) * T); float* tm = (float*)malloc(sizeof(float) * T);
+    float* tgx = (float*)malloc(sizeof(float) * T); float* tgy = (float*)malloc(sizeof(float) * T);
+    uint8_t* tb = (uint8_t*)malloc(T); uint8_t* tskip = (uint8_t*)malloc(T);
+    tile_tables_impl(W, H, gaze, alpha_pool, tl, tm, tgx, tgy, tb, 1);
+    {
+        const float lb = cur_level - blend_width, hb = cur_level + 1;
+        for (int i = 0; i < T; i++) tskip[i] = !(tm[i] > lb && tm[i] < hb);
+    }
+    if (tile_skip_out) memcpy(tile_skip_out, tskip, T);
+    bin_in_t in; memset(&in, 0, sizeof(in));
+    in.mode = 3; in.cam = cam; in.P = P; in.M = M; in.means3D = means3D; in.scales = scales; in.rot = rot; in.tile_skip = tskip;
+    bin_out_t o; memset(&o, 0, sizeof(o));
+    o.sp = (splat_t*)calloc((size_t)P + 1, sizeof(splat_t)); o.vis = (uint8_t*)calloc((size_t)P + 1, 1);
+    o.radii = radii; o.cov3d = (float*)calloc((size_t)P * 6 + 6, sizeof(float));
+    const int64_t n = run_binning(&in, &o, fx, fy, gx, gy);
+    uint32_t* rng = (uint32_t*)calloc((size_t)T * 2, sizeof(uint32_t));
+    fill_lists(&o, T, point_list, list_cap, rng);
+    if (ranges) memcpy(ranges, rng, sizeof(uint32_t) * 2 * (size_t)T);
+    float* rgb = (float*)calloc((size_t)P * 3 + 3, sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; i++) {
+        if (radii[i] <= 0) continue;
+        float d[3]; view_dir(cam, means3D + 3 * i, d);
+        const float* sh = shs + (size_t)3 * M * i;
+        float res[3] = {SH_C0 * sh[0], SH_C0 * sh[1], SH_C0 * sh[2]};
+        sh_accumulate(sh, 1, cam->sh_degree, d[0], d[1], d[2], res);
+        for (int ch = 0; ch < 3; ch++) rgb[3 * i + ch] = fmaxf(res[ch] + 0.5f, 0.0f);
+    }
+    memset(out_color, 0, sizeof(float) * 3 * (size_t)W * H);
+    {
+        mmfr_blend_ctx bc = {cam, W, H, gx, rng, o.inst, o.sp, tm, tgx, tgy, tb, tskip, opacity, rgb, cur_level, out_color};
+        run_tiles(blend_tile_mmfr, &bc, T);
+    }
+    free(tl); free(tm); free(tgx); free(tgy); free(tb); free(tskip); free(o.sp); free(o.vis); free(o.cov3d); free(o.inst);
+    free(rng); free(rgb);
+    return n;
 }
 
 /* =================================================================================================================

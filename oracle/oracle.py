@@ -37,6 +37,7 @@ def lib():
         _lib.orc_forward_ps1.restype = C.c_int64
         _lib.orc_forward_fov.restype = C.c_int64
         _lib.orc_forward_smfr.restype = C.c_int64
+        _lib.orc_forward_mmfr.restype = C.c_int64
         _lib.orc_backward_ps1.restype = C.c_int
     return _lib
 
@@ -141,6 +142,26 @@ def forward_smfr(scene, cam, gaze, alpha=0.05, bg=(0.0, 0.0, 0.0), list_cap=None
            _f32(scene["highest_levels"])]
     n = L.orc_forward_smfr(C.byref(c), P, M, *[_p(a) for a in ins], _p(g), C.c_float(alpha), _p(o["color"]), _p(o["radii"]),
                            _p(o["point_list"]), C.c_int64(cap), _p(o["ranges"]))
+    o["num_rendered"] = int(n)
+    o["point_list"] = o["point_list"][: min(n, cap)]
+    return o
+
+
+def forward_mmfr(scene, cam, cur_level, gaze, alpha=0.05, bg=(0.0, 0.0, 0.0), list_cap=None):
+    """MMFR baseline (mmfr_pcheck_obb), ONE level call: scene carries that level's model (shs [P,M,3], opacity [P,1])."""
+    L = lib()
+    P = scene["means3D"].shape[0]
+    M = scene["shs"].shape[1]
+    W, H = cam["image_width"], cam["image_height"]
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    c = _cam(cam, scene["sh_degree"], bg)
+    cap = int(list_cap or max(1 << 20, 64 * P))
+    o = {"color": np.zeros((3, H, W), np.float32), "radii": np.zeros(P, np.int32), "tile_skip": np.zeros(T, np.uint8),
+         "point_list": np.zeros(cap, np.uint32), "ranges": np.zeros((T, 2), np.uint32)}
+    g = _f32(np.asarray(gaze, np.float32))
+    ins = [_f32(scene["means3D"]), _f32(scene["opacity"]), _f32(scene["scales"]), _f32(scene["rotations"]), _f32(scene["shs"])]
+    n = L.orc_forward_mmfr(C.byref(c), P, M, *[_p(a) for a in ins], C.c_float(float(cur_level)), _p(g), C.c_float(alpha),
+                           _p(o["color"]), _p(o["radii"]), _p(o["point_list"]), C.c_int64(cap), _p(o["ranges"]), _p(o["tile_skip"]))
     o["num_rendered"] = int(n)
     o["point_list"] = o["point_list"][: min(n, cap)]
     return o

@@ -55,6 +55,16 @@ def smfr_forward(mod, sc, cam, gaze, alpha=0.05, blending=True, bg=None, debug=F
         cam["image_height"], cam["image_width"], sc["shs"], sc["sh_degree"], cam["campos"], False, debug)
 
 
+def mmfr_forward(mod, sc, cam, cur_level, gaze, alpha=0.05, blending=True, bg=None, debug=False):
+    """ref_mmfr_C (MMFR baseline, one level call): 23 args, mmfr_pcheck_obb/rasterize_points.h:17-43.  NOTE: the reference
+    keeps its tile tables in process-static memory and refreshes them only when cur_level == 0 — call level 0 first."""
+    bg = bg if bg is not None else torch.zeros(3, device="cuda")
+    return mod.rasterize_gaussians(
+        float(cur_level), gaze, float(alpha), bool(blending), bg, sc["means3D"], _empty(), sc["opacity"], sc["scales"],
+        sc["rotations"], 1.0, _empty(), cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"],
+        cam["image_height"], cam["image_width"], sc["shs"], sc["sh_degree"], cam["campos"], False, debug)
+
+
 def ps1_forward(mod, sc, cam, bg=None, debug=False, loss_map=None):
     """`loss_map` (CUDA [H,W]) only for ref_lwmc_C, whose pybind signature takes it between `prefiltered` and `debug`
     (.../pcheck_obb_loss_weighted_max_count/rasterize_points.cu:35-57)."""

@@ -139,6 +139,25 @@ def test_smfr_matches_reference_golden(scene_small, golden_dir, gi):
     assert np.array_equal(color.cpu().numpy(), g["color"])
 
 
+@pytest.mark.parametrize("level", [0, 1])
+def test_mmfr_matches_reference_golden(scene_small, golden_dir, level):
+    g = _g(golden_dir, f"mmfr_small_c0_g0_l{level}.npz")
+    s, c = scene_small
+    sub = {k: (v[:: 1 << level] if isinstance(v, np.ndarray) and v.ndim > 0 and v.shape[0] == s["means3D"].shape[0] else v)
+           for k, v in s.items()}
+    sc = _cuda({k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in sub.items()})
+    import diff_gaussian_rasterization_mmfr_pcheck_obb as m
+    rs = _settings(m, c, s["sh_degree"])
+    gz = torch.from_numpy(np.asarray(g["gaze"], np.float32)).cuda()
+    n, color, radii, pl, rg, item = ops.forward_mmfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                     level, gz, 0.05, True, rs, want_lists=True)
+    assert n == int(g["num_rendered"])
+    assert np.array_equal(radii.cpu().numpy(), g["radii"])
+    assert np.array_equal(pl.cpu().numpy(), g["point_list"])
+    assert np.array_equal(rg.cpu().numpy(), g["ranges"])
+    assert np.array_equal(color.cpu().numpy(), g["color"])
+
+
 @pytest.mark.parametrize("gi", [0, 1])
 def test_fov_matches_reference_golden(scene_small, golden_dir, gi):
     g = _g(golden_dir, f"fov_small_c0_g{gi}.npz")
@@ -216,6 +235,37 @@ def test_smfr_baseline_vs_oracle_full_and_lazy(gaze):
     col_l, radii_l = r(means3D=sc["means3D"], means2D=None, opacities=sc["opacity"], shs=sc["shs"], scales=sc["scales"],
                        rotations=sc["rotations"], highest_levels=sc["highest_levels"], gazeArray=g, alpha=0.05, blending=True)
     assert torch.equal(col_l, color) and torch.equal(radii_l, radii)
+
+
+def test_mmfr_baseline_vs_oracle_and_levels_sum_to_full_image():
+    """MMFR baseline (mmfr_pcheck_obb): per level call lists exact, image within tolerance, lazy ==
+    full-sort bits; with the SAME model at all four levels the level images add up to the PS=1 image (the blending
+    weights of a level pair sum to one, skipped tiles contribute zero)."""
+    import oracle
+    import diff_gaussian_rasterization_mmfr_pcheck_obb as m
+    s = synth.make_scene_cube(5000, 29)
+    c = _small_cam(400, 240)
+    gaze = (0.35, 0.6)
+    sc = _cuda(s)
+    rs = _settings(m, c, s["sh_degree"])
+    g = torch.tensor(np.asarray(gaze, np.float32)).cuda()
+    total = torch.zeros((3, 240, 400), device="cuda")
+    r = m.GaussianRasterizer(raster_settings=rs)
+    for level in range(4):
+        o = oracle.forward_mmfr(s, c, level, gaze)
+        n, color, radii, pl, rg, item = ops.forward_mmfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                         level, g, 0.05, True, rs, want_lists=True)
+        assert n == o["num_rendered"], level
+        assert np.array_equal(radii.cpu().numpy(), o["radii"])
+        assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
+        assert np.array_equal(rg.cpu().numpy().astype(np.uint32), o["ranges"])
+        assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
+        col_l, radii_l = r(means3D=sc["means3D"], means2D=None, opacities=sc["opacity"], shs=sc["shs"], scales=sc["scales"],
+                           rotations=sc["rotations"], cur_level=level, gazeArray=g, alpha=0.05, blending=True)
+        assert torch.equal(col_l, color) and torch.equal(radii_l, radii)
+        total += color
+    (n1, full, _, _, _, _), _, _ = _run_ps1(ops.MODE_OBB, s, c)
+    assert float((total - full).abs().max()) <= 1e-5
 
 
 def test_sum_backward_vs_oracle():

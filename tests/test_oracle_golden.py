@@ -142,6 +142,21 @@ def test_smfr_baseline_matches_reference(scene_small, golden_dir, gi):
     assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
 
 
+@pytest.mark.parametrize("level", [0, 1])
+def test_mmfr_baseline_matches_reference(scene_small, golden_dir, level):
+    """mmfr_pcheck_obb (MMFR), one level call; the level-l model of the fixture is every 2^l-th Gaussian of the scene."""
+    g = _g(golden_dir, f"mmfr_small_c0_g0_l{level}.npz")
+    s, c = scene_small
+    sub = {k: (v[:: 1 << level] if isinstance(v, np.ndarray) and v.ndim > 0 and v.shape[0] == s["means3D"].shape[0] else v)
+           for k, v in s.items()}
+    o = oracle.forward_mmfr(sub, c, level, g["gaze"])
+    assert o["num_rendered"] == int(g["num_rendered"])
+    assert np.array_equal(o["radii"], g["radii"])
+    assert np.array_equal(o["point_list"], g["point_list"].astype(np.uint32))
+    assert np.array_equal(o["ranges"], g["ranges"].astype(np.uint32))
+    assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
+
+
 def test_tile_tables_shape_and_monotone_eccentricity():
     t = oracle.tile_tables(1920, 1080, (0.5, 0.5))
     lvl = t["tile_level"].reshape(68, 120)

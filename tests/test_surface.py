@@ -7,6 +7,7 @@ import pytest
 import torch
 
 PKGS = ["diff_gaussian_rasterization_fov_pcheck_obb", "diff_gaussian_rasterization_naive_pcheck_obb",
+        "diff_gaussian_rasterization_mmfr_pcheck_obb",
         "diff_gaussian_rasterization_pcheck_obb",
         "diff_gaussian_rasterization_pcheck_obb_sum", "diff_gaussian_rasterization_pcheck_obb_max",
         "diff_gaussian_rasterization_pcheck_obb_loss_weighted_max_count", "diff_gaussian_rasterization"]
@@ -41,6 +42,17 @@ def test_smfr_signatures_match_reference():
     assert list(inspect.signature(m.GaussianRasterizer.forward).parameters) == [
         "self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp",
         "shs_dcs", "highest_levels", "gazeArray", "alpha", "blending"]
+
+
+def test_mmfr_signatures_match_reference():
+    """mmfr_pcheck_obb/diff_gaussian_rasterization_mmfr_pcheck_obb/__init__.py:20-36,215-217."""
+    m = importlib.import_module("diff_gaussian_rasterization_mmfr_pcheck_obb")
+    assert list(inspect.signature(m.rasterize_gaussians).parameters) == [
+        "means3D", "means2D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp",
+        "raster_settings", "cur_level", "gazeArray", "alpha", "blending"]
+    assert list(inspect.signature(m.GaussianRasterizer.forward).parameters) == [
+        "self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp",
+        "shs_dcs", "cur_level", "gazeArray", "alpha", "blending"]
 
 
 @pytest.mark.parametrize("name", ["diff_gaussian_rasterization_pcheck_obb", "diff_gaussian_rasterization_pcheck_obb_sum",
@@ -98,5 +110,5 @@ def test_non_hot_path_variants_explain_themselves():
 
 def test_gaussian_wrapper_import_line_works():
     """fov3dgs/gaussian_wrapper.py:2-7 imports six names at module import; all must resolve."""
-    for n in PKGS[2:]:
+    for n in PKGS[3:]:
         importlib.import_module(n).GaussianRasterizer

@@ -185,6 +185,58 @@ def run_smfr(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
         print(json.dumps({k: v for k, v in rep.items() if k != "trace"}), flush=True)
 
 
+def run_mmfr(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
+    """MMFR baseline (mmfr_pcheck_obb) vs ref_mmfr_C: four level calls per gaze (level 0 first: the reference refreshes
+    its static tile tables only then); the level models are nested subsets of the scene (every 1, 2, 4, 8-th Gaussian)."""
+    mod = ref_api.ref_module("ref_mmfr_C")
+    full = to_cuda(scn)
+    c = to_cuda(cam)
+    W, H = cam["image_width"], cam["image_height"]
+    bg = torch.zeros(3, device="cuda")
+    rs = settings(c, full["sh_degree"], bg)
+    levels = []
+    for l in range(4):
+        sub = {k: (v[:: 1 << l].contiguous() if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == full["means3D"].shape[0] else v)
+               for k, v in full.items()}
+        levels.append(sub)
+    for gi, g in enumerate(gazes):
+        gaze = torch.tensor(g, dtype=torch.float32, device="cuda")
+        for l, sc in enumerate(levels):
+            P = sc["means3D"].shape[0]
+            rep = {"variant": "mmfr", "tag": tag, "P": P, "W": W, "H": H, "gaze": list(g), "cur_level": l}
+            try:
+                if mod is None:
+                    raise RuntimeError("reference module ref_mmfr_C is not built")
+                n_r, col_r, rad_r, geom, binning, img = ref_api.mmfr_forward(mod, sc, c, l, gaze)
+                torch.cuda.synchronize()
+                br = ref_api.decode_binning(binning, n_r)
+                ir = ref_api.decode_img(img, W, H)
+                n_o, col_o, rad_o, pl_o, rg_o, item = ops.forward_mmfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                                       l, gaze, 0.05, True, rs, want_lists=True)
+                torch.cuda.synchronize()
+                rep["num_rendered_ref"] = int(n_r); rep["num_rendered_ours"] = int(n_o)
+                rep["radii_mismatch"] = int((rad_r != rad_o).sum().item())
+                rep["point_list_mismatch"] = int((br["point_list"][:n_r] != pl_o[:n_r]).sum().item()) if n_r == n_o else -1
+                T = ((W + 15) // 16) * ((H + 15) // 16)
+                rep["ranges_mismatch"] = int((ir["ranges"][:T] != rg_o[:T]).sum().item())
+                d = (col_r - col_o).abs()
+                rep["img_max_abs"] = float(d.max().item()); rep["img_n_gt_1e-6"] = int((d > 1e-6).sum().item())
+                _, col_l, _ = ops.forward_mmfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"], l, gaze, 0.05, True, rs)
+                rep["lazy_img_max_abs"] = float((col_l - col_r).abs().max().item())
+                if golden_dir and gi < 1:
+                    np.savez_compressed(os.path.join(golden_dir, f"mmfr_{tag}_g{gi}_l{l}.npz"), gaze=np.array(g, np.float32), cur_level=np.int64(l),
+                                        color=col_r.cpu().numpy(), radii=rad_r.cpu().numpy(), num_rendered=np.int64(n_r),
+                                        point_list=br["point_list"].cpu().numpy(), ranges=ir["ranges"][:T].cpu().numpy())
+                if do_time and gi == 0:
+                    rep["time_ref"] = time_fn(lambda: ref_api.mmfr_forward(mod, sc, c, l, gaze))
+                    rep["time_ours"] = time_fn(lambda: ops.forward_mmfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"],
+                                                                        l, gaze, 0.05, True, rs))
+            except Exception as ex:
+                rep["error"] = repr(ex); rep["trace"] = traceback.format_exc()[-1500:]
+            rep_list.append(rep)
+            print(json.dumps({k: v for k, v in rep.items() if k != "trace"}), flush=True)
+
+
 PS1_VARIANTS = {"obb": ("ref_obb_C", ops.MODE_OBB), "sum": ("ref_sum_C", ops.MODE_SUM), "max": ("ref_max_C", ops.MODE_MAX),
                 "lwmc": ("ref_lwmc_C", ops.MODE_LWMC)}
 
@@ -317,6 +369,8 @@ def main():
                     run_fov(scn, cam, synth.GAZES_9[: a.gazes], reports, a.time, gd, tag)
                 elif v == "smfr":
                     run_smfr(scn, cam, synth.GAZES_9[: a.gazes], reports, a.time, gd, tag)
+                elif v == "mmfr":
+                    run_mmfr(scn, cam, synth.GAZES_9[: a.gazes], reports, a.time, gd, tag)
                 else:
                     run_ps1(v, scn, cam, reports, a.time, gd, tag)
         json.dump(reports, open(a.out, "w"), indent=1)
