@@ -268,6 +268,43 @@ def test_mmfr_baseline_vs_oracle_and_levels_sum_to_full_image():
     assert float((total - full).abs().max()) <= 1e-5
 
 
+def test_render_from_ply_and_camera_json(tmp_path):
+    """north_star: "identical point_cloud.ply + camera JSON inputs" — the whole input path (fovgs.io: PLY files of the four
+    levels, compose rule, cameras.json) feeding the foveated rasterizer, checked against the oracle on the same files."""
+    import json
+    import oracle
+    from fovgs import io
+    rng = np.random.default_rng(8)
+    s = synth.make_scene_cube(4000, 8)
+    P = s["means3D"].shape[0]
+    raw0 = {"xyz": s["means3D"], "features_dc": s["shs"][:, :1], "features_rest": s["shs"][:, 1:],
+            "opacity": np.log(s["opacity"] / (1 - s["opacity"])).astype(np.float32), "scaling": np.log(s["scales"]).astype(np.float32),
+            "rotation": s["rotations"], "sh_degree": 3}
+    paths = [str(tmp_path / "l0" / "point_cloud.ply")]
+    io.write_ply(paths[0], raw0)
+    keep = np.arange(P)
+    for i in range(1, 4):
+        keep = np.sort(rng.choice(keep, size=len(keep) // 2, replace=False))
+        raw = {k: (v[keep] if isinstance(v, np.ndarray) else v) for k, v in raw0.items()}
+        raw["features_dc"] = raw["features_dc"] + rng.normal(0, 0.2, raw["features_dc"].shape).astype(np.float32)
+        raw["indexes"] = keep.astype(np.int32).reshape(-1, 1)
+        paths.append(str(tmp_path / f"l{i}" / "point_cloud.ply"))
+        io.write_ply(paths[-1], raw, with_index=True)
+    c0 = _small_cam(320, 208)
+    wv = c0["viewmatrix"].astype(np.float64)
+    entry = io.camera_to_json_entry(0, wv[:3, :3], wv[3, :3], c0["FoVx"], c0["FoVy"], 320, 208, "view0")
+    cj = str(tmp_path / "cameras.json")
+    json.dump([entry], open(cj, "w"))
+    scene = io.compose_levels([io.raw_model_from_ply(p) for p in paths])
+    cam = io.cameras_from_json(cj)[0]
+    assert scene["highest_levels"].max() == 3 and cam["image_width"] == 320
+    o = oracle.forward_fov(scene, cam, (0.4, 0.5))
+    (n, color, radii, pl, rg, item), _, _ = _run_fov(scene, cam, (0.4, 0.5))
+    assert n == o["num_rendered"] and np.array_equal(radii.cpu().numpy(), o["radii"])
+    assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
+    assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
+
+
 def test_sum_backward_vs_oracle():
     import oracle
     s = synth.make_scene_cube(3000, 33)
