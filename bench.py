@@ -116,6 +116,33 @@ def clocks_summary(lines):
     return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class CameraUpload:
+    """Per-frame host inputs of the e2e loops: viewmatrix (16) + projmatrix (16) + campos (3) + gaze (2) floats are packed
+    into ONE pinned staging buffer and reach the device with ONE 148-byte copy per frame (four separate copies cost ~90 us
+    of stream time per frame); the rasterizer gets views of the device buffer.  Both bench arms use it."""
+
+    def __init__(self, cams, gazes, dev, depth=8):
+        self.dev = dev
+        self.meta = cams
+        self.host = []
+        for c in cams:
+            per_gaze = []
+            for g in gazes:
+                buf = np.concatenate([np.asarray(c["viewmatrix"], np.float32).ravel(), np.asarray(c["projmatrix"], np.float32).ravel(),
+                                      np.asarray(c["campos"], np.float32).ravel(), np.asarray(g, np.float32).ravel()])
+                per_gaze.append(torch.from_numpy(buf).pin_memory())
+            self.host.append(per_gaze)
+        self.bytes = 37 * 4
+
+    def upload(self, ci, gi):
+        d = self.host[ci][gi].to(self.dev, non_blocking=True)
+        c = dict(self.meta[ci])
+        c["viewmatrix"] = d[0:16].view(4, 4)
+        c["projmatrix"] = d[16:32].view(4, 4)
+        c["campos"] = d[32:35]
+        return c, d[35:37]
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -212,18 +239,14 @@ def run_ours(args, wl, rank, world, dev):
             stats.append(dict(ops.last_stats))
 
         # ---------------- e2e: host inputs, image back to the host ----------------
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        cams_host = [{k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in c.items()} for c in wl.cams]
-        gazes_host = [pin(np.asarray(g, np.float32)) for g in wl.gazes]
-        h2d = (16 + 16 + 3 + 2) * 4
+        upl = CameraUpload(wl.cams, wl.gazes, dev)
+        h2d = upl.bytes
         d2h = 3 * wl.H * wl.W * 4
         readback = Readback(dev, (3, wl.H, wl.W))
 
         def e2e_frame(f):
-            c = cams_host[f % 30]
-            cd = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
-            g = gazes_host[f % 9].to(dev, non_blocking=True)
-            img, _ = render(settings(cd), g)      # public API; reads the 64-byte frame statistics (host sync per frame)
+            cd, g = upl.upload(f % 30, f % 9)     # one 148-byte H2D copy from pinned memory
+            img, _ = render(settings(cd), g)      # public API
             readback.push(img)
 
         def e2e_loop():
@@ -294,15 +317,11 @@ def run_reference(args, wl, rank, world, dev):
         stop_evt.set()
         th.join(timeout=2.0)
         # e2e with host camera / gaze and image read-back, same protocol as our arm
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        cams_host = [{k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in c.items()} for c in wl.cams]
-        gazes_host = [pin(np.asarray(g, np.float32)) for g in wl.gazes]
+        upl = CameraUpload(wl.cams, wl.gazes, dev)
         readback = Readback(dev, (3, wl.H, wl.W))
 
         def e2e_frame(f):
-            c = cams_host[f % 30]
-            cd = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
-            g = gazes_host[f % 9].to(dev, non_blocking=True)
+            cd, g = upl.upload(f % 30, f % 9)
             out = render(cd, g)
             readback.push(out[1])
 

@@ -189,12 +189,22 @@ def _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace):
         last_stats = st
         if not st["overflow"]:
             if fresh_workspace:
-                _train_capacity_hint[(device.index, P, W, H)] = max(1 << 20, int(st["num_rendered"] * 1.25) + 1024)
+                # The training workspace is allocated per forward (it is the saved state of backward).  Its capacity only
+                # ever grows, in 4 Mi-instance steps: every iteration (a new camera, a new instance count) then asks torch's
+                # caching allocator for the SAME size and gets the block the previous iteration released — a capacity that
+                # followed num_rendered made every step a fresh multi-GB cudaMalloc (measured: 73 ms per forward).
+                key = (device.index, P, W, H)
+                need = int(st["num_rendered"] * 1.25) + 1024
+                _train_capacity_hint[key] = max(_train_capacity_hint.get(key, 1 << 20), _round_capacity(need))
             return item, st
-        min_cap = int(st["num_rendered"] * 1.25) + 1024
+        min_cap = _round_capacity(int(st["num_rendered"] * 1.25) + 1024)
 
 
 _train_capacity_hint = {}
+
+
+def _round_capacity(n, step=1 << 22):
+    return int(min(((int(n) + step - 1) // step) * step, 0xFFFFFFF0))
 
 
 def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highest_levels, gazeArray, alpha, blending,
