@@ -18,11 +18,12 @@
 // `gaussians_count` is defined by 256-entry batch boundaries.  `out_point_list` requests also use the full path.
 #include <type_traits>
 #include "fovgs_internal.cuh"
-#ifdef FOVGS_TILE_TIMING
-#include <cstdio>
-#endif
 
 namespace fovgs {
+
+#ifdef FOVGS_TILE_TIMING
+__device__ uint32_t g_tile_times[4 * 65536];
+#endif
 
 constexpr int LCAP = 2048;
 constexpr float kStartBlendL = 0.5f;
@@ -724,12 +725,14 @@ __global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x;
 #ifdef FOVGS_TILE_TIMING
-    unsigned long long tt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
-    struct TT { unsigned long long t0; int tile; uint32_t n; const Workspace* w; unsigned sm;
+    // measurement build only: (start, end) of every tile's CTA in ns + SM id, read back with fovgs_debug_tile_times()
+    struct TT { unsigned long long t0; int tile; uint32_t n; unsigned sm;
                 __device__ ~TT() { if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    printf("TT %d %u %llu %llu %u %u\n", tile, n, t0, t1, sm, blockIdx.x); } } };
+                    g_tile_times[4 * tile + 0] = (uint32_t)t0; g_tile_times[4 * tile + 1] = (uint32_t)t1;
+                    g_tile_times[4 * tile + 2] = sm; g_tile_times[4 * tile + 3] = n; } } };
+    unsigned long long tt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
     unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    TT tt_guard{tt0, tile, min(ws.tile_offset[tile + 1], hdr->cap) - min(ws.tile_offset[tile], hdr->cap), &ws, smid};
+    TT tt_guard{tt0, tile, min(ws.tile_offset[tile + 1], hdr->cap) - min(ws.tile_offset[tile], hdr->cap), smid};
 #endif
     const int bx = ((tid >> 5) & 1) * 8, by = (tid >> 6) * 4;             // this warp's 8x4 pixel block inside the tile
     const int lxi = bx + (tid & 7), lyi = by + ((tid >> 3) & 3);
@@ -861,3 +864,9 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
 }
 
 }  // namespace fovgs
+
+#ifdef FOVGS_TILE_TIMING
+extern "C" int fovgs_debug_tile_times(uint32_t* host_out, int tiles) {
+    return (int)cudaMemcpyFromSymbol(host_out, fovgs::g_tile_times, sizeof(uint32_t) * 4 * (size_t)tiles);
+}
+#endif

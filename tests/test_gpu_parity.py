@@ -305,6 +305,54 @@ def test_render_from_ply_and_camera_json(tmp_path):
     assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
 
 
+def test_large_image_uses_global_level_table():
+    """More tiles than the shared level-code table of k_pre holds (LC_MAX = 16384): the per-candidate level test falls back
+    to the global float table.  2608 x 2000 -> 163 x 125 = 20375 tiles; foveated, SMFR and MMFR against the oracle."""
+    import oracle
+    W, H = 2608, 2000
+    s = synth.add_foveation(synth.make_scene_cube(3000, 51))
+    s["scales"] = (s["scales"] * 2.0).astype(np.float32)
+    c = synth.look_at_camera(W, H, 65.0, (0.2, 0.1, -3.2))
+    gaze = (0.45, 0.55)
+    o = oracle.forward_fov(s, c, gaze, list_cap=1 << 22)
+    (n, color, radii, pl, rg, item), sc, rs = _run_fov(s, c, gaze)
+    assert n == o["num_rendered"] and np.array_equal(radii.cpu().numpy(), o["radii"])
+    assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
+    assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
+    g = torch.tensor(np.asarray(gaze, np.float32)).cuda()
+    o2 = oracle.forward_smfr(s, c, gaze)
+    n2, col2, rad2 = ops.forward_smfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"], sc["highest_levels"],
+                                      g, 0.05, True, rs)
+    assert n2 == o2["num_rendered"] and np.abs(col2.cpu().numpy() - o2["color"]).max() <= IMG_TOL
+    o3 = oracle.forward_mmfr(s, c, 1, gaze)
+    n3, col3, rad3 = ops.forward_mmfr(sc["means3D"], sc["opacity"], sc["scales"], sc["rotations"], sc["shs"], 1, g, 0.05, True, rs)
+    assert n3 == o3["num_rendered"] and np.array_equal(rad3.cpu().numpy(), o3["radii"])
+    assert np.abs(col3.cpu().numpy() - o3["color"]).max() <= IMG_TOL
+
+
+def test_conservative_cull_is_exact_on_adversarial_inputs():
+    """k_pre phase 0 drops Gaussians whose tile rectangle must be empty.  Stress it where a loose bound would show: huge and
+    strongly anisotropic splats just outside the screen, unnormalised quaternions, Gaussians hugging the near plane, a scaled
+    (non-rigid) view matrix, scale_modifier != 1 — lists and radii must still equal the oracle's exactly."""
+    import oracle
+    import diff_gaussian_rasterization_pcheck_obb as m
+    rng = np.random.default_rng(77)
+    P = 6000
+    s = synth.make_scene_cube(P, 77)
+    s["means3D"] = (rng.uniform(-1, 1, (P, 3)) * np.array([6.0, 6.0, 1.5])).astype(np.float32)     # most are off-screen
+    s["scales"] = np.exp(rng.normal(-1.5, 1.3, (P, 3))).astype(np.float32)                          # some cover the whole image
+    q = rng.normal(size=(P, 4)) * rng.uniform(0.5, 1.6, (P, 1))                                      # |q| != 1
+    s["rotations"] = q.astype(np.float32)
+    c = synth.look_at_camera(304, 176, 55.0, (0.0, 0.0, -2.2))
+    near = rng.choice(P, 300, replace=False)                                                         # hug the near plane z = 0.2
+    s["means3D"][near, 2] = (-2.2 + 0.2 + rng.normal(0, 0.01, 300)).astype(np.float32)
+    o = oracle.forward_ps1(s, c, "obb")
+    (n, color, radii, item, pl, rg), _, _ = _run_ps1(ops.MODE_OBB, s, c)
+    assert n == o["num_rendered"] and np.array_equal(radii.cpu().numpy(), o["radii"])
+    assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
+    assert (o["radii"] > 0).sum() > 200 and (o["radii"] == 0).sum() > 2000
+
+
 def test_sum_backward_vs_oracle():
     import oracle
     s = synth.make_scene_cube(3000, 33)
