@@ -182,6 +182,8 @@ EXPORTS = (
     "fovgs_forward_ps1",
     "fovgs_backward_ps1",
     "fovgs_mark_visible",
+    "fovgs_knn_workspace_bytes",
+    "fovgs_knn_mean_dist2",
     "fovgs_read_stats_async",
     "fovgs_fov_tile_tables",
     "fovgs_ps1_geometry",
@@ -219,6 +221,10 @@ def lib():
     L.fovgs_forward_ps1.argtypes = [C.POINTER(Ps1FwdArgs), C.c_void_p]
     L.fovgs_backward_ps1.argtypes = [C.POINTER(Ps1BwdArgs), C.c_void_p]
     L.fovgs_mark_visible.argtypes = [C.c_int32, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_knn_workspace_bytes.restype = C.c_size_t
+    L.fovgs_knn_workspace_bytes.argtypes = [C.c_int32]
+    L.fovgs_knn_mean_dist2.restype = C.c_int
+    L.fovgs_knn_mean_dist2.argtypes = [C.c_int32, _f, _f, _f, C.c_size_t, C.c_void_p]
     L.fovgs_read_stats_async.argtypes = [_f, _f, C.c_void_p]
     L.fovgs_fov_tile_tables.argtypes = [_f, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_ps1_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]

@@ -569,6 +569,23 @@ def mark_visible(positions, viewmatrix, projmatrix):
     return present
 
 
+def knn_mean_dist2(points):
+    """simple_knn.distCUDA2 (fov3dgs/submodules/simple-knn/spatial.cu:15-26): mean squared distance of every point to its
+    three nearest neighbours, float32 [P]."""
+    if points.dim() != 2 or points.size(1) != 3:
+        raise RuntimeError("points must have dimensions (num_points, 3)")
+    device = points.device
+    P = points.size(0)
+    out = torch.zeros((P,), dtype=torch.float32, device=device)
+    if P != 0:
+        pts = _prep(points, "points", device)
+        nbytes = lib().fovgs_knn_workspace_bytes(P)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib().fovgs_knn_mean_dist2(P, pts.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, stream), "fovgs_knn_mean_dist2")
+    return out
+
+
 def fov_tile_tables(item, W, H):
     """Parity helper: (tile_level, tile_min, grad_x, grad_y, blending) of the last FOV frame in `item`."""
     device = item["ws"].device

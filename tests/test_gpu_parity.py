@@ -353,6 +353,33 @@ def test_conservative_cull_is_exact_on_adversarial_inputs():
     assert (o["radii"] > 0).sum() > 200 and (o["radii"] == 0).sum() > 2000
 
 
+@pytest.mark.parametrize("kind,P", [("uniform", 20000), ("clustered", 30000), ("tiny", 3), ("duplicates", 5000)])
+def test_simple_knn_distCUDA2_matches_exact_knn(kind, P):
+    """simple_knn._C.distCUDA2: mean squared distance to the 3 nearest neighbours, against an exact
+    k-d tree on the CPU (scipy), on uniform, strongly clustered (COLMAP-like) and degenerate inputs."""
+    from scipy.spatial import cKDTree
+    from simple_knn._C import distCUDA2
+    rng = np.random.default_rng(len(kind) + P)
+    if kind == "uniform":
+        pts = rng.uniform(-5, 5, (P, 3))
+    elif kind == "clustered":
+        centers = rng.normal(0, 10, (40, 3))
+        pts = centers[rng.integers(0, 40, P)] + rng.normal(0, 0.05, (P, 3)) * rng.uniform(0.1, 3.0, (P, 1))
+        pts[:50] = rng.uniform(-200, 200, (50, 3))            # far outliers stretch the grid
+    elif kind == "duplicates":
+        pts = np.repeat(rng.uniform(-1, 1, (P // 5, 3)), 5, axis=0)
+    else:
+        pts = rng.uniform(-1, 1, (P, 3))
+    pts = pts.astype(np.float32)
+    out = distCUDA2(torch.from_numpy(pts).cuda()).cpu().numpy()
+    if P < 4:
+        assert out.shape == (P,) and (out > 1e37).all()               # fewer than 3 neighbours: FLT_MAX-based, like the reference
+        return
+    d, _ = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=4)
+    ref = (d[:, 1:] ** 2).mean(axis=1)
+    assert np.allclose(out, ref, rtol=2e-5, atol=1e-12)
+
+
 def test_sum_backward_vs_oracle():
     import oracle
     s = synth.make_scene_cube(3000, 33)
