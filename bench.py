@@ -362,7 +362,7 @@ def roofline(res, wl, steps):
     T = ((wl.W + 15) // 16) * ((wl.H + 15) // 16)
     P, pix = wl.P, wl.W * wl.H
     blend_share = Tb / T
-    color_bytes = V * (4 + 12 + 180 + 48 + 16) + V * 64      # visible list + xyz + SH rest + 4 dc + 4 opacity; 4 level records
+    color_bytes = V * (4 + 256) + V * 64      # visible list + one packed 256-B row (SH rest, 4 dc, 4 opacity, xyz); 4 level records
     bytes_model = {
         # k_pre: reads xyz+scale+rot+level of all P; writes radii, 2 geometry records per visible, 16 B per staged instance
         "preprocess": P * (12 + 12 + 16 + 4) + P * 4 + V * (32 + 4) + N * 12 + T * 8,
@@ -441,7 +441,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "gaussians": wl.P, "width": wl.W, "height": wl.H, "levels": 4, "alpha": 0.05,
                        "frames_per_rank": args.steps, "sharding": "frame (camera,gaze) round-robin, model replicated",
-                       "l2_policy": "inputs larger than L2 (model 1.7 GB + 0.6 GB of per-frame records vs 126 MB L2)"},
+                       "l2_policy": "inputs larger than L2 (model 1.7 GB + 0.6 GB of per-frame records vs 126 MB L2)",
+                       "model_cache": "on (library default): packed colour rows of the static model tensors, built once"},
             "clocks": res["clocks"],
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"]},
         }

@@ -59,8 +59,21 @@ int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     in.shs = a->M_rest > 0 ? a->shs_rest : nullptr; in.shs_dcs = a->shs_dcs; in.highest_levels = a->highest_levels;
     in.radii = a->radii; in.out_color = a->out_color;
     in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    in.packed_rows = (a->M_rest <= 15) ? a->packed_color_rows : nullptr;
     e = launch_forward(ws, in, W, H, MODE_FOV, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_fov");
+    return 0;
+}
+
+int fovgs_pack_color_rows(int32_t P, int32_t M_rest, const float* means3D, const float* shs_rest, const float* shs_dcs,
+                          const float* opacities, float* rows, void* stream) {
+    if (P < 0 || M_rest < 0 || M_rest > 15) return fail(FOVGS_ERR_INVALID_ARG, "pack_color_rows: P >= 0 and 0 <= M_rest <= 15%s");
+    if (P == 0) return 0;
+    if (!means3D || !shs_dcs || !opacities || !rows || (M_rest > 0 && !shs_rest))
+        return fail(FOVGS_ERR_INVALID_ARG, "pack_color_rows: null pointer%s");
+    if (((uintptr_t)rows) & 255) return fail(FOVGS_ERR_INVALID_ARG, "pack_color_rows: rows must be 256-byte aligned%s");
+    cudaError_t e = launch_pack_color_rows(P, M_rest, means3D, shs_rest, shs_dcs, opacities, rows, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "pack_color_rows");
     return 0;
 }
 

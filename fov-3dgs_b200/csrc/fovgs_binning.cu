@@ -731,6 +731,35 @@ __device__ __forceinline__ void color_tma_role(const Workspace& ws, const FrameI
         int sh_off = 0;          // float offset of this Gaussian's SH block inside its window
         bool sh_direct = false;  // window would leave the tensor: plain loads instead
         uint32_t tx = 0;
+        // packed model rows (FOV): ONE aligned 256-byte bulk copy per Gaussian = 8 full sectors in 2 DRAM lines, instead of
+        // a 4-byte-aligned 180-byte row + 48 + 16 + 12 bytes from four tensors (about 11.5 sectors in 6-7 lines)
+        const bool packed = MODE == MODE_FOV && in.packed_rows != nullptr;
+        if (packed) {
+            mbar_arrive_expect_tx(bar, valid ? 256u : 0u);
+            if (valid) bulk_g2s(b, in.packed_rows + (size_t)id * 64, 256, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            if (valid) {
+                float dx = b[61] - campos_s[0], dy = b[62] - campos_s[1], dz = b[63] - campos_s[2];
+                const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+                dx = dx / len; dy = dy / len; dz = dz / len;
+                float4* rec = ws.rec + (size_t)REC_FOV * id;
+                float3 rs = make_float3(0.f, 0.f, 0.f);
+                if (nsh) rs = sh_accumulate(b, 0, deg, dx, dy, dz, rs);
+                rs.x += 0.5f; rs.y += 0.5f; rs.z += 0.5f;
+#pragma unroll
+                for (int l = 0; l < FOV_LEVELS; l++) {
+                    float4 o;
+                    o.x = b[57 + l];
+                    o.y = fmaxf(SH_C0 * b[45 + 3 * l + 0] + rs.x, 0.0f);
+                    o.z = fmaxf(SH_C0 * b[45 + 3 * l + 1] + rs.y, 0.0f);
+                    o.w = fmaxf(SH_C0 * b[45 + 3 * l + 2] + rs.z, 0.0f);
+                    rec[2 + l] = o;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         if (valid) {
             if (nsh) {
                 const uintptr_t beg = shs_beg + (size_t)id * (size_t)nsh * 4, end = beg + (size_t)nsh * 4;
@@ -923,9 +952,10 @@ cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, in
 cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
     const int grid = num_sms * 6;
     // TMA bulk gathers need 16-byte aligned bases (the SH window logic handles the 4-byte aligned per-Gaussian offsets)
-    const bool aligned = (((uintptr_t)in.shs | (uintptr_t)in.shs_dcs | (uintptr_t)in.opacities) & 15) == 0;
+    const bool packed = mode == MODE_FOV && in.packed_rows != nullptr && (((uintptr_t)in.packed_rows) & 15) == 0;
+    const bool aligned = packed || (((uintptr_t)in.shs | (uintptr_t)in.shs_dcs | (uintptr_t)in.opacities) & 15) == 0;
     const int nsh = in.shs ? 3 * in.M : 0;
-    if (aligned && nsh <= 48 && !g_no_tma) {
+    if (aligned && nsh <= (packed ? 45 : 48) && !g_no_tma) {
         const size_t shs_floats = (size_t)in.P * (size_t)nsh;
         switch (mode) {
             case MODE_OBB: k_color_tma<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
@@ -943,6 +973,29 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
         case MODE_MMFR: k_color<MODE_MMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
         default: k_color<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in); break;
     }
+    return cudaGetLastError();
+}
+
+// one-time re-layout of the static model tensors the colour stage gathers (see FrameInputs::packed_rows)
+__global__ void k_pack_color_rows(int P, int M_rest, const float* __restrict__ means3D, const float* __restrict__ shs_rest,
+                                  const float* __restrict__ shs_dcs, const float* __restrict__ opacities, float* __restrict__ rows) {
+    const size_t n = (size_t)P * 64;
+    const int nsh = 3 * M_rest;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t g = i >> 6;
+        const int k = (int)(i & 63);
+        float v = 0.0f;
+        if (k < 45) v = (k < nsh) ? shs_rest[g * (size_t)nsh + k] : 0.0f;
+        else if (k < 57) v = shs_dcs[g * 12 + (k - 45)];
+        else if (k < 61) v = opacities[g * 4 + (k - 57)];
+        else v = means3D[g * 3 + (k - 61)];
+        rows[i] = v;
+    }
+}
+
+cudaError_t launch_pack_color_rows(int P, int M_rest, const float* means3D, const float* shs_rest, const float* shs_dcs,
+                                   const float* opacities, float* rows, cudaStream_t st) {
+    k_pack_color_rows<<<148 * 16, 256, 0, st>>>(P, M_rest, means3D, shs_rest, shs_dcs, opacities, rows);
     return cudaGetLastError();
 }
 

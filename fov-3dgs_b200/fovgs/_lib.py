@@ -68,6 +68,7 @@ class FovFwdArgs(C.Structure):
         ("max_instances", C.c_int64),
         ("out_point_list", _f),
         ("out_ranges", _f),
+        ("packed_color_rows", _f),
     ]
 
 
@@ -177,6 +178,7 @@ class Ps1BwdArgs(C.Structure):
 EXPORTS = (
     "fovgs_workspace_bytes",
     "fovgs_forward_fov",
+    "fovgs_pack_color_rows",
     "fovgs_forward_smfr",
     "fovgs_forward_mmfr",
     "fovgs_forward_ps1",
@@ -216,6 +218,8 @@ def lib():
     L.fovgs_workspace_bytes.restype = C.c_size_t
     L.fovgs_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     L.fovgs_forward_fov.argtypes = [C.POINTER(FovFwdArgs), C.c_void_p]
+    L.fovgs_pack_color_rows.argtypes = [C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_pack_color_rows.restype = C.c_int
     L.fovgs_forward_smfr.argtypes = [C.POINTER(SmfrFwdArgs), C.c_void_p]
     L.fovgs_forward_mmfr.argtypes = [C.POINTER(MmfrFwdArgs), C.c_void_p]
     L.fovgs_forward_ps1.argtypes = [C.POINTER(Ps1FwdArgs), C.c_void_p]

@@ -14,6 +14,7 @@ FOVGS_DEFERRED_CHECK=1 to skip even that (the previous frame's statistics are th
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -207,6 +208,64 @@ def _round_capacity(n, step=1 << 22):
     return int(min(((int(n) + step - 1) // step) * step, 0xFFFFFFF0))
 
 
+# ---- packed model rows for the foveated colour stage --------------------------------------------------------------------
+# The colour stage gathers, per visible Gaussian, 180 B of SH rest (4-byte aligned), 48 B of dc, 16 B of opacity and 12 B of
+# xyz from four tensors: ~11.5 DRAM sectors in 6-7 lines for 256 useful bytes.  Those four tensors are the static part of a
+# foveated model (render_compose_gazes_fps.py passes the same tensor objects every frame: pc.get_xyz, pc.get_rest_features,
+# shs_dcs.pt, opacities.pt), so they are re-laid ONCE into one aligned 256-byte row per Gaussian and the gather becomes one
+# bulk copy of 8 full sectors.  The cache entry is bound to the caller's tensor OBJECTS: it is keyed by (id, data_ptr,
+# _version, shape) of all four — any in-place update bumps `_version` and re-packs — and dropped by weak-reference callbacks
+# when one of them dies (so a recycled id / address cannot alias).  Writes that bypass autograd's version counter
+# (`tensor.data[...] = ...`, foreign kernels on `data_ptr()`) are invisible to it: call `invalidate_model_cache()` after
+# such writes or set FOVGS_MODEL_CACHE=0.  `raster_settings.debug=True` re-packs and compares on every frame.
+_MODEL_CACHE = os.environ.get("FOVGS_MODEL_CACHE", "1") != "0"
+_packed_cache = {}
+
+
+def set_model_cache(on):
+    global _MODEL_CACHE
+    _MODEL_CACHE = bool(on)
+    if not on:
+        _packed_cache.clear()
+
+
+def invalidate_model_cache():
+    _packed_cache.clear()
+
+
+def _pack_rows(P, M_rest, means3D, shs_rest, shs_dcs, opacities, device):
+    rows = torch.empty((P, 64), dtype=torch.float32, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    check(lib().fovgs_pack_color_rows(P, M_rest, means3D.data_ptr(), _ptr(shs_rest), shs_dcs.data_ptr(), opacities.data_ptr(),
+                                      rows.data_ptr(), stream), "fovgs_pack_color_rows")
+    return rows
+
+
+def _packed_rows(user, prepared, P, M_rest, device, verify):
+    """user: the caller's four tensor objects (means3D, shs_rest, shs_dcs, opacities); prepared: their contiguous fp32 forms."""
+    if not _MODEL_CACHE or M_rest > 15 or any(not isinstance(t, torch.Tensor) for t in user if t is not None):
+        return None
+    key = tuple(None if t is None else (id(t), t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in user)
+    ent = _packed_cache.get(key)
+    if ent is None:
+        rows = _pack_rows(P, M_rest, *prepared, device)
+        if len(_packed_cache) >= 4:
+            _packed_cache.pop(next(iter(_packed_cache)))
+        refs = []
+        for t in user:
+            if t is not None:
+                try:
+                    refs.append(weakref.finalize(t, _packed_cache.pop, key, None))
+                except TypeError:
+                    return rows          # not weak-referenceable: use the rows for this call only
+        _packed_cache[key] = {"rows": rows, "refs": refs}
+        return rows
+    if verify and not torch.equal(ent["rows"], _pack_rows(P, M_rest, *prepared, device)):
+        raise RuntimeError("fovgs: the packed model cache is stale (a model tensor was modified without bumping its version "
+                           "counter); call fovgs.ops.invalidate_model_cache() after such writes")
+    return ent["rows"]
+
+
 def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highest_levels, gazeArray, alpha, blending,
                 raster_settings, want_lists=False):
     """Foveated forward.  Returns (num_rendered, color[3,H,W], radii[P]) (+ point_list, ranges when want_lists)."""
@@ -220,6 +279,7 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
         z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
         return 0, z, torch.zeros((0,), dtype=torch.int32, device=device)
     keep = []
+    user_model = (means3D, shs_rest if (shs_rest is not None and shs_rest.numel()) else None, shs_dcs, opacities)
     means3D = _prep(means3D, "means3D", device)
     opacities = _prep(opacities, "opacities", device)
     if opacities.numel() != P * 4:
@@ -243,9 +303,11 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
     radii = torch.empty((P,), dtype=torch.int32, device=device)
     T = ((W + 15) // 16) * ((H + 15) // 16)
     lists = {}
+    packed = _packed_rows(user_model, (means3D, shs_rest, shs_dcs, opacities), P, M_rest, device, bool(rs.debug))
 
     def launch(item, stream):
         a = FovFwdArgs()
+        a.packed_color_rows = None if packed is None else packed.data_ptr()
         a.cam = cam
         a.P = P
         a.M_rest = M_rest

@@ -558,6 +558,67 @@ def test_tma_colour_stage_equals_register_staged_stage(scene_small):
     assert torch.equal(outs[0][3][v2], outs[1][3][v2])
 
 
+def test_packed_model_cache_is_bit_identical_and_tracks_updates(scene_small):
+    """The foveated colour stage reads the static model tensors through a packed copy (one aligned 256-byte row per
+    Gaussian) cached on the caller's tensor objects.  Same bits with and without it; an in-place update (version counter)
+    re-packs; `.data` writes are caught in debug mode; dead tensors drop their entry."""
+    import gc
+    import diff_gaussian_rasterization_fov_pcheck_obb as m
+    s, c = scene_small
+    sc = _cuda(synth.add_foveation(s))
+    rs = _settings(m, c, 3)
+    g = torch.tensor([0.4, 0.6], device="cuda")
+
+    def run(settings=rs):
+        return ops.forward_fov(sc["means3D"], sc["opacities4"], sc["scales"], sc["rotations"], sc["shs_rest"], sc["shs_dcs"],
+                               sc["highest_levels"], g, 0.05, True, settings)[1].clone()
+
+    ops.invalidate_model_cache()
+    ops.set_model_cache(False)
+    ref = run()
+    ops.set_model_cache(True)
+    a = run()
+    assert len(ops._packed_cache) == 1
+    b = run()
+    assert len(ops._packed_cache) == 1 and torch.equal(ref, a) and torch.equal(ref, b)
+    sc["shs_dcs"].mul_(0.5)                       # in-place: version bump -> new key -> re-pack
+    ops.set_model_cache(False); ref2 = run(); ops.set_model_cache(True)
+    c2 = run()
+    assert torch.equal(ref2, c2) and not torch.equal(ref, c2)
+    sc["opacities4"].data.mul_(0.5)               # bypasses the version counter: stale rows, caught by debug mode
+    with pytest.raises(RuntimeError, match="stale"):
+        run(_settings(m, c, 3, debug=True))
+    ops.invalidate_model_cache()
+    assert torch.equal(run(), run(_settings(m, c, 3, debug=True)))
+    n_before = len(ops._packed_cache)
+    sc["shs_dcs"] = sc["shs_dcs"].clone()         # the old tensor object dies -> its entry goes with it
+    gc.collect()
+    assert len(ops._packed_cache) == n_before - 1
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_lower_sh_degrees_through_packed_and_unpacked_colour_paths(deg):
+    """Models with fewer SH coefficients (M_rest = 0, 3, 8): the packed colour rows are zero padded, the TMA windows shrink."""
+    import oracle
+    s = synth.make_scene_cube(3000, 61)
+    s["shs"] = np.ascontiguousarray(s["shs"][:, : (deg + 1) ** 2])
+    s["sh_degree"] = deg
+    f = synth.add_foveation(s)
+    c = _small_cam(256, 160)
+    o = oracle.forward_fov(f, c, (0.5, 0.4))
+    for cache in (True, False):
+        ops.set_model_cache(cache)
+        try:
+            (n, color, radii, pl, rg, item), _, _ = _run_fov(f, c, (0.5, 0.4))
+        finally:
+            ops.set_model_cache(True)
+        assert n == o["num_rendered"] and np.array_equal(radii.cpu().numpy(), o["radii"])
+        assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
+    o1 = oracle.forward_ps1(s, c, "obb")
+    (n1, col1, rad1, item1, pl1, rg1), _, _ = _run_ps1(ops.MODE_OBB, s, c)
+    assert n1 == o1["num_rendered"] and np.abs(col1.cpu().numpy() - o1["color"]).max() <= IMG_TOL
+
+
 def test_capacity_overflow_regrows(monkeypatch):
     monkeypatch.setenv("FOVGS_INSTANCE_CAPACITY", "1000")
     ops._pool.clear()
