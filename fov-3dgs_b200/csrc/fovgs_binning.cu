@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                     keep = !out;                      // NaN anywhere: comparisons are false -> keep
                 }
                 if (!keep) in.radii[idx0] = 0;
+                // the reference prints and __trap()s (fatal for the context) when `prefiltered` is set and a Gaussian fails the
+                // near-plane test (auxiliary.h:286-293); here the frame completes and the count travels in the statistics
+                if (cam.prefiltered && tz <= 0.2f) atomicAdd(&ws.hdr->stats.reserved[3], 1u);
             }
             const unsigned km = __ballot_sync(0xffffffffu, keep);
             if (keep) wm.queue[qn + __popc(km & lt_mask)] = (uint32_t)idx0;

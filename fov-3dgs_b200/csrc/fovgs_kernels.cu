@@ -185,7 +185,7 @@ struct SetupArgs {
     const float* bg;
     const float* gaze;
     float tanfovx, tanfovy, focal_x, focal_y, scale_modifier, alpha, cur_level;
-    int W, H, gx, gy, sh_degree, M, P, tiles;
+    int W, H, gx, gy, sh_degree, M, P, tiles, prefiltered;
     uint32_t cap;
 };
 
@@ -220,6 +220,7 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->cam.grid_y = a.gy;
             h->cam.sh_degree = a.sh_degree;
             h->cam.M = a.M;
+            h->cam.prefiltered = a.prefiltered;
             h->alpha = a.alpha;
             h->cur_level = a.cur_level;
             h->P = a.P;
@@ -351,7 +352,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     a.scale_modifier = cam.scale_modifier; a.alpha = alpha; a.cur_level = cur_level;
     a.W = cam.image_width; a.H = cam.image_height;
     a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
-    a.sh_degree = cam.sh_degree; a.M = M; a.P = P; a.tiles = a.gx * a.gy; a.cap = cap;
+    a.sh_degree = cam.sh_degree; a.prefiltered = cam.prefiltered; a.M = M; a.P = P; a.tiles = a.gx * a.gy; a.cap = cap;
     const int T = a.tiles;
     prof_mark(0, st);
     k_setup<<<(T + 255) / 256, 256, 0, st>>>(ws, a);

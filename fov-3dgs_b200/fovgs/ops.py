@@ -157,6 +157,7 @@ def _stats_dict(item):
         "blend_consumed": int(s[5]) & 0xFFFFFFFF,
         "blend_block_pairs": int(s[6]) & 0xFFFFFFFF,
         "candidates": int(s[7]) & 0xFFFFFFFF,
+        "prefiltered_violations": int(s[8]) & 0xFFFFFFFF,
     }
 
 
@@ -188,6 +189,9 @@ def _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace):
         torch.cuda.current_stream(device).synchronize()
         st = _stats_dict(item)
         last_stats = st
+        if st["prefiltered_violations"]:
+            raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen! "
+                               f"({st['prefiltered_violations']} Gaussians behind the near plane)")
         if not st["overflow"]:
             if fresh_workspace:
                 # The training workspace is allocated per forward (it is the saved state of backward).  Its capacity only

@@ -495,6 +495,30 @@ def test_edge_cases_empty_culled_single_and_huge():
     assert np.abs(col.cpu().numpy() - o["color"]).max() <= IMG_TOL
 
 
+def test_prefiltered_flag_reports_near_plane_violations(scene_small):
+    """`prefiltered=True` promises that no Gaussian is behind the near plane; the reference prints and __trap()s when the
+    promise is broken (auxiliary.h:286-293).  Here the call raises RuntimeError with the reference's message instead of
+    killing the CUDA context; with the promise kept the flag changes nothing."""
+    import diff_gaussian_rasterization_pcheck_obb as m
+    s, c = scene_small
+    sc = _cuda(s)
+    cc = _cuda(c)
+
+    def rs(pref):
+        return m.GaussianRasterizationSettings(c["image_height"], c["image_width"], c["tanfovx"], c["tanfovy"], torch.zeros(3, device="cuda"),
+                                               1.0, cc["viewmatrix"], cc["projmatrix"], 3, cc["campos"], pref, False)
+
+    kw = dict(means2D=None, opacities=sc["opacity"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    a = m.GaussianRasterizer(raster_settings=rs(False))(means3D=sc["means3D"], **kw)[0]
+    b = m.GaussianRasterizer(raster_settings=rs(True))(means3D=sc["means3D"], **kw)[0]      # scene is entirely in front
+    assert torch.equal(a, b)
+    behind = sc["means3D"].clone()
+    behind[:7, 2] = -50.0
+    with pytest.raises(RuntimeError, match="filtered although prefiltered is set"):
+        m.GaussianRasterizer(raster_settings=rs(True))(means3D=behind, **kw)
+    m.GaussianRasterizer(raster_settings=rs(False))(means3D=behind, **kw)                    # without the promise: just culled
+
+
 def test_equal_depth_ties_are_ordered_by_id():
     """Many Gaussians on one fronto-parallel plane: equal depth bits -> the stable order is by Gaussian id."""
     import oracle
