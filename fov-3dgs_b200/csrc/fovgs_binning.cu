@@ -16,6 +16,7 @@
 //   k_color_tma  SH colours of the visible Gaussians (TMA bulk gathers).
 //   k_scatter  staged instances -> their tiles' segments (cursor atomics; trivially balanced: one thread per instance).
 #include "fovgs_internal.cuh"
+#include "fovgs_tma.cuh"
 
 namespace fovgs {
 
@@ -635,32 +636,6 @@ __global__ void __launch_bounds__(CW * 32) k_color(Workspace ws, FrameInputs in)
 // aligned window and the consumer reads at the residual offset.  Requires 16-byte aligned base pointers (checked on the
 // host; otherwise k_color is used).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // Scatter: staged instance -> its tile's segment of the key array (cursor allocation inside the segment).  12 B in, one
 // L2 fetch-and-add and one scattered 8-byte store per instance; the next batch's loads are in flight while this batch is

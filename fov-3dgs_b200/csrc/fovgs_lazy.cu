@@ -652,40 +652,44 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                 }
                 __syncwarp();
                 kept += cnt;
-                for (uint32_t k = 0; k < cnt; k++) {
-                    if (__all_sync(0xffffffffu, done)) break;
-                    const int j = wl[k];
+                // one splat of the warp's list against this lane's pixel; returns alpha*T of the hit (0 if none)
+                auto composite = [&](const int j, const float power, bool& in_cut) -> float {
                     float w = 0.0f;
-                    bool in_cut = false;
-                    if (!done) {
-                        const float4 a = sm.bl.sA[j];
-                        const float4 bq = sm.bl.sB[j];
-                        const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-                        const float power = gauss_power(a.z, a.w, bq.x, dx, dy);
-                        if (!(power > 0.0f || power < -4.5f)) {
-                            in_cut = true;
-                            const float alpha = fminf(0.99f, FM(bq.y, expf(power)));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                const float test_T = FM(T, FS(1.0f, alpha));
-                                if (test_T < 0.0001f) {
-                                    done = true;
-                                } else {
-                                    // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
-                                    const float4 c = sm.bl.sC[j];
-                                    w = FM(alpha, T);
-                                    C0 = FF(T, FM(alpha, c.x), C0);
-                                    C1 = FF(T, FM(alpha, c.y), C1);
-                                    C2 = FF(T, FM(alpha, c.z), C2);
-                                    T = test_T;
-                                    last_contributor = b0 + (uint32_t)j + 1u;
-                                }
+                    in_cut = false;
+                    if (!done && !(power > 0.0f || power < -4.5f)) {
+                        in_cut = true;
+                        const float alpha = fminf(0.99f, FM(sm.bl.sB[j].y, expf(power)));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float test_T = FM(T, FS(1.0f, alpha));
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
+                                const float4 c = sm.bl.sC[j];
+                                w = FM(alpha, T);
+                                C0 = FF(T, FM(alpha, c.x), C0);
+                                C1 = FF(T, FM(alpha, c.y), C1);
+                                C2 = FF(T, FM(alpha, c.z), C2);
+                                T = test_T;
+                                last_contributor = b0 + (uint32_t)j + 1u;
                             }
                         }
                     }
+                    return w;
+                };
+                auto record = [&](const int j, const float w, const bool in_cut) {
                     if (STAT == STAT_SUM) {
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-                        if (lane == 0 && w != 0.0f) atomicAdd(&sx.acc[j], w);
+                        // sum of alpha*T over the warp's 32 pixels with two REDUX instead of a 5-step shuffle tree per splat:
+                        // block floating point — the largest term fixes a power-of-two scale that puts it just below 2^26,
+                        // the 32 scaled terms are rounded to integers and summed exactly (< 2^31).  Error <= 2^-26 of the
+                        // largest term per addend, i.e. fp32-summation accuracy (the reference's atomics are no better).
+                        const unsigned wb = __reduce_max_sync(0xffffffffu, __float_as_uint(w));
+                        if (wb) {
+                            const int e = (int)(wb >> 23) - 127;                       // largest term in [2^e, 2^(e+1))
+                            const float up = __uint_as_float((unsigned)(127 + 25 - e) << 23);
+                            const unsigned si = __reduce_add_sync(0xffffffffu, __float2uint_rn(w * up));
+                            if (lane == 0) atomicAdd(&sx.acc[j], (float)si * __uint_as_float((unsigned)(127 - 25 + e) << 23));
+                        }
                     } else if (STAT == STAT_MAX) {
                         const unsigned hits = __ballot_sync(0xffffffffu, in_cut);
                         const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(w));   // w >= 0: bit order = value order
@@ -696,6 +700,31 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     } else {
                         if (w > max_contrib) { max_contrib = w; max_idx = sx.ids[j]; }
                     }
+                };
+                auto power_of = [&](const int j) {
+                    const float4 a = sm.bl.sA[j];
+                    return gauss_power(a.z, a.w, sm.bl.sB[j].x, FS(a.x, pixx), FS(a.y, pixy));
+                };
+                // four falloff exponents in flight (independent of T), then applied in list order
+                const uint32_t* __restrict__ wl4 = reinterpret_cast<const uint32_t*>(wl);
+                uint32_t k = 0;
+                for (; k + 3 < cnt; k += 4) {
+                    if (__all_sync(0xffffffffu, done)) break;
+                    const uint32_t q = wl4[k >> 2];
+                    const int j0 = q & 0xff, j1 = (q >> 8) & 0xff, j2 = (q >> 16) & 0xff, j3 = q >> 24;
+                    const float p0 = power_of(j0), p1 = power_of(j1), p2 = power_of(j2), p3 = power_of(j3);
+                    bool c0, c1, c2, c3;
+                    const float w0 = composite(j0, p0, c0); record(j0, w0, c0);
+                    const float w1 = composite(j1, p1, c1); record(j1, w1, c1);
+                    const float w2 = composite(j2, p2, c2); record(j2, w2, c2);
+                    const float w3 = composite(j3, p3, c3); record(j3, w3, c3);
+                }
+                for (; k < cnt; k++) {
+                    if (__all_sync(0xffffffffu, done)) break;
+                    const int j = wl[k];
+                    bool c;
+                    const float w = composite(j, power_of(j), c);
+                    record(j, w, c);
                 }
             }
             __syncthreads();
