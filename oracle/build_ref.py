@@ -79,9 +79,14 @@ def build_one(name, verbose=False):
     return so_path(name)
 
 
-def build_all(force=False, verbose=False):
+# the variant bench.py --impl reference needs; __graft_entry__.build() builds only this one (about 3 minutes) unless
+# FOVGS_BUILD_ALL_REFS=1 — the other six (parity tools, goldens) take ~25 more minutes of compile time
+BENCH_VARIANTS = ("ref_fov_C",)
+
+
+def build_all(force=False, verbose=False, names=None):
     built = {}
-    for name in VARIANTS:
+    for name in (names or VARIANTS):
         p = so_path(name)
         if p and not force:
             built[name] = p
