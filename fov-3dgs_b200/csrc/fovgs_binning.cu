@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
 
         // ---------------- phase B: candidate tiles (lane = candidate), 32 per round ----------------
         uint32_t owners_before = 0;   // non-empty owners whose range starts before the current window
+#pragma unroll 2   // two rounds share no registers: the staging stores of round r need not drain before round r+1 starts
         for (uint32_t r = 0; r < total; r += 32) {
             const uint32_t c = r + lane;
             const bool valid = c < total;
