@@ -26,6 +26,12 @@ __device__ uint32_t g_tile_times[4 * 65536];
 #endif
 
 constexpr int LCAP = 2048;
+#ifndef LAZY_FIRST_GROUP
+#define LAZY_FIRST_GROUP 512u   // first sorted group of a partitioned tile; doubles up to LCAP
+#endif
+#ifndef LAZY_DIRECT_MAX
+#define LAZY_DIRECT_MAX 2048u    // tiles up to this many instances are sorted whole in shared memory (<= LCAP)
+#endif
 constexpr float kStartBlendL = 0.5f;
 
 struct SortScratch { uint32_t whist[8][256]; uint32_t totals[256]; };
@@ -455,7 +461,7 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     const uint32_t n = send - sbeg;
     if (n == 0) return;
     const uint64_t* __restrict__ gA = ws.keysA + sbeg;
-    if (n <= (uint32_t)LCAP) {
+    if (n <= LAZY_DIRECT_MAX) {
 #pragma unroll 4
         for (uint32_t i = tid; i < n; i += 256) sm.keys[0][i] = gA[i];
         __syncthreads();
@@ -539,10 +545,16 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     // ---- front-to-back over groups of buckets ----
     int b = 0;
     bool all_done = false;
+    // group size grows geometrically: a tile that saturates within its nearest few hundred splats sorts only those, a tile that
+    // needs everything pays at most a few extra group boundaries
+    uint32_t gcap = LAZY_FIRST_GROUP;
     while (b < 256 && !all_done) {
         const uint32_t g0 = sm.bucket_off[b];
-        // buckets [b, e) fit the shared buffer together: bucket_off is monotone, so the fitting ones form a prefix — count them
-        const int e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= (uint32_t)LCAP);
+        // buckets [b, e) fit the group together: bucket_off is monotone, so the fitting ones form a prefix — count them
+        int e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= gcap);
+        if (e == b && gcap < (uint32_t)LCAP)   // the next bucket alone exceeds the small cap: take what the buffer holds
+            e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= (uint32_t)LCAP);
+        gcap = min(gcap * 2u, (uint32_t)LCAP);
         if (e == b) {
             // one bucket larger than the shared buffer (>= 2048 keys agreeing in all depth bits above `shift`):
             // order it completely with the block radix sort on the global ping-pong ranges (this tile's slice of

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfovgs.so")
+# FOVGS_LIB_PATH: load another build of the same library (A/B measurements of compile-time parameters)
+LIB_PATH = os.environ.get("FOVGS_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libfovgs.so")
 
 FOVGS_PS1_OBB = 0
 FOVGS_PS1_SUM = 1
