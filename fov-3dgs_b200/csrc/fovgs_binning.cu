@@ -108,9 +108,27 @@ __device__ __forceinline__ bool project_splat_cov(const CamParams& cam, float mx
     return true;
 }
 
-constexpr int PB = 256;            // threads per block
+#ifndef PRE_PB
+#define PRE_PB 256
+#endif
+#ifndef PRE_CTAS
+#define PRE_CTAS 4
+#endif
+#ifndef PRE_WCHUNK
+#define PRE_WCHUNK 512
+#endif
+#ifndef PRE_TICKET
+#define PRE_TICKET 64
+#endif
+#ifndef SCAT_U
+#define SCAT_U 8
+#endif
+#ifndef SCAT_CTAS
+#define SCAT_CTAS 8
+#endif
+constexpr int PB = PRE_PB;         // threads per block
 constexpr int WPB = PB / 32;       // warps per block; every warp is an autonomous worker (no block barriers)
-constexpr uint32_t WCHUNK = 512;   // staging slots a warp reserves per global atomic
+constexpr uint32_t WCHUNK = PRE_WCHUNK;   // staging slots a warp reserves per global atomic
 constexpr uint32_t VCHUNK = 128;   // visible-list slots a warp reserves per global atomic
 constexpr int SHW = 65;            // k_color: floats per staged Gaussian (64 + 1 pad: conflict-free lane-strided reads)
 
@@ -135,7 +153,8 @@ struct ScanSmem {
 };
 
 constexpr int LC_MAX = 16384;      // tiles whose level code fits the shared table (1080p: 8160)
-constexpr int PRE_CHUNK = 128;     // Gaussians per work ticket of k_pre
+constexpr int PRE_CHUNK = PRE_TICKET;   // Gaussians per work ticket of k_pre
+static_assert(PRE_CHUNK % 32 == 0 && PRE_CHUNK <= 256, "ticket = whole batches; its inputs are prefetched by one warp");
 
 struct PreSmem {
     CamParams cam;
@@ -153,7 +172,7 @@ template <int NT>
 __device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s);
 
 template <int MODE>
-__global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
+__global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs in) {
     __shared__ PreSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -204,7 +223,7 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
     const float cull_k = sm.cull_k;
     const float scr_w = (float)(16 * cam.grid_x), scr_h = (float)(16 * cam.grid_y);
     const bool use_codes = is_foveated(MODE) && ws.hdr->tiles <= LC_MAX;
-    // Dynamic work distribution: warps draw 128-Gaussian chunks from a global ticket counter (splats that cover hundreds
+    // Dynamic work distribution: warps draw 64-Gaussian chunks (PRE_TICKET) from a global ticket counter (splats that cover hundreds
     // of tiles are rare and random, a static partition leaves a 12 % tail).  The next ticket is requested one chunk ahead;
     // its value is only looked at when the current chunk is used up.
     const uint32_t nchunks = ((uint32_t)in.P + PRE_CHUNK - 1) / PRE_CHUNK;
@@ -280,12 +299,12 @@ __global__ void __launch_bounds__(PB, 4) k_pre(Workspace ws, FrameInputs in) {
                 // the new chunk's inputs start their way up from HBM now (means 12 lines, scales 12, rotations 16)
                 const size_t g0 = (size_t)cur * PRE_CHUNK;
                 const char* pm = (const char*)(in.means3D + 3 * g0) + 128 * lane;
-                if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
+                if (lane < PRE_CHUNK * 12 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
                 if (in.cov3D_precomp == nullptr) {
                     const char* ps = (const char*)(in.scales + 3 * g0) + 128 * lane;
                     const char* pr = (const char*)(in.rotations + 4 * g0) + 128 * lane;
-                    if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps));
-                    if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+                    if (lane < PRE_CHUNK * 12 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps));
+                    if (lane < PRE_CHUNK * 16 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
                 }
             }
         }
@@ -645,7 +664,7 @@ __global__ void __launch_bounds__(CW * 32) k_color(Workspace ws, FrameInputs in)
 __device__ __forceinline__ void scatter_role(const Workspace& ws, const uint32_t t, const uint32_t nthreads) {
     const uint32_t n = min(ws.hdr->stage_cursor, ws.stage_cap);
     const uint32_t cap = ws.hdr->cap;
-    constexpr int U = 4;
+    constexpr int U = SCAT_U;
     uint32_t tl[U], ntl[U];
     unsigned long long k[U], nk[U];
     auto load = [&](uint32_t i0, uint32_t* T, unsigned long long* K) {
@@ -917,7 +936,7 @@ __device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s) {
 
 cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
     const int need = (in.P + PB - 1) / PB;
-    const int grid = max(1, min(need, min(num_sms * 4, (int)STAGE_MAX_BLOCKS)));
+    const int grid = max(1, min(need, min(num_sms * PRE_CTAS, (int)STAGE_MAX_BLOCKS)));
     switch (mode) {
         case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, 0, st>>>(ws, in); break;
         case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, 0, st>>>(ws, in); break;
@@ -979,7 +998,7 @@ cudaError_t launch_pack_color_rows(int P, int M_rest, const float* means3D, cons
 }
 
 cudaError_t launch_scatter(const Workspace& ws, int num_sms, cudaStream_t st) {
-    k_scatter<<<num_sms * 8, 256, 0, st>>>(ws);
+    k_scatter<<<num_sms * SCAT_CTAS, 256, 0, st>>>(ws);
     return cudaGetLastError();
 }
 
