@@ -29,6 +29,12 @@ constexpr int LCAP = 2048;
 #ifndef LAZY_FIRST_GROUP
 #define LAZY_FIRST_GROUP 512u   // first sorted group of a partitioned tile; doubles up to LCAP
 #endif
+#ifndef LAZY_CTAS
+#define LAZY_CTAS 4            // CTAs per SM the kernel is compiled for (register cap 64)
+#endif
+#ifndef LAZY_MU
+#define LAZY_MU 8
+#endif
 #ifndef LAZY_DIRECT_MAX
 #define LAZY_DIRECT_MAX 2048u    // tiles up to this many instances are sorted whole in shared memory (<= LCAP)
 #endif
@@ -471,7 +477,7 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     }
     // ---- MSD partition of the tile's keys by their highest varying depth byte ----
     uint64_t* gB = ws.keysB + sbeg;
-    constexpr int MU = 8;   // keys in flight per thread in the partition passes (L2 round trips overlap)
+    constexpr int MU = LAZY_MU;   // keys in flight per thread in the partition passes (L2 round trips overlap)
     // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile).  The position is
     // guessed from the first 2048 keys (the scatter left them in arbitrary order) and verified for free by the histogram
     // pass, which ORs the differences of ALL keys; a wrong guess (never seen in practice) repeats the histogram.
@@ -757,7 +763,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
 }
 
 template <int MODE, int STAT = STAT_SUM>
-__global__ void __launch_bounds__(256, 4) k_lazy_blend(Workspace ws, FrameInputs in) {
+__global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, FrameInputs in) {
     extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
     LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
     const FrameHeader* __restrict__ hdr = ws.hdr;
