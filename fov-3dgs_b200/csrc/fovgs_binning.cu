@@ -134,6 +134,7 @@ constexpr int SHW = 65;            // k_color: floats per staged Gaussian (64 + 
 
 struct WarpSmem {
     float px[32], py[32], e1x[32], e1y[32], e2x[32], e2y[32], l1[32], l2[32], hl1[32], rw[32];
+    float mnx[32], mxx[32], mny[32], mxy[32];   // extents of the OBB's corners (tile-axis separations of the OBB test)
     uint32_t dbits[32];
     int x0[32], y0[32], w[32];
     uint32_t pref[33];
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                     if (use_codes) hcode = (uint32_t)li + 1u;
                 }
             }
+            float e_mnx = 0.f, e_mxx = 0.f, e_mny = 0.f, e_mxy = 0.f;
             if (!single0 && true) {
                 // The OBB test starts with the two tile-axis separations (auxiliary.h:95-118; obb_hits_tile): a tile
                 // column tx can only pass when max(vx) - (16 tx + 8) >= -8 and min(vx) - (16 tx + 8) <= 8, same for
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                 const float mxx = fmaxf(fmaxf(oc.vx[0], oc.vx[1]), fmaxf(oc.vx[2], oc.vx[3]));
                 const float mny = fminf(fminf(oc.vy[0], oc.vy[1]), fminf(oc.vy[2], oc.vy[3]));
                 const float mxy = fmaxf(fmaxf(oc.vy[0], oc.vy[1]), fmaxf(oc.vy[2], oc.vy[3]));
+                e_mnx = mnx; e_mxx = mxx; e_mny = mny; e_mxy = mxy;
                 if (fabsf(mnx) < 1e8f && fabsf(mxx) < 1e8f) {
                     const float e = 0.05f + 1e-6f * (fabsf(mnx) + fabsf(mxx));
                     cx0 = max(cx0, (int)fmaxf(ceilf((mnx - 16.0f - e) * 0.0625f), 0.0f));
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
             wm.px[lane] = s.px; wm.py[lane] = s.py;
             wm.e1x[lane] = s.e1x; wm.e1y[lane] = s.e1y; wm.e2x[lane] = s.e2x; wm.e2y[lane] = s.e2y;
             wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
+            wm.mnx[lane] = e_mnx; wm.mxx[lane] = e_mxx; wm.mny[lane] = e_mny; wm.mxy[lane] = e_mxy;
             wm.dbits[lane] = __float_as_uint(s.depth);
             wm.x0[lane] = cx0; wm.y0[lane] = cy0; wm.w[lane] = cw; wm.rw[lane] = 1.0f / (float)max(cw, 1);
             if (is_foveated(MODE)) { wm.hl1[lane] = FA(hl, 1.0f); wm.hcode[lane] = hcode; }
@@ -429,10 +433,9 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                     const float cx = wm.px[owner], cy = wm.py[owner];
                     const float e1x = wm.e1x[owner], e1y = wm.e1y[owner], e2x = wm.e2x[owner], e2y = wm.e2y[owner];
                     const float l1 = wm.l1[owner], l2 = wm.l2[owner];
-                    ObbCorners oc;
-                    obb_corners(cx, cy, e1x, e1y, e2x, e2y, l1, l2, oc);
                     const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
-                    pass = obb_hits_tile(oc, cx, cy, e1x, e1y, e2x, e2y, l1, l2, tcx, tcy);
+                    pass = obb_hits_tile_ext(wm.mnx[owner], wm.mxx[owner], wm.mny[owner], wm.mxy[owner], cx, cy, e1x, e1y, e2x, e2y,
+                                             l1, l2, tcx, tcy);
                 }
                 // RED (no return value).  Measured alternative: taking the returned rank here so that the scatter needs no
                 // atomics costs k_pre +0.05 ms (even with the dependent store deferred by a round) and saves the scatter
