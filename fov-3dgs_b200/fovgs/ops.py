@@ -222,8 +222,11 @@ def _round_capacity(n, step=1 << 22):
 # when one of them dies (so a recycled id / address cannot alias).  Writes that bypass autograd's version counter
 # (`tensor.data[...] = ...`, foreign kernels on `data_ptr()`) are invisible to it: call `invalidate_model_cache()` after
 # such writes or set FOVGS_MODEL_CACHE=0.  `raster_settings.debug=True` re-packs and compares on every frame.
+# Packing costs about one frame (1 ms for 6 M Gaussians), so it only happens at the SECOND consecutive call that brings the same
+# four tensor objects: a caller that builds fresh tensors every frame never pays for it (and gets the un-packed gather).
 _MODEL_CACHE = os.environ.get("FOVGS_MODEL_CACHE", "1") != "0"
 _packed_cache = {}
+_packed_candidate = [None]
 
 
 def set_model_cache(on):
@@ -235,6 +238,7 @@ def set_model_cache(on):
 
 def invalidate_model_cache():
     _packed_cache.clear()
+    _packed_candidate[0] = None
 
 
 def _pack_rows(P, M_rest, means3D, shs_rest, shs_dcs, opacities, device):
@@ -252,6 +256,10 @@ def _packed_rows(user, prepared, P, M_rest, device, verify):
     key = tuple(None if t is None else (id(t), t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in user)
     ent = _packed_cache.get(key)
     if ent is None:
+        if _packed_candidate[0] != key:      # first sighting of these tensors: remember them, gather un-packed this frame
+            _packed_candidate[0] = key
+            return None
+        _packed_candidate[0] = None
         rows = _pack_rows(P, M_rest, *prepared, device)
         if len(_packed_cache) >= 4:
             _packed_cache.pop(next(iter(_packed_cache)))

@@ -601,18 +601,22 @@ def test_packed_model_cache_is_bit_identical_and_tracks_updates(scene_small):
     ops.set_model_cache(False)
     ref = run()
     ops.set_model_cache(True)
-    a = run()
+    a0 = run()                                    # first sighting of these tensor objects: un-packed gather, nothing cached
+    assert len(ops._packed_cache) == 0
+    a = run()                                     # second consecutive call with the same objects: packed
     assert len(ops._packed_cache) == 1
     b = run()
-    assert len(ops._packed_cache) == 1 and torch.equal(ref, a) and torch.equal(ref, b)
-    sc["shs_dcs"].mul_(0.5)                       # in-place: version bump -> new key -> re-pack
+    assert len(ops._packed_cache) == 1 and torch.equal(ref, a0) and torch.equal(ref, a) and torch.equal(ref, b)
+    sc["shs_dcs"].mul_(0.5)                       # in-place: version bump -> new key -> re-pack (at the second call)
     ops.set_model_cache(False); ref2 = run(); ops.set_model_cache(True)
+    run()
     c2 = run()
-    assert torch.equal(ref2, c2) and not torch.equal(ref, c2)
+    assert torch.equal(ref2, c2) and not torch.equal(ref, c2) and len(ops._packed_cache) == 1
     sc["opacities4"].data.mul_(0.5)               # bypasses the version counter: stale rows, caught by debug mode
     with pytest.raises(RuntimeError, match="stale"):
         run(_settings(m, c, 3, debug=True))
     ops.invalidate_model_cache()
+    run()
     assert torch.equal(run(), run(_settings(m, c, 3, debug=True)))
     n_before = len(ops._packed_cache)
     sc["shs_dcs"] = sc["shs_dcs"].clone()         # the old tensor object dies -> its entry goes with it
