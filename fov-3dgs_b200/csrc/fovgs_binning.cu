@@ -1,19 +1,22 @@
 // fovgs_binning.cu — per-Gaussian stage of the forward path, written for load balance.
 //
-//   k_pre      project every Gaussian (pinned arithmetic, fovgs_math.cuh), then test its candidate tiles with a
-//              BLOCK-LEVEL LOAD-BALANCED EXPANSION: the 256 Gaussians of a batch publish their tile rectangles in
-//              shared memory, an exclusive scan turns rectangle sizes into a candidate index space, and all 256
-//              threads walk that space together (thread -> candidate -> owner via binary search).  A splat that
-//              covers 2000 tiles costs 8 block rounds instead of stalling one warp for 2000 serial iterations —
-//              the reference's `filter`/`OBB_test` and `duplicateWithKeys` (FOV/cuda_rasterizer/
-//              rasterizer_impl.cu:264-383, 423-486) are thread-per-Gaussian loops and account for ~58 % of its frame
-//              at 6 M Gaussians (profiles/r1_launches_fov_6M_reference.csv).
-//              Surviving (tile, depth|id) instances are staged densely (block-granular allocation, one global
-//              atomic per 4096 slots) and counted per tile; colours of visible Gaussians are evaluated in the same
-//              kernel.  Replaces preprocessCUDA + InclusiveSum x2 + filter + duplicateWithKeys + compute_fov_colors.
+//   k_pre      persistent, warp-autonomous (one block barrier at start, one at the end).  Warps draw 64-Gaussian work
+//              tickets from a global counter.  Phase 0 (lane = Gaussian): a conservative screen cull drops the Gaussians
+//              whose tile rectangle must be empty; survivors are compacted through a per-warp ring.  Phase A (lane =
+//              surviving Gaussian): exact projection with pinned arithmetic (fovgs_math.cuh); the candidate rectangle is
+//              clipped to the level's tile bounding box and to the OBB's tile-axis band.  Phase B (lane = candidate tile):
+//              WARP-LEVEL LOAD-BALANCED EXPANSION — the 32 rectangles form one candidate index space (shuffle scan), 32
+//              candidates per round find their owner through a `redux.or` head mask, then run the exact level and OBB
+//              tests; a splat that covers 2000 tiles costs 63 warp rounds instead of stalling one lane for 2000 serial
+//              iterations (the reference's `filter`/`OBB_test` and `duplicateWithKeys`, FOV/cuda_rasterizer/
+//              rasterizer_impl.cu:264-383, 423-486, are thread-per-Gaussian loops: ~58 % of its frame at 6 M Gaussians,
+//              profiles/r1_launches_fov_6M_reference.csv).  Surviving (tile, depth|id) instances are counted per tile (RED
+//              on 256-byte-strided counters) and staged densely in per-warp 512-slot chunks.  Phase C: radii, geometry
+//              records, visible list.  Replaces preprocessCUDA + InclusiveSum x2 + filter/OBB_test + duplicateWithKeys.
 //   tile scan  exclusive scan of the tile histogram (= the reference's `ranges`, no identifyTileRanges), run by the LAST
 //              CTA of k_pre to finish (ticket counter), so it costs no launch and no idle GPU.
-//   k_color_tma  SH colours of the visible Gaussians (TMA bulk gathers).
+//   k_color_tma  SH colours of the visible Gaussians (TMA bulk gathers; packed 256-byte model rows for foveated models);
+//              k_color is the register-staged fallback.  Replaces compute_fov_colors / computeColorFromSH.
 //   k_scatter  staged instances -> their tiles' segments (cursor atomics; trivially balanced: one thread per instance).
 #include "fovgs_internal.cuh"
 #include "fovgs_tma.cuh"

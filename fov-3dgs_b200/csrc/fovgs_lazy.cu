@@ -1,4 +1,4 @@
-// fovgs_lazy.cu — fused "sort only what you composite" kernel for the inference variants (FOV, OBB).
+// fovgs_lazy.cu — fused "sort only what you composite" kernel: all variants (FOV, SMFR, MMFR, OBB, training family).
 //
 // Measurement that motivates it (6 M Gaussians, 1080p, gaze at the dense centre): the blend stage consumes 1.7 M of the
 // 16.9 M binned instances (10 %) before every pixel of its tile has saturated (T < 1e-4) — the reference, and our
@@ -8,14 +8,16 @@
 //   1. n <= 2048: load the tile's keys into shared memory, sort (rank sort / LSD radix on the varying depth bits, ties
 //      by id), composite.
 //   2. n  > 2048: one MSD pass partitions the tile's keys (global, L2-resident) into <= 256 depth buckets by their
-//      highest varying depth byte; buckets are then grouped front to back into chunks of <= 2048 keys, each chunk is
-//      sorted in shared memory and composited; the loop stops as soon as all 256 pixels are done — the buckets behind
+//      highest varying depth byte; buckets are then grouped front to back into chunks (<= 512 keys first, doubling up to
+//      2048), each chunk is sorted in shared memory and composited; the loop stops as soon as all 256 pixels are done — the buckets behind
 //      are never sorted, never gathered.
 //
 // Per-pixel arithmetic and traversal order are exactly those of k_blend (fovgs_blend.cu), so images stay bit-identical
 // to the reference; only WHERE batch boundaries fall differs, which no pixel can observe (a pixel's `done` is its own).
-// The training variant (SUM) keeps the full sort: its backward needs the complete lists, and its
-// `gaussians_count` is defined by 256-entry batch boundaries.  `out_point_list` requests also use the full path.
+// The training family (SUM / MAX / LWMC) runs on the same producer with the reference's batch-exact semantics: the sorted
+// prefix is appended to `point_list` (what its backward walks) and composited in 256-entry batches at absolute list
+// positions (lazy_tile_sum).  Only `out_point_list` requests / FOVGS_OPT_FULL_SORT use the full-sort path (fovgs_sort.cu
+// + fovgs_blend.cu).
 #include <type_traits>
 #include "fovgs_internal.cuh"
 
