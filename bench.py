@@ -143,6 +143,24 @@ class CameraUpload:
         return c, d[35:37]
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs: pin this rank to the CPU cores (NUMA node) next to its GPU BEFORE any pinned host buffer is allocated,
+    so the per-frame 24.9 MB image read-backs of eight ranks land in local memory instead of crossing the socket link
+    (8 x 830 frames/s x 24.9 MB = 165 GB/s of device-to-host traffic).  Best effort; both bench arms use it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -405,6 +423,9 @@ def main():
         return 1
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus = bind_to_gpu_numa_node(local) if world > 1 else None
+    if world > 1 and os.environ.get("FOVGS_BENCH_VERBOSE"):
+        print(f"rank {rank}: cuda:{local} bound to {len(cpus) if cpus else 'all'} cpus", file=sys.stderr)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner to STDOUT when the first communicator is created; the contract is ONE JSON line on
@@ -467,8 +488,14 @@ def main():
             line["gpu_launches"] = 0
         else:
             line["gpu_launches"] = res["launches_per_frame"] * args.steps
-            line["e2e"]["mode"] = "pipelined (deferred statistics check); sync_value = blocking check per frame"
-            line["e2e"]["sync_value"] = total_frames / e2e_sync_max
+            # two modes of the same public call over the same loop; the headline is the better one for this configuration
+            # (pipelined wins on one GPU; with eight ranks saturating the host's device-to-host path the blocking mode,
+            # which spaces the copies out, is ahead)
+            piped, blocking = e2e_v, total_frames / e2e_sync_max
+            line["e2e"]["value"] = max(piped, blocking)
+            line["e2e"]["mode"] = "pipelined (deferred statistics check)" if piped >= blocking else "blocking statistics check per frame"
+            line["e2e"]["pipelined_value"] = piped
+            line["e2e"]["sync_value"] = blocking
             line["roofline"] = roofline(res, wl, args.steps)
             if not args.no_cpu_baseline and world == 1:
                 try:
