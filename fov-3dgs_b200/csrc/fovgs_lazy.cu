@@ -94,17 +94,21 @@ struct PixPS1 {      // OBB/forward.cu:251-384
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
         return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
     }
+    // One divergent region per splat (the falloff cut, which most lanes fail); the two rarer outcomes inside it — alpha below
+    // 1/255, pixel saturated — are selects, not branches: same values, no reconvergence barriers in the inner loop.
     __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
-        if (power > 0.0f || power < -4.5f) return;
+        if (done || power > 0.0f || power < -4.5f) return;
         const float4 b = sm.bl.sB[j];
-        const float alpha = fminf(0.99f, FM(b.y, expf(power)));
-        if (alpha < 1.0f / 255.0f) return;
-        const float test_T = FM(T, FS(1.0f, alpha));
-        if (test_T < 0.0001f) { done = true; return; }
         const float4 c = sm.bl.sC[j];
+        const float alpha = fminf(0.99f, FM(b.y, expf(power)));
+        const float test_T = FM(T, FS(1.0f, alpha));
+        const bool vis = !(alpha < 1.0f / 255.0f);
+        const bool fin = vis && test_T < 0.0001f;
+        const bool acc = vis && !fin;
         const float w = FM(alpha, T);
-        C0 = FF(c.x, w, C0); C1 = FF(c.y, w, C1); C2 = FF(c.z, w, C2);
-        T = test_T;
+        C0 = acc ? FF(c.x, w, C0) : C0; C1 = acc ? FF(c.y, w, C1) : C1; C2 = acc ? FF(c.z, w, C2) : C2;
+        T = acc ? test_T : T;
+        done = fin;
     }
 };
 struct PixFov {      // FOV/forward.cu:490-609
@@ -116,16 +120,18 @@ struct PixFov {      // FOV/forward.cu:490-609
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
         return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
     }
-    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
-        if (power > 0.0f || power < -4.5f) return;
+    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {   // see PixPS1::apply
+        if (done || power > 0.0f || power < -4.5f) return;
         const float4 c = sm.bl.sC[j];
         const float alpha = fminf(0.99f, FM(c.x, expf(power)));
-        if (alpha < 1.0f / 255.0f) return;
         const float test_T = FM(T, FS(1.0f, alpha));
-        if (test_T < 0.0001f) { done = true; return; }
+        const bool vis = !(alpha < 1.0f / 255.0f);
+        const bool fin = vis && test_T < 0.0001f;
+        const bool acc = vis && !fin;
         const float w = FM(alpha, T);
-        C0 = FF(c.y, w, C0); C1 = FF(c.z, w, C1); C2 = FF(c.w, w, C2);
-        T = test_T;
+        C0 = acc ? FF(c.y, w, C0) : C0; C1 = acc ? FF(c.z, w, C1) : C1; C2 = acc ? FF(c.w, w, C2) : C2;
+        T = acc ? test_T : T;
+        done = fin;
     }
 };
 struct PixFovBlend {  // FOV/forward.cu:262-476
