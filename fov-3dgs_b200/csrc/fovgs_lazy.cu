@@ -146,36 +146,33 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
         return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
     }
-    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
-        if (power > 0.0f || power < -4.5f) return;
+    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {   // selects, not branches: see PixPS1::apply
+        if (done || power > 0.0f || power < -4.5f) return;
         const float4 b = sm.bl.sB[j];
+        const float4 c1 = sm.bl.sC[j];
+        const float4 c2 = sm.bl.sD[j];
         const float e = expf(power);
-        if (!L1_done) {
-            const float4 c = sm.bl.sC[j];
-            const float alpha1 = fminf(0.99f, FM(c.x, e));
-            if (!(alpha1 < 1.0f / 255.0f)) {
-                const float test_T1 = FM(T1, FS(1.0f, alpha1));
-                L1_done = test_T1 < 0.0001f;
-                if (!L1_done) {
-                    const float w = FM(alpha1, T1);
-                    A0 = FF(c.y, w, A0); A1 = FF(c.z, w, A1); A2 = FF(c.w, w, A2);
-                    T1 = test_T1;
-                }
-            }
+        {
+            const float alpha1 = fminf(0.99f, FM(c1.x, e));
+            const float test_T1 = FM(T1, FS(1.0f, alpha1));
+            const bool vis = !L1_done && !(alpha1 < 1.0f / 255.0f);
+            const bool fin = vis && test_T1 < 0.0001f;
+            const bool acc = vis && !fin;
+            const float w = FM(alpha1, T1);
+            A0 = acc ? FF(c1.y, w, A0) : A0; A1 = acc ? FF(c1.z, w, A1) : A1; A2 = acc ? FF(c1.w, w, A2) : A2;
+            T1 = acc ? test_T1 : T1;
+            L1_done = L1_done || fin;
         }
-        if (!L2_done) {
-            const float4 c = sm.bl.sD[j];
-            const float alpha2 = fminf(0.99f, FM(c.x, e));
-            const bool skip2 = (alpha2 < 1.0f / 255.0f) || (FA(b.y, 1.0f) < L2_f);
-            if (!skip2) {
-                const float test_T2 = FM(T2, FS(1.0f, alpha2));
-                L2_done = test_T2 < 0.0001f;
-                if (!L2_done) {
-                    const float w = FM(alpha2, T2);
-                    B0 = FF(c.y, w, B0); B1 = FF(c.z, w, B1); B2 = FF(c.w, w, B2);
-                    T2 = test_T2;
-                }
-            }
+        {
+            const float alpha2 = fminf(0.99f, FM(c2.x, e));
+            const float test_T2 = FM(T2, FS(1.0f, alpha2));
+            const bool vis = !L2_done && !((alpha2 < 1.0f / 255.0f) || (FA(b.y, 1.0f) < L2_f));
+            const bool fin = vis && test_T2 < 0.0001f;
+            const bool acc = vis && !fin;
+            const float w = FM(alpha2, T2);
+            B0 = acc ? FF(c2.y, w, B0) : B0; B1 = acc ? FF(c2.z, w, B1) : B1; B2 = acc ? FF(c2.w, w, B2) : B2;
+            T2 = acc ? test_T2 : T2;
+            L2_done = L2_done || fin;
         }
         if (L1_done && L2_done) done = true;
     }
