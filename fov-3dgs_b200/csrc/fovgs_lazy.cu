@@ -681,22 +681,21 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     in_cut = false;
                     if (!done && !(power > 0.0f || power < -4.5f)) {
                         in_cut = true;
+                        // the two rarer outcomes (alpha below 1/255, pixel saturated) are selects, not branches
+                        const float4 c = sm.bl.sC[j];
                         const float alpha = fminf(0.99f, FM(sm.bl.sB[j].y, expf(power)));
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            const float test_T = FM(T, FS(1.0f, alpha));
-                            if (test_T < 0.0001f) {
-                                done = true;
-                            } else {
-                                // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
-                                const float4 c = sm.bl.sC[j];
-                                w = FM(alpha, T);
-                                C0 = FF(T, FM(alpha, c.x), C0);
-                                C1 = FF(T, FM(alpha, c.y), C1);
-                                C2 = FF(T, FM(alpha, c.z), C2);
-                                T = test_T;
-                                last_contributor = b0 + (uint32_t)j + 1u;
-                            }
-                        }
+                        const float test_T = FM(T, FS(1.0f, alpha));
+                        const bool vis = !(alpha < 1.0f / 255.0f);
+                        const bool fin = vis && test_T < 0.0001f;
+                        const bool acc = vis && !fin;
+                        // SUM accumulates (f*alpha)*T and records alpha*T per Gaussian (SUM/forward.cu:400-404)
+                        w = acc ? FM(alpha, T) : 0.0f;
+                        C0 = acc ? FF(T, FM(alpha, c.x), C0) : C0;
+                        C1 = acc ? FF(T, FM(alpha, c.y), C1) : C1;
+                        C2 = acc ? FF(T, FM(alpha, c.z), C2) : C2;
+                        T = acc ? test_T : T;
+                        last_contributor = acc ? b0 + (uint32_t)j + 1u : last_contributor;
+                        done = fin;
                     }
                     return w;
                 };
