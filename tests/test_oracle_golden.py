@@ -180,3 +180,52 @@ def test_edge_cases_empty_and_culled():
     o1 = oracle.forward_ps1(one, c, "obb")
     assert o1["num_rendered"] >= 1 and o1["radii"][0] > 0
     assert o1["color"].max() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# size-independent properties of the restatement itself (no goldens needed): they hold for the reference by construction
+# ---------------------------------------------------------------------------------------------------------------
+def test_property_mmfr_levels_of_one_model_add_up_to_the_full_image():
+    """The four MMFR level calls partition the image: plain tiles belong to one level, blending tiles are shared by a
+    pair whose smoothstep weights sum to one, skipped tiles are zero — so the SAME model at all levels reproduces PS=1."""
+    s = synth.make_scene_cube(2500, 13)
+    c = synth.look_at_camera(240, 160, 70.0, (0.3, 0.2, -3.5))
+    total = sum(oracle.forward_mmfr(s, c, l, (0.4, 0.55))["color"] for l in range(4))
+    full = oracle.forward_ps1(s, c, "obb")["color"]
+    assert np.abs(total - full).max() <= 1e-6
+
+
+def test_property_training_family_shares_image_lists_and_state():
+    """SUM / MAX / LWMC differ only in their statistics: same image bits, same lists, same final_T / n_contrib; LWMC hands
+    out exactly the loss of every inside pixel; MAX's contribution is a maximum of alpha*T <= 0.99 and never exceeds SUM's."""
+    s = synth.make_scene_cube(3000, 17)
+    c = synth.look_at_camera(176, 112, 70.0, (0.3, 0.2, -3.5))
+    lm = np.random.default_rng(3).random((112, 176)).astype(np.float32)
+    a = oracle.forward_ps1(s, c, "sum")
+    b = oracle.forward_ps1(s, c, "max")
+    d = oracle.forward_ps1(s, c, "lwmc", loss_map=lm)
+    for o in (b, d):
+        assert np.array_equal(o["color"], a["color"]) and np.array_equal(o["point_list"], a["point_list"])
+        assert np.array_equal(o["n_contrib"], a["n_contrib"]) and np.array_equal(o["final_T"], a["final_T"])
+    assert np.array_equal(d["gaussians_count"], a["gaussians_count"])
+    assert abs(float(d["contributions"].sum()) - float(lm.sum())) <= 1e-4 * float(lm.sum())
+    assert b["contributions"].max() <= 0.99 and np.all(b["contributions"] <= a["contributions"] + 1e-6)
+    assert np.all((b["contributions"] > 0) == (a["contributions"] > 0))
+    # MAX counts (pixel, Gaussian) pairs inside the falloff cut: at least one per contributing Gaussian
+    assert np.all(b["gaussians_count"][a["contributions"] > 0] >= 1)
+
+
+def test_property_smfr_equals_fov_when_levels_carry_one_model_and_no_tile_blends():
+    """With identical opacity / dc on every level the two foveated variants differ only inside blending tiles (the shared-
+    model kernel's single alpha test) and in the order the SH terms are summed (dc first vs dc last: one ulp of colour);
+    where no tile blends, lists are equal and images agree to that ulp.  alpha = 0 pooling -> level 0 everywhere -> no
+    blending tile."""
+    s = synth.add_foveation(synth.make_scene_cube(2500, 19))
+    s["opacities4"] = np.repeat(s["opacity"], 4, axis=1).astype(np.float32)
+    s["shs_dcs"] = np.repeat(s["shs"][:, 0:1, :], 4, axis=1).astype(np.float32)
+    c = synth.look_at_camera(240, 160, 70.0, (0.3, 0.2, -3.5))
+    f = oracle.forward_fov(s, c, (0.5, 0.5), alpha=0.0)
+    n = oracle.forward_smfr(s, c, (0.5, 0.5), alpha=0.0)
+    assert f["tile_blend"].sum() == 0
+    assert f["num_rendered"] == n["num_rendered"] and np.array_equal(f["point_list"], n["point_list"])
+    assert np.abs(f["color"] - n["color"]).max() <= 1e-6
