@@ -1,5 +1,6 @@
 // fovgs_api.cu — the extern "C" surface declared in include/fovgs.h (argument checking, workspace carving,
 // launch orchestration).  No torch types, no allocation, no hidden state.
+#include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 #include "fovgs_internal.cuh"
@@ -16,6 +17,16 @@ static int fail_cuda(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s", where, cudaGetErrorString(e));
     return FOVGS_ERR_CUDA;
 }
+
+namespace fovgs {
+// message setter for the entry points that live in other translation units (fovgs_step.cu)
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace fovgs
 
 extern "C" {
 

@@ -175,6 +175,23 @@ class Ps1BwdArgs(C.Structure):
     ]
 
 
+class AdamGroup(C.Structure):
+    _fields_ = [
+        ("param", _f),
+        ("grad", _f),
+        ("exp_avg", _f),
+        ("exp_avg_sq", _f),
+        ("n", C.c_int64),
+        ("step", C.c_int64),
+        ("lr", C.c_double),
+        ("beta1", C.c_double),
+        ("beta2", C.c_double),
+        ("eps", C.c_double),
+    ]
+
+
+ADAM_MAX_GROUPS = 8
+
 # every symbol include/fovgs.h declares (tests/test_abi.py checks this list against the header)
 EXPORTS = (
     "fovgs_workspace_bytes",
@@ -187,6 +204,9 @@ EXPORTS = (
     "fovgs_mark_visible",
     "fovgs_knn_workspace_bytes",
     "fovgs_knn_mean_dist2",
+    "fovgs_activate_forward",
+    "fovgs_activate_backward",
+    "fovgs_adam_step",
     "fovgs_read_stats_async",
     "fovgs_fov_tile_tables",
     "fovgs_ps1_geometry",
@@ -230,6 +250,12 @@ def lib():
     L.fovgs_knn_workspace_bytes.argtypes = [C.c_int32]
     L.fovgs_knn_mean_dist2.restype = C.c_int
     L.fovgs_knn_mean_dist2.argtypes = [C.c_int32, _f, _f, _f, C.c_size_t, C.c_void_p]
+    L.fovgs_activate_forward.argtypes = [C.c_int32, _f, _f, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_activate_forward.restype = C.c_int
+    L.fovgs_activate_backward.argtypes = [C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_activate_backward.restype = C.c_int
+    L.fovgs_adam_step.argtypes = [C.POINTER(AdamGroup), C.c_int32, C.c_void_p]
+    L.fovgs_adam_step.restype = C.c_int
     L.fovgs_read_stats_async.argtypes = [_f, _f, C.c_void_p]
     L.fovgs_fov_tile_tables.argtypes = [_f, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_ps1_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]

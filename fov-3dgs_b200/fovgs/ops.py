@@ -716,3 +716,50 @@ def profile_read_all():
         check(lib().fovgs_profile_read_frame(k, buf, 6), "fovgs_profile_read_frame")
         out.append(dict(zip(STAGE_NAMES, [float(x) for x in buf])))
     return out
+
+
+# ---------------------------------------------------------------- training-step elementwise work
+class _Activate(torch.autograd.Function):
+    """exp / normalize / sigmoid of the raw scaling, rotation and opacity parameters in one pass each way
+    (fov3dgs/scene/gaussian_model.py:40-60,200-237)."""
+
+    @staticmethod
+    def forward(ctx, raw_scale, raw_rot, raw_opacity):
+        device = raw_scale.device
+        P = raw_scale.size(0)
+        rs, rr, ro = _prep(raw_scale, "scaling", device), _prep(raw_rot, "rotation", device), _prep(raw_opacity, "opacity", device)
+        scale, rot, opac = torch.empty_like(rs), torch.empty_like(rr), torch.empty_like(ro)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib().fovgs_activate_forward(P, rs.data_ptr(), rr.data_ptr(), ro.data_ptr(), scale.data_ptr(), rot.data_ptr(),
+                                           opac.data_ptr(), stream), "fovgs_activate_forward")
+        ctx.save_for_backward(rr, scale, opac)
+        return scale, rot, opac
+
+    @staticmethod
+    def backward(ctx, d_scale, d_rot, d_opac):
+        rr, scale, opac = ctx.saved_tensors
+        device = rr.device
+        P = rr.size(0)
+        need = ctx.needs_input_grad
+        ds = _prep(d_scale, "d_scale", device) if need[0] else None
+        dr = _prep(d_rot, "d_rot", device) if need[1] else None
+        do = _prep(d_opac, "d_opacity", device) if need[2] else None
+        g_s = torch.empty_like(scale) if need[0] else None
+        g_r = torch.empty_like(rr) if need[1] else None
+        g_o = torch.empty_like(opac) if need[2] else None
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib().fovgs_activate_backward(P, rr.data_ptr(), scale.data_ptr(), opac.data_ptr(), _ptr(ds), _ptr(dr), _ptr(do),
+                                            _ptr(g_s), _ptr(g_r), _ptr(g_o), stream), "fovgs_activate_backward")
+        return g_s, g_r, g_o
+
+
+def activate(raw_scale, raw_rot, raw_opacity):
+    """(get_scaling, get_rotation, get_opacity) of GaussianModel from (_scaling [P,3], _rotation [P,4], _opacity [P,1]),
+    differentiable; one launch forward, one backward."""
+    if raw_scale.dim() != 2 or raw_scale.size(1) != 3 or raw_rot.dim() != 2 or raw_rot.size(1) != 4:
+        raise RuntimeError("scaling must have dimensions (num_points, 3) and rotation (num_points, 4)")
+    if raw_rot.size(0) != raw_scale.size(0) or raw_opacity.numel() != raw_scale.size(0):
+        raise RuntimeError("scaling, rotation and opacity must describe the same number of points")
+    if raw_scale.size(0) == 0:
+        return torch.empty_like(raw_scale), torch.empty_like(raw_rot), torch.empty_like(raw_opacity)
+    return _Activate.apply(raw_scale, raw_rot, raw_opacity)

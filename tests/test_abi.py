@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in _header_symbols():
         assert hasattr(L, s), f"libfovgs.so does not export {s}"
     assert sorted(_lib.EXPORTS) == _header_symbols()
-    assert L.fovgs_version() == 101
+    assert L.fovgs_version() == 102
 
 
 def test_workspace_bytes_is_monotone_and_mode_dependent():
@@ -68,3 +68,17 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfovgs.so")
     with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback|not found"):
         _lib.lib()
+
+
+def test_step_entry_points_validate_before_any_cuda_call():
+    from fovgs import _lib
+    L = _lib.lib()
+    g = _lib.AdamGroup()
+    g.n, g.step = 4, 0                                                    # step must be >= 1, pointers null
+    assert L.fovgs_adam_step((_lib.AdamGroup * 1)(g), 1, None) == -1
+    assert b"group 0" in L.fovgs_last_error()
+    assert L.fovgs_adam_step(None, 9, None) == -1
+    assert L.fovgs_adam_step(None, 0, None) == 0
+    assert L.fovgs_activate_forward(0, None, None, None, None, None, None, None) == 0
+    assert L.fovgs_activate_forward(4, None, None, None, 16, None, None, None) == -1    # output without its input
+    assert L.fovgs_activate_backward(-1, None, None, None, None, None, None, None, None, None, None) == -1
