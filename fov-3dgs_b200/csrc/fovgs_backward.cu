@@ -259,7 +259,7 @@ __device__ __forceinline__ void bwd_preprocess_one(const CamParams& cam, const W
                                                    const int idx, const float* sh, float* dsh) {
     const float* v = cam.view;
     const float* proj = cam.proj;
-    const float3 mean = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    const float3 mean = make_float3(a.means3D[3 * (size_t)idx], a.means3D[3 * (size_t)idx + 1], a.means3D[3 * (size_t)idx + 2]);
 
     // ---------------- computeCov2DCUDA (backward.cu:144-274) ----------------
     const float* cov3D = a.cov3D_precomp ? a.cov3D_precomp + 6 * (size_t)idx : ws.cov3D + 6 * (size_t)idx;

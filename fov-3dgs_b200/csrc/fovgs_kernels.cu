@@ -250,7 +250,7 @@ __device__ __forceinline__ void load_cam(CamParams& dst_smem, const FrameHeader*
 __global__ void k_mark_visible(int P, const float* __restrict__ pts, const float* __restrict__ view, uint8_t* __restrict__ present) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
-    const float z = xform_row(view, 2, pts[3 * idx], pts[3 * idx + 1], pts[3 * idx + 2]);
+    const float z = xform_row(view, 2, pts[3 * (size_t)idx], pts[3 * (size_t)idx + 1], pts[3 * (size_t)idx + 2]);
     present[idx] = z > 0.2f ? 1 : 0;
 }
 
@@ -262,17 +262,17 @@ __global__ void k_export_geometry(Workspace ws, int P, int mode, const int* __re
     const int R = rec_size(mode);
     const float4* rec = ws.rec + (size_t)R * idx;
     const float4 r0 = rec[0], r1 = rec[1];
-    if (means2D) { means2D[2 * idx] = r0.x; means2D[2 * idx + 1] = r0.y; }
+    if (means2D) { means2D[2 * (size_t)idx] = r0.x; means2D[2 * (size_t)idx + 1] = r0.y; }
     if (depths) depths[idx] = r1.z;
-    if (conic) { conic[3 * idx] = r0.z; conic[3 * idx + 1] = r0.w; conic[3 * idx + 2] = r1.x; }
-    if (cov3D && mode == MODE_SUM) for (int k = 0; k < 6; k++) cov3D[6 * idx + k] = ws.cov3D[6 * (size_t)idx + k];
-    if (rgb && !is_foveated(mode)) { const float4 c = rec[2]; rgb[3 * idx] = c.x; rgb[3 * idx + 1] = c.y; rgb[3 * idx + 2] = c.z; }
+    if (conic) { conic[3 * (size_t)idx] = r0.z; conic[3 * (size_t)idx + 1] = r0.w; conic[3 * (size_t)idx + 2] = r1.x; }
+    if (cov3D && mode == MODE_SUM) for (int k = 0; k < 6; k++) cov3D[6 * (size_t)idx + k] = ws.cov3D[6 * (size_t)idx + k];
+    if (rgb && !is_foveated(mode)) { const float4 c = rec[2]; rgb[3 * (size_t)idx] = c.x; rgb[3 * (size_t)idx + 1] = c.y; rgb[3 * (size_t)idx + 2] = c.z; }
     if (level_colors && mode == MODE_FOV)
         for (int l = 0; l < FOV_LEVELS; l++) {
             const float4 c = rec[2 + l];
-            level_colors[(idx * 4 + l) * 3 + 0] = c.y;
-            level_colors[(idx * 4 + l) * 3 + 1] = c.z;
-            level_colors[(idx * 4 + l) * 3 + 2] = c.w;
+            level_colors[((size_t)idx * 4 + l) * 3 + 0] = c.y;
+            level_colors[((size_t)idx * 4 + l) * 3 + 1] = c.z;
+            level_colors[((size_t)idx * 4 + l) * 3 + 2] = c.w;
         }
 }
 

@@ -20,7 +20,7 @@ void set_error(const char* fmt, ...);
 __global__ void __launch_bounds__(256) k_activate_fwd(int P, const float* __restrict__ raw_scale, const float* __restrict__ raw_rot,
                                                       const float* __restrict__ raw_opacity, float* __restrict__ scale,
                                                       float* __restrict__ rot, float* __restrict__ opacity) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)P; i += (size_t)gridDim.x * blockDim.x) {
         if (scale) {
             scale[3 * i + 0] = expf(raw_scale[3 * i + 0]);
             scale[3 * i + 1] = expf(raw_scale[3 * i + 1]);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_activate_bwd(int P, const float* __rest
                                                       const float* __restrict__ d_rot, const float* __restrict__ d_opacity,
                                                       float* __restrict__ d_raw_scale, float* __restrict__ d_raw_rot,
                                                       float* __restrict__ d_raw_opacity) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)P; i += (size_t)gridDim.x * blockDim.x) {
         if (d_raw_scale) {
             d_raw_scale[3 * i + 0] = __fmul_rn(d_scale[3 * i + 0], scale[3 * i + 0]);
             d_raw_scale[3 * i + 1] = __fmul_rn(d_scale[3 * i + 1], scale[3 * i + 1]);
