@@ -4,7 +4,7 @@
 pair around the rasterizer call alone and followed by torch.cuda.synchronize(); fps_view = 5 / (sum of the 5 times);
 mean over views, then mean over gazes.  Synthetic bench workload (6 M Gaussians, 1920x1080, 30 ring cameras).
 
-  python tools/fps_protocol.py [--views 30] [--impl ours|reference|both]
+  python tools/fps_protocol.py [--views 30] [--impl ours|reference|both] [--size big|ref]
 """
 import argparse, json, os, sys
 import numpy as np, torch
@@ -36,13 +36,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--views", type=int, default=30)
     ap.add_argument("--impl", default="both")
+    ap.add_argument("--size", default="big", help="big = bench workload; ref = 1.16 M Gaussians at 1237x822 (the published 702 FPS case)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    wl = bench.Workload("big")
+    wl = bench.Workload(a.size)
     sc = bench.to_dev(wl.scene, dev); bg = torch.zeros(3, device=dev)
     cams = [bench.to_dev(c, dev) for c in wl.cams[: a.views]]
     gazes = [torch.tensor([g[0], g[1]]).float().cuda() for g in wl.gazes]
-    out = {}
+    out = {"workload": wl.name}
     if a.impl in ("ours", "both"):
         import diff_gaussian_rasterization_fov_pcheck_obb as pkg
 
