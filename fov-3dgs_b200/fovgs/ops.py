@@ -136,28 +136,30 @@ def _new_workspace(device, mode, P, W, H, cap):
         raise RuntimeError("fovgs_workspace_bytes rejected the frame configuration")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
     stats = torch.zeros(16, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(16, dtype=torch.int32)
-    return {"ws": ws, "cap": cap, "bytes": nbytes, "stats": stats, "pending": False}
+    # `stats_np` aliases the (pinned) host tensor: reading 16 ints through it costs ~1 us, indexing the tensor ~3 us each
+    return {"ws": ws, "cap": cap, "bytes": nbytes, "stats": stats, "stats_np": stats.numpy(), "stats_ptr": stats.data_ptr(),
+            "ws_ptr": ws.data_ptr(), "pending": False}
 
 
 _pool = _Pool()
 
 
 def _read_stats(item, stream):
-    check(lib().fovgs_read_stats_async(item["ws"].data_ptr(), item["stats"].data_ptr(), stream), "fovgs_read_stats_async")
+    check(lib().fovgs_read_stats_async(item["ws_ptr"], item["stats_ptr"], stream), "fovgs_read_stats_async")
 
 
 def _stats_dict(item):
-    s = item["stats"]
+    s = item["stats_np"].tolist()
     return {
-        "num_rendered": int(s[0]) & 0xFFFFFFFF,
-        "overflow": int(s[1]),
-        "num_visible": int(s[2]) & 0xFFFFFFFF,
-        "num_blend_tiles": int(s[3]) & 0xFFFFFFFF,
-        "max_tile_instances": int(s[4]) & 0xFFFFFFFF,
-        "blend_consumed": int(s[5]) & 0xFFFFFFFF,
-        "blend_block_pairs": int(s[6]) & 0xFFFFFFFF,
-        "candidates": int(s[7]) & 0xFFFFFFFF,
-        "prefiltered_violations": int(s[8]) & 0xFFFFFFFF,
+        "num_rendered": s[0] & 0xFFFFFFFF,
+        "overflow": s[1],
+        "num_visible": s[2] & 0xFFFFFFFF,
+        "num_blend_tiles": s[3] & 0xFFFFFFFF,
+        "max_tile_instances": s[4] & 0xFFFFFFFF,
+        "blend_consumed": s[5] & 0xFFFFFFFF,
+        "blend_block_pairs": s[6] & 0xFFFFFFFF,
+        "candidates": s[7] & 0xFFFFFFFF,
+        "prefiltered_violations": s[8] & 0xFFFFFFFF,
     }
 
 

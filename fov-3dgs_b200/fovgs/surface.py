@@ -43,8 +43,30 @@ def _check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp):
         raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
 
 
+_EMPTY = torch.Tensor([])
+
+
 def _empty_if_none(t):
-    return torch.Tensor([]) if t is None else t
+    # the reference builds a fresh torch.Tensor([]) per missing argument (~2 us each); one shared, never-written instance does
+    return _EMPTY if t is None else t
+
+
+class _NoGradCtx:
+    """Stands in for the autograd context while gradients are disabled (render_compose_gazes_fps*.py, render.py and prune.py
+    run under torch.no_grad()): Function.apply then only adds per-argument bookkeeping (~25 us per frame) to a forward whose
+    outputs carry no graph either way."""
+
+    def mark_non_differentiable(self, *tensors):
+        pass
+
+    def save_for_backward(self, *tensors):
+        pass
+
+
+def _apply(fn, *args):
+    if not torch.is_grad_enabled():
+        return fn.forward(_NoGradCtx(), *args)
+    return fn.apply(*args)
 
 
 def _mark_visible(raster_settings, positions):
@@ -97,7 +119,7 @@ class _RasterizeGaussiansFov(torch.autograd.Function):
 
 def _fov_rasterize_gaussians(means3D, means2D, shs_rest, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                              raster_settings, shs_dcs, highest_levels, gazeArray, alpha: float, blending: bool):
-    return _RasterizeGaussiansFov.apply(means3D, means2D, shs_rest, colors_precomp, opacities, scales, rotations,
+    return _apply(_RasterizeGaussiansFov, means3D, means2D, shs_rest, colors_precomp, opacities, scales, rotations,
                                         cov3Ds_precomp, raster_settings, shs_dcs, highest_levels, gazeArray, alpha,
                                         blending)
 
@@ -174,7 +196,7 @@ class _RasterizeGaussiansSmfr(torch.autograd.Function):
 
 def _smfr_rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                               raster_settings, highest_levels, gazeArray, alpha: float, blending: bool):
-    return _RasterizeGaussiansSmfr.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+    return _apply(_RasterizeGaussiansSmfr, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                          raster_settings, highest_levels, gazeArray, alpha, blending)
 
 
@@ -250,7 +272,7 @@ class _RasterizeGaussiansMmfr(torch.autograd.Function):
 
 def _mmfr_rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                               raster_settings, cur_level, gazeArray, alpha: float, blending: bool):
-    return _RasterizeGaussiansMmfr.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+    return _apply(_RasterizeGaussiansMmfr, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                          raster_settings, cur_level, gazeArray, alpha, blending)
 
 
@@ -371,7 +393,7 @@ def _make_ps1_api(mode: int):
     if mode == ops.MODE_LWMC:
         def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                 raster_settings, loss_map):
-            return Fn.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+            return _apply(Fn, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                             raster_settings, loss_map)
 
         class GaussianRasterizer(nn.Module):
@@ -399,7 +421,7 @@ def _make_ps1_api(mode: int):
 
     def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                             raster_settings):
-        return Fn.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+        return _apply(Fn, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings)
 
     class GaussianRasterizer(nn.Module):
