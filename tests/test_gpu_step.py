@@ -150,3 +150,58 @@ def test_adam_survives_the_reference_optimizer_surgery():
     step_all(3)
     for gm, gr in zip(o_mine.param_groups, o_ref.param_groups):
         assert torch.allclose(gm["params"][0], gr["params"][0], rtol=1e-6, atol=1e-6)
+
+
+def test_fine_tuning_loop_reduces_the_loss_like_the_torch_side():
+    """eff_finetune.py:95-147 in miniature: activations -> pcheck_obb_sum rasterizer -> L1 -> backward -> Adam, 40 iterations
+    from a perturbed model towards the render of the unperturbed one.  Arm A uses fovgs.ops.activate + fovgs.optim.Adam,
+    arm B torch.exp / F.normalize / torch.sigmoid + torch.optim.Adam around the same rasterizer.  Both must reduce the loss,
+    and end within 5 % of each other (parameter-wise equality is not a property of Adam with eps = 1e-15: an update is
+    lr * sign(g) for the first step, and the rasterizer's atomics make g's last bits run-dependent)."""
+    import diff_gaussian_rasterization_pcheck_obb_sum as pkg
+    from fovgs import synth
+    scene = synth.make_scene_cube(3000, 3)
+    cam = synth.look_at_camera(160, 128, 60.0, (0.0, 0.0, -4.0))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    bg = torch.zeros(3, device="cuda")
+    rs = pkg.GaussianRasterizationSettings(cam["image_height"], cam["image_width"], cam["tanfovx"], cam["tanfovy"], bg, 1.0,
+                                           t(cam["viewmatrix"]), t(cam["projmatrix"]), 3, t(cam["campos"]), False, False)
+    rast = pkg.GaussianRasterizer(raster_settings=rs)
+    op = np.clip(scene["opacity"].astype(np.float64), 1e-4, 1 - 1e-4)
+    raw0 = {"xyz": scene["means3D"], "f_dc": scene["shs"][:, :1], "f_rest": scene["shs"][:, 1:],
+            "opacity": np.log(op / (1 - op)).astype(np.float32), "scaling": np.log(scene["scales"]), "rotation": scene["rotations"]}
+    lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "f_rest": 2.5e-3 / 20, "opacity": 0.05, "scaling": 5e-3, "rotation": 1e-3}
+
+    def render(p, ours):
+        if ours:
+            s, q, o = ops.activate(p["scaling"], p["rotation"], p["opacity"])
+        else:
+            s, q, o = torch.exp(p["scaling"]), torch.nn.functional.normalize(p["rotation"]), torch.sigmoid(p["opacity"])
+        shs = torch.cat((p["f_dc"], p["f_rest"]), dim=1)
+        return rast(means3D=p["xyz"], means2D=torch.zeros_like(p["xyz"], requires_grad=True), shs=shs, colors_precomp=None,
+                    opacities=o, scales=s, rotations=q, cov3D_precomp=None)[0]
+
+    with torch.no_grad():
+        target = render({k: t(v) for k, v in raw0.items()}, True)
+    r = np.random.default_rng(4)
+    start = dict(raw0)
+    start["f_dc"] = (raw0["f_dc"] + r.normal(0, 0.3, raw0["f_dc"].shape)).astype(np.float32)
+    start["opacity"] = (raw0["opacity"] + r.normal(0, 1.0, raw0["opacity"].shape)).astype(np.float32)
+
+    def run(ours):
+        p = {k: torch.nn.Parameter(t(v)) for k, v in start.items()}
+        groups = [{"params": [p[k]], "lr": lrs[k], "name": k} for k in lrs]
+        opt = (optim.Adam if ours else torch.optim.Adam)(groups, lr=0.0, eps=1e-15)
+        losses = []
+        for _ in range(40):
+            loss = (render(p, ours) - target).abs().mean()
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            losses.append(float(loss))
+        return losses
+
+    a, b = run(True), run(False)
+    assert abs(a[0] - b[0]) <= 1e-5 * a[0]                             # same start; activations agree to an ulp
+    assert a[-1] < 0.7 * a[0] and b[-1] < 0.7 * b[0], (a[0], a[-1], b[0], b[-1])
+    assert abs(a[-1] - b[-1]) <= 0.05 * b[-1], (a[-1], b[-1])

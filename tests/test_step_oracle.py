@@ -79,3 +79,46 @@ def test_fused_adam_host_behaviour():
     o2 = optim.Adam([{"params": [p], "lr": 0.1, "name": "xyz"}], lr=0.0, eps=1e-15)
     assert set(o2.state_dict()["param_groups"][0]) >= {"lr", "betas", "eps", "name", "params"}
     o2.load_state_dict(ref.state_dict())                               # interchangeable state dicts
+
+
+def test_oracle_fine_tuning_loop_descends():
+    """The CPU restatements chained as eff_finetune.py:95-147 chains the real thing — activations, pcheck_obb_sum forward, L1,
+    backward, activation backward, Adam — from a perturbed model towards the render of the unperturbed one: the loss must fall
+    (a sign error anywhere in the gradient chain makes it rise).  The GPU twin is tests/test_gpu_step.py."""
+    import oracle
+    from fovgs import synth
+    scene = synth.make_scene_cube(1500, 3)
+    cam = synth.look_at_camera(96, 80, 60.0, (0.0, 0.0, -4.0))
+    op = np.clip(scene["opacity"].astype(np.float64), 1e-4, 1 - 1e-4)
+    raw0 = {"xyz": scene["means3D"].copy(), "f_dc": scene["shs"][:, :1].copy(), "f_rest": scene["shs"][:, 1:].copy(),
+            "opacity": np.log(op / (1 - op)).astype(np.float32), "scaling": np.log(scene["scales"]),
+            "rotation": scene["rotations"].copy()}
+    lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "f_rest": 2.5e-3 / 20, "opacity": 0.05, "scaling": 5e-3, "rotation": 1e-3}
+
+    def model(p):
+        s, q, o = so.activate(p["scaling"], p["rotation"], p["opacity"])
+        return {"means3D": p["xyz"], "scales": s, "rotations": q, "opacity": o, "sh_degree": 3,
+                "shs": np.ascontiguousarray(np.concatenate([p["f_dc"], p["f_rest"]], 1))}
+
+    target = oracle.forward_ps1(model(raw0), cam, "sum")["color"]
+    r = np.random.default_rng(4)
+    p = {k: v.copy() for k, v in raw0.items()}
+    p["f_dc"] = (raw0["f_dc"] + r.normal(0, 0.3, raw0["f_dc"].shape)).astype(np.float32)
+    p["opacity"] = (raw0["opacity"] + r.normal(0, 1.0, raw0["opacity"].shape)).astype(np.float32)
+    m = {k: np.zeros_like(x) for k, x in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    losses = []
+    for it in range(1, 16):
+        sc = model(p)
+        o = oracle.forward_ps1(sc, cam, "sum")
+        d = o["color"] - target
+        losses.append(float(np.abs(d).mean()))
+        g = oracle.backward_ps1(sc, cam, o, (np.sign(d) / d.size).astype(np.float32))
+        gs, gq, go = so.activate_backward(p["rotation"], sc["scales"], sc["opacity"], g["dL_dscales"], g["dL_drotations"],
+                                          g["dL_dopacity"].reshape(-1, 1))
+        grads = {"xyz": g["dL_dmeans3D"], "f_dc": g["dL_dsh"][:, :1], "f_rest": g["dL_dsh"][:, 1:], "opacity": go,
+                 "scaling": gs, "rotation": gq}
+        for k in p:
+            so.adam_step(p[k], np.ascontiguousarray(grads[k], dtype=np.float32), m[k], v[k], it, lrs[k], eps=1e-15)
+    assert losses[-1] < 0.6 * losses[0], losses
+    assert all(b < a * 1.02 for a, b in zip(losses, losses[1:])), losses
