@@ -198,7 +198,7 @@ def test_fine_tuning_loop_reduces_the_loss_like_the_torch_side():
             loss.backward()
             opt.step()
             opt.zero_grad(set_to_none=True)
-            losses.append(float(loss))
+            losses.append(float(loss.detach()))
         return losses
 
     a, b = run(True), run(False)
