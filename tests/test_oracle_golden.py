@@ -229,3 +229,76 @@ def test_property_smfr_equals_fov_when_levels_carry_one_model_and_no_tile_blends
     assert f["tile_blend"].sum() == 0
     assert f["num_rendered"] == n["num_rendered"] and np.array_equal(f["point_list"], n["point_list"])
     assert np.abs(f["color"] - n["color"]).max() <= 1e-6
+
+
+def test_property_background_enters_linearly_through_the_final_transmittance():
+    """out = C + T_final * bg (SUM/CR/forward.cu:421-429): rendering with a background equals the black-background image plus the
+    stored final_T times the colour, per channel; and final_T lies in (0, 1]."""
+    s = synth.make_scene_cube(2500, 23)
+    c = synth.look_at_camera(208, 144, 70.0, (0.2, -0.1, -3.5))
+    bg = (0.25, 0.5, 0.875)
+    a = oracle.forward_ps1(s, c, "sum")
+    b = oracle.forward_ps1(s, c, "sum", bg=bg)
+    T = a["final_T"].reshape(144, 208)
+    assert T.min() > 0.0 and T.max() <= 1.0
+    assert np.array_equal(a["final_T"], b["final_T"]) and np.array_equal(a["point_list"], b["point_list"])
+    for ch in range(3):
+        assert np.abs(b["color"][ch] - (a["color"][ch] + T * np.float32(bg[ch]))).max() <= 2e-7
+    f0 = oracle.forward_fov(synth.add_foveation(s), c, (0.5, 0.5))
+    f1 = oracle.forward_fov(synth.add_foveation(s), c, (0.5, 0.5), bg=(1.0, 1.0, 1.0))
+    d = f1["color"] - f0["color"]                                     # = the (blended) final transmittance, same in every channel
+    assert d.min() >= 0.0 and d.max() <= 1.0 + 1e-6 and np.abs(d[0] - d[1]).max() <= 2e-7 and np.abs(d[0] - d[2]).max() <= 2e-7
+
+
+def test_property_tile_lists_are_sorted_by_depth_then_id_and_cover_num_rendered():
+    """ranges partition [0, num_rendered) in tile order; inside a tile the ids are ordered by (depth bits, id) — the unique order
+    a stable radix sort of (tile << 32 | depth_bits) over id-ordered emission produces (FOV/CR/rasterizer_impl.cu:423-486,843-854)."""
+    s = synth.add_foveation(synth.make_scene_cube(3000, 29))
+    c = synth.look_at_camera(240, 160, 70.0, (0.3, 0.2, -3.5))
+    for o in (oracle.forward_ps1(s, c, "obb"), oracle.forward_fov(s, c, (0.3, 0.7))):
+        r = o["ranges"].astype(np.int64)
+        nz = r[r[:, 1] > r[:, 0]]
+        assert nz[0, 0] == 0 and nz[-1, 1] == o["num_rendered"] and np.array_equal(nz[1:, 0], nz[:-1, 1])
+        depth_bits = np.ascontiguousarray(o["depths"], np.float32).view(np.uint32).astype(np.int64)
+        for a, b in nz:
+            ids = o["point_list"][a:b].astype(np.int64)
+            key = (depth_bits[ids] << 32) | ids
+            assert np.all(np.diff(key) > 0)
+
+
+def test_property_image_does_not_depend_on_the_storage_order_of_the_gaussians():
+    """Compositing order is by depth (ties by id; random depths have none): permuting the model's rows permutes radii and
+    relabels the lists, and leaves every pixel bit-identical."""
+    s = synth.add_foveation(synth.make_scene_cube(2500, 31))
+    c = synth.look_at_camera(208, 144, 70.0, (0.2, -0.1, -3.5))
+    # a few of 2500 random fp32 depths collide (birthday bound); drop them so that no tie exists
+    bits = np.ascontiguousarray(oracle.forward_fov(s, c, (0.6, 0.4))["depths"]).view(np.uint32)
+    _, first, counts = np.unique(bits, return_index=True, return_counts=True)
+    keep = np.sort(first[counts == 1])
+    n = len(keep)
+    assert n > 2400
+    s = {k: (np.ascontiguousarray(v[keep]) if isinstance(v, np.ndarray) and v.shape[:1] == (2500,) else v) for k, v in s.items()}
+    perm = np.random.default_rng(5).permutation(n)
+    sp = {k: (np.ascontiguousarray(v[perm]) if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in s.items()}
+    a, b = oracle.forward_fov(s, c, (0.6, 0.4)), oracle.forward_fov(sp, c, (0.6, 0.4))
+    assert a["num_rendered"] == b["num_rendered"] and np.array_equal(a["radii"][perm], b["radii"])
+    assert np.array_equal(perm[b["point_list"]], a["point_list"])
+    assert np.array_equal(a["color"], b["color"])
+    a, b = oracle.forward_ps1(s, c, "sum"), oracle.forward_ps1(sp, c, "sum")
+    assert np.array_equal(a["color"], b["color"]) and np.array_equal(a["gaussians_count"][perm], b["gaussians_count"])
+
+
+def test_property_culled_gaussians_change_nothing():
+    """Gaussians behind the near plane (z_view <= 0.2, auxiliary.h:271-296) or far outside the frustum get radius 0, emit no
+    instance, and leave the image of the rest untouched; the oracle is deterministic (two runs, same bits)."""
+    s = synth.make_scene_cube(2000, 37)
+    c = synth.look_at_camera(208, 144, 70.0, (0.0, 0.0, -4.0))
+    extra = synth.make_scene_cube(500, 41)
+    extra["means3D"] = extra["means3D"].copy()
+    extra["means3D"][:250, 2] = -4.0 - np.abs(extra["means3D"][:250, 2]) - 0.5      # behind the camera at z = -4
+    extra["means3D"][250:, 0] += 500.0                                              # far off to the side
+    both = {k: (np.ascontiguousarray(np.concatenate([s[k], extra[k]], 0)) if isinstance(v, np.ndarray) else v) for k, v in s.items()}
+    a, a2, b = oracle.forward_ps1(s, c, "obb"), oracle.forward_ps1(s, c, "obb"), oracle.forward_ps1(both, c, "obb")
+    assert np.array_equal(a["color"], a2["color"]) and np.array_equal(a["point_list"], a2["point_list"])
+    assert np.all(b["radii"][2000:] == 0) and b["num_rendered"] == a["num_rendered"]
+    assert np.array_equal(b["point_list"], a["point_list"]) and np.array_equal(b["color"], a["color"])
