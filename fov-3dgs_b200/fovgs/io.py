@@ -9,6 +9,10 @@
                               feature layout (f_rest is stored channel-major [P,3,15] and transposed to [P,15,3]).
   compose_levels              compose_models.py:39-80: highest_levels [P,1], shs_dcs [P,L,3], opacities [P,L] of the
                               multi-level ("ours") model from the level-0 PLY and the indexed PLYs of levels 1..L-1.
+  save_composed / load_composed   the three tensors compose_models.py:75-80 saves next to the model and
+                              render_compose_gazes_fps.py:85-96 loads: highest_levels.pt [P,1], shs_dcs.pt [P,L,3], opacities.pt
+                              [P,L] (torch.save files, float32)
+  smfr_levels                 gen_naive_FR.py:33-59: the SMFR baseline's highest_levels.pth — nested random subsets of one model
   camera_from_json_entry      one entry of cameras.json (utils/camera_utils.py:62-82) -> the camera dict the rasterizer
   cameras_from_json           settings are built from (scene/cameras.py:17-57, utils/graphics_utils.py:38-71).
 
@@ -187,6 +191,46 @@ def compose_levels(level_models):
     out["opacities4"] = opac
     out["shs_rest"] = np.ascontiguousarray(base["shs"][:, 1:, :])
     return out
+
+
+def save_composed(folder, composed):
+    """Writes highest_levels.pt / shs_dcs.pt / opacities.pt as compose_models.py:75-80 does (CPU float32 torch tensors), so that
+    render_compose_gazes_fps.py:85-96 (`torch.load(...).cuda()`) reads them unchanged."""
+    import torch
+    os.makedirs(folder, exist_ok=True)
+    for name, key in (("highest_levels.pt", "highest_levels"), ("shs_dcs.pt", "shs_dcs"), ("opacities.pt", "opacities4")):
+        torch.save(torch.from_numpy(np.ascontiguousarray(composed[key], dtype=np.float32)), os.path.join(folder, name))
+
+
+def load_composed(folder):
+    """The inverse: {"highest_levels" [P,1], "shs_dcs" [P,L,3], "opacities4" [P,L]} as float32 numpy arrays."""
+    import torch
+    out = {}
+    for name, key in (("highest_levels.pt", "highest_levels"), ("shs_dcs.pt", "shs_dcs"), ("opacities.pt", "opacities4")):
+        t = torch.load(os.path.join(folder, name), map_location="cpu")
+        out[key] = np.ascontiguousarray(t.detach().float().numpy())
+    P = out["shs_dcs"].shape[0]
+    if out["highest_levels"].reshape(-1).shape[0] != P or out["opacities4"].shape != out["shs_dcs"].shape[:2]:
+        raise ValueError(f"{folder}: highest_levels / shs_dcs / opacities do not describe the same model")
+    out["highest_levels"] = out["highest_levels"].reshape(P, 1)
+    return out
+
+
+def smfr_levels(level_sizes, seed=None):
+    """gen_naive_FR.py:33-59.  `level_sizes[0]` = P of the shared model, `level_sizes[i]` = number of Gaussians level i keeps.
+    Level i's subset is the first `level_sizes[i]` entries of level i-1's (randomly permuted) subset, so the subsets nest;
+    returns highest_levels [P] float32 (the reference saves a 1-D tensor as highest_levels.pth)."""
+    P = int(level_sizes[0])
+    rng = np.random.default_rng(seed)
+    current = rng.permutation(P)
+    highest = np.zeros(P, np.float32)
+    for i in range(1, len(level_sizes)):
+        n = int(level_sizes[i])
+        if n > len(current):
+            raise ValueError(f"level {i} keeps {n} Gaussians but level {i - 1} has only {len(current)}")
+        current = current[:n]
+        highest[current] = i
+    return highest
 
 
 def _projection(znear, zfar, fovx, fovy):

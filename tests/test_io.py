@@ -130,3 +130,30 @@ def test_synth_cameras_agree_with_io_camera_math():
     d = io.camera_from_rt(R, T, c["FoVx"], c["FoVy"], 640, 360)
     assert np.allclose(d["viewmatrix"], c["viewmatrix"], atol=1e-6) and np.allclose(d["projmatrix"], c["projmatrix"], atol=1e-5)
     assert np.allclose(d["campos"], c["campos"], atol=1e-5)
+
+
+def test_composed_tensors_round_trip_as_the_reference_saves_them(tmp_path):
+    """compose_models.py:75-80 / render_compose_gazes_fps.py:85-96: three torch.save files next to the model."""
+    import torch
+    from fovgs import synth
+    f = synth.add_foveation(synth.make_scene_cube(300, 2))
+    io.save_composed(str(tmp_path / "composed_4_4"), f)
+    for name, shape in (("highest_levels.pt", (300, 1)), ("shs_dcs.pt", (300, 4, 3)), ("opacities.pt", (300, 4))):
+        t = torch.load(str(tmp_path / "composed_4_4" / name))
+        assert isinstance(t, torch.Tensor) and tuple(t.shape) == shape and t.dtype == torch.float32 and not t.is_cuda
+    g = io.load_composed(str(tmp_path / "composed_4_4"))
+    for k in ("highest_levels", "shs_dcs", "opacities4"):
+        assert np.array_equal(g[k], f[k])
+    torch.save(torch.zeros(299, 1), str(tmp_path / "composed_4_4" / "highest_levels.pt"))
+    with pytest.raises(ValueError):
+        io.load_composed(str(tmp_path / "composed_4_4"))
+
+
+def test_smfr_levels_nest_like_gen_naive_FR():
+    """gen_naive_FR.py:33-59: level i keeps the first n_i entries of level i-1's shuffled subset."""
+    hl = io.smfr_levels([1000, 400, 200, 150], seed=0)
+    assert hl.shape == (1000,) and hl.dtype == np.float32
+    assert [(hl >= i).sum() for i in range(4)] == [1000, 400, 200, 150]
+    assert not np.array_equal(hl, io.smfr_levels([1000, 400, 200, 150], seed=1))
+    with pytest.raises(ValueError):
+        io.smfr_levels([100, 50, 60])
