@@ -1,0 +1,174 @@
+"""CPU: the host-side logic of the torch-facing layer (fovgs/ops.py, fovgs/surface.py) with the C library stubbed out — the
+capacity / overflow protocol, the deferred statistics check, the packed-model cache's state machine and the no-grad call path.
+The kernels behind them are covered by the `-m gpu` tests; nothing here computes an image."""
+import gc
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from fovgs import ops, surface
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+@pytest.fixture
+def stubbed(monkeypatch):
+    """ops with a fake library: workspaces are tiny CPU tensors, `launch` is the test's own function."""
+    fake = types.SimpleNamespace(fovgs_workspace_bytes=lambda *a: 1024, fovgs_read_stats_async=lambda *a: 0)
+    monkeypatch.setattr(ops, "lib", lambda: fake)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(ops, "_pool", ops._Pool())
+    monkeypatch.setattr(ops, "_train_capacity_hint", {})
+    monkeypatch.setattr(ops, "_DEFERRED", False)
+    return ops
+
+
+def test_capacity_rounding_and_environment_override(monkeypatch):
+    assert ops._round_capacity(1) == 1 << 22 and ops._round_capacity((1 << 22) + 1) == 2 << 22
+    assert ops._round_capacity(1 << 40) == 0xFFFFFFF0                       # instance ids and counts travel in 32 bits
+    monkeypatch.delenv("FOVGS_INSTANCE_CAPACITY", raising=False)
+    assert ops._initial_capacity(10) == 1 << 20 and ops._initial_capacity(1 << 20) == 8 << 20
+    monkeypatch.setenv("FOVGS_INSTANCE_CAPACITY", "12345")
+    assert ops._initial_capacity(10) == 12345
+
+
+def test_overflow_reruns_with_a_larger_workspace_and_never_truncates(stubbed):
+    dev = torch.device("cpu")
+    caps = []
+
+    def launch(item, stream):
+        caps.append(item["cap"])
+        need = 5_000_000
+        item["stats_np"][:] = 0
+        item["stats_np"][0] = need
+        item["stats_np"][1] = 1 if item["cap"] < need else 0
+        item["stats_np"][2] = 77
+
+    item, st = stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 1000, 64, 64, fresh_workspace=False)
+    assert len(caps) == 2 and caps[0] == 1 << 20 and caps[1] >= 5_000_000 * 1.25 and caps[1] % (1 << 22) == 0
+    assert st["num_rendered"] == 5_000_000 and st["overflow"] == 0 and st["num_visible"] == 77
+    assert stubbed.last_stats == st
+    # the pooled workspace kept its grown capacity: the next frame runs once
+    caps.clear()
+    stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 1000, 64, 64, fresh_workspace=False)
+    assert caps == [item["cap"]]
+
+
+def test_training_workspace_capacity_only_grows(stubbed):
+    dev = torch.device("cpu")
+    seen = []
+
+    def launch_n(n):
+        def launch(item, stream):
+            seen.append(item["cap"])
+            item["stats_np"][:] = 0
+            item["stats_np"][0] = n
+            item["stats_np"][1] = 1 if item["cap"] < n else 0
+        return launch
+
+    stubbed._run_with_capacity(launch_n(9_000_000), dev, ops.MODE_SUM, 1000, 64, 64, fresh_workspace=True)
+    big = seen[-1]
+    stubbed._run_with_capacity(launch_n(100), dev, ops.MODE_SUM, 1000, 64, 64, fresh_workspace=True)
+    assert seen[-1] == big                                                  # same size again: the allocator's block is reused
+
+
+def test_prefiltered_violation_and_deferred_overflow_raise(stubbed):
+    dev = torch.device("cpu")
+
+    def bad_prefilter(item, stream):
+        item["stats_np"][:] = 0
+        item["stats_np"][8] = 3
+
+    with pytest.raises(RuntimeError, match="Point is filtered although prefiltered is set"):
+        stubbed._run_with_capacity(bad_prefilter, dev, ops.MODE_OBB, 10, 32, 32, fresh_workspace=False)
+
+    stubbed.set_deferred_check(True)
+    try:
+        def overflowing(item, stream):
+            item["stats_np"][:] = 0
+            item["stats_np"][0] = 1 << 30
+            item["stats_np"][1] = 1
+
+        item, st = stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert st is None and item["pending"]                               # not inspected yet
+        with pytest.raises(RuntimeError, match="previous frame overflowed"):
+            stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+    finally:
+        stubbed.set_deferred_check(False)
+
+
+def test_packed_model_cache_state_machine(monkeypatch):
+    packs = []
+
+    def fake_pack(P, M_rest, means3D, shs_rest, shs_dcs, opacities, device):
+        packs.append(P)
+        return torch.zeros(P, 64)
+
+    monkeypatch.setattr(ops, "_pack_rows", fake_pack)
+    monkeypatch.setattr(ops, "_MODEL_CACHE", True)
+    ops.invalidate_model_cache()
+    P = 8
+    model = (torch.zeros(P, 3), torch.zeros(P, 15, 3), torch.zeros(P, 4, 3), torch.zeros(P, 4))
+    dev = torch.device("cpu")
+    assert ops._packed_rows(model, model, P, 15, dev, False) is None and packs == []      # first sighting: un-packed gather
+    rows = ops._packed_rows(model, model, P, 15, dev, False)                              # second: packed once
+    assert rows is not None and packs == [P]
+    assert ops._packed_rows(model, model, P, 15, dev, False) is rows and packs == [P]     # then served from the cache
+    model[3].add_(1.0)                                                                    # in-place update bumps _version
+    assert ops._packed_rows(model, model, P, 15, dev, False) is None
+    assert ops._packed_rows(model, model, P, 15, dev, False) is not None and packs == [P, P]
+    fresh = tuple(t.clone() for t in model)                                               # one-shot tensors never pay
+    assert ops._packed_rows(fresh, fresh, P, 15, dev, False) is None and packs == [P, P]
+    n = len(ops._packed_cache)
+    del model, rows
+    gc.collect()
+    assert len(ops._packed_cache) < n                                                     # entry dies with its tensors
+    ops.set_model_cache(False)
+    try:
+        assert ops._packed_rows(fresh, fresh, P, 15, dev, False) is None
+        assert ops._packed_rows(fresh, fresh, P, 15, dev, False) is None and packs == [P, P]
+    finally:
+        ops.set_model_cache(True)
+        ops.invalidate_model_cache()
+
+
+def test_no_grad_calls_skip_function_apply_and_grad_calls_do_not():
+    calls = []
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, tag):
+            calls.append(type(ctx).__name__)
+            ctx.tag = tag
+            ctx.save_for_backward(x)
+            y = x * 2
+            ctx.mark_non_differentiable(y)
+            return y
+
+        @staticmethod
+        def backward(ctx, g):
+            return None, None
+
+    x = torch.ones(3, requires_grad=True)
+    with torch.no_grad():
+        y = surface._apply(Fn, x, "a")
+    assert calls == ["_NoGradCtx"] and not y.requires_grad and torch.equal(y, torch.full((3,), 2.0))
+    surface._apply(Fn, x, "b")
+    assert len(calls) == 2 and calls[1] != "_NoGradCtx"
+    e = surface._empty_if_none(None)
+    assert e.numel() == 0 and surface._empty_if_none(None) is e and surface._empty_if_none(x) is x
+
+
+def test_stats_dict_reads_unsigned_counters():
+    item = {"stats_np": np.zeros(16, np.int32)}
+    item["stats_np"][0] = -1                                                # 0xFFFFFFFF instances as int32
+    item["stats_np"][2] = 5
+    st = ops._stats_dict(item)
+    assert st["num_rendered"] == 0xFFFFFFFF and st["num_visible"] == 5 and st["overflow"] == 0
