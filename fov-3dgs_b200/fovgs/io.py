@@ -216,6 +216,22 @@ def load_composed(folder):
     return out
 
 
+def load_foveated_model(base_folder, layer_num, max_pooling_size, iteration=55000, max_sh_degree=3):
+    """The model files render_compose_gazes_fps.py:80-90 reads, as the scene dict `forward_fov` takes:
+    `<base>/1_PS1_<L>_<S>/point_cloud/iteration_<it>/point_cloud.ply` (geometry, SH rest) and
+    `<base>/composed_<L>_<S>/{highest_levels,shs_dcs,opacities}.pt`."""
+    ply = os.path.join(base_folder, f"1_PS1_{layer_num}_{max_pooling_size}", "point_cloud", f"iteration_{iteration}", "point_cloud.ply")
+    m = model_from_ply(ply, max_sh_degree)
+    c = load_composed(os.path.join(base_folder, f"composed_{layer_num}_{max_pooling_size}"))
+    P = m["means3D"].shape[0]
+    if c["shs_dcs"].shape[0] != P:
+        raise ValueError(f"composed tensors describe {c['shs_dcs'].shape[0]} Gaussians, {ply} has {P}")
+    out = {"means3D": m["means3D"], "scales": m["scales"], "rotations": m["rotations"], "sh_degree": m["sh_degree"],
+           "shs_rest": np.ascontiguousarray(m["shs"][:, 1:, :]), "opacity": m["opacity"], "shs": m["shs"]}
+    out.update(c)
+    return out
+
+
 def smfr_levels(level_sizes, seed=None):
     """gen_naive_FR.py:33-59.  `level_sizes[0]` = P of the shared model, `level_sizes[i]` = number of Gaussians level i keeps.
     Level i's subset is the first `level_sizes[i]` entries of level i-1's (randomly permuted) subset, so the subsets nest;

@@ -157,3 +157,26 @@ def test_smfr_levels_nest_like_gen_naive_FR():
     assert not np.array_equal(hl, io.smfr_levels([1000, 400, 200, 150], seed=1))
     with pytest.raises(ValueError):
         io.smfr_levels([100, 50, 60])
+
+
+def test_load_foveated_model_reads_the_layout_of_the_fps_script(tmp_path):
+    """render_compose_gazes_fps.py:80-90: <base>/1_PS1_<L>_<S>/point_cloud/iteration_55000/point_cloud.ply + <base>/composed_<L>_<S>/*.pt."""
+    from fovgs import synth
+    sc = synth.make_scene_cube(200, 6)
+    op = np.clip(sc["opacity"].astype(np.float64), 1e-4, 1 - 1e-4)
+    raw = {"xyz": sc["means3D"], "features_dc": sc["shs"][:, :1], "features_rest": sc["shs"][:, 1:],
+           "opacity": np.log(op / (1 - op)).astype(np.float32), "scaling": np.log(sc["scales"]), "rotation": sc["rotations"],
+           "sh_degree": 3}
+    d = tmp_path / "1_PS1_4_4" / "point_cloud" / "iteration_55000"
+    d.mkdir(parents=True)
+    io.write_ply(str(d / "point_cloud.ply"), raw)
+    f = synth.add_foveation(sc)
+    io.save_composed(str(tmp_path / "composed_4_4"), f)
+    m = io.load_foveated_model(str(tmp_path), 4, 4)
+    assert np.array_equal(m["means3D"], sc["means3D"]) and np.array_equal(m["shs_rest"], f["shs_rest"])
+    assert np.allclose(m["scales"], sc["scales"], rtol=1e-6) and np.allclose(m["rotations"], sc["rotations"], atol=1e-6)
+    for k in ("highest_levels", "shs_dcs", "opacities4"):
+        assert np.array_equal(m[k], f[k])
+    io.save_composed(str(tmp_path / "composed_4_4"), synth.add_foveation(synth.make_scene_cube(199, 6)))
+    with pytest.raises(ValueError):
+        io.load_foveated_model(str(tmp_path), 4, 4)

@@ -37,13 +37,25 @@ def main():
     ap.add_argument("--views", type=int, default=30)
     ap.add_argument("--impl", default="both")
     ap.add_argument("--size", default="big", help="big = bench workload; ref = 1.16 M Gaussians at 1237x822 (the published 702 FPS case)")
+    ap.add_argument("--base_folder", help="a trained model instead of the synthetic workload: the folder render_compose_gazes_fps.py "
+                    "takes (1_PS1_<L>_<S>/point_cloud/iteration_55000/point_cloud.ply + composed_<L>_<S>/*.pt)")
+    ap.add_argument("--layer_num", type=int, default=4); ap.add_argument("--max_pooling_size", type=int, default=4)
+    ap.add_argument("--cameras", help="cameras.json of the model (with --base_folder); the test views come first in it "
+                    "(scene/__init__.py:55-61), so --views 25 takes bicycle's 25 test views")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    wl = bench.Workload(a.size)
-    sc = bench.to_dev(wl.scene, dev); bg = torch.zeros(3, device=dev)
-    cams = [bench.to_dev(c, dev) for c in wl.cams[: a.views]]
-    gazes = [torch.tensor([g[0], g[1]]).float().cuda() for g in wl.gazes]
-    out = {"workload": wl.name}
+    if a.base_folder:
+        from fovgs import io, synth
+        scene = io.load_foveated_model(a.base_folder, a.layer_num, a.max_pooling_size)
+        cams_np = io.cameras_from_json(a.cameras)[: a.views]
+        name, gz = f"{os.path.basename(os.path.normpath(a.base_folder))}_{scene['means3D'].shape[0]}g", synth.GAZES_9
+    else:
+        wl = bench.Workload(a.size)
+        scene, cams_np, name, gz = wl.scene, wl.cams[: a.views], wl.name, wl.gazes
+    sc = bench.to_dev(scene, dev); bg = torch.zeros(3, device=dev)
+    cams = [bench.to_dev(c, dev) for c in cams_np]
+    gazes = [torch.tensor([g[0], g[1]]).float().cuda() for g in gz]
+    out = {"workload": name}
     if a.impl in ("ours", "both"):
         import diff_gaussian_rasterization_fov_pcheck_obb as pkg
 
