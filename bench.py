@@ -413,6 +413,16 @@ def roofline(res, wl, steps):
             "stage_ms_mean": mean, "N_mean": N, "V_mean": V, "blend_tile_share": blend_share}
 
 
+def cpu_reference_line(wl, args):
+    """The reference arm when the reference's CUDA extension cannot run: the CPU oracle port on a bounded sample."""
+    cb = cpu_baseline(wl)
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "device": "cpu"}, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,6 +438,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
+        if args.impl == "reference":
+            # no GPU: the reference's CUDA cannot run either; its CPU restatement (the oracle port) is the only arm left
+            if rank == 0:
+                print(json.dumps(cpu_reference_line(Workload(args.size), args)))
+            return 0
         print(json.dumps({"impl": args.impl, "error": "no CUDA device: the product path has no CPU fallback"}))
         return 1
     torch.cuda.set_device(local)
@@ -458,12 +473,7 @@ def main():
         if res is None:
             # reference extension not built here: fall back to the CPU oracle port on rank 0 (bounded sample)
             if rank == 0:
-                cb = cpu_baseline(wl)
-                print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                                  "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
-                                  "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                                  "config": {"workload": wl.name, "device": "cpu"}, "cpu_baseline": cb,
-                                  "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                print(json.dumps(cpu_reference_line(wl, args)))
             return 0
     else:
         res = run_ours(args, wl, rank, world, dev)
