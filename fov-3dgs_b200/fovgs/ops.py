@@ -104,13 +104,14 @@ def _camera(rs, device, keep):
 
 
 class _Pool:
-    """Reusable workspaces for the inference paths, one per (device, mode, P, W, H)."""
+    """Reusable workspaces for the inference paths, one per (device, mode, P, W, H, stream): one workspace is one in-flight
+    frame, frames queued on one stream are ordered, frames on different streams must not share scratch memory."""
 
     def __init__(self):
         self.items = {}
 
-    def get(self, device, mode, P, W, H, min_cap=0):
-        key = (device.index, mode, P, W, H)
+    def get(self, device, mode, P, W, H, min_cap=0, stream=0):
+        key = (device.index, mode, P, W, H, stream)
         it = self.items.get(key)
         if it is None or it["cap"] < min_cap:
             cap = max(min_cap, _initial_capacity(P))
@@ -176,7 +177,7 @@ def _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace):
             cap = max(min_cap, _train_capacity_hint.get((device.index, P, W, H), _initial_capacity(P)))
             item = _new_workspace(device, mode, P, W, H, cap)
         else:
-            item = _pool.get(device, mode, P, W, H, min_cap)
+            item = _pool.get(device, mode, P, W, H, min_cap, stream)
             if _DEFERRED and item["pending"]:
                 # previous frame's statistics have long landed in pinned memory
                 st = _stats_dict(item)

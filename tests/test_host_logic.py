@@ -61,6 +61,27 @@ def test_overflow_reruns_with_a_larger_workspace_and_never_truncates(stubbed):
     assert caps == [item["cap"]]
 
 
+def test_frames_on_different_streams_do_not_share_a_workspace(stubbed, monkeypatch):
+    dev = torch.device("cpu")
+    used = []
+
+    def launch(item, stream):
+        used.append((stream, item["ws_ptr"]))
+        item["stats_np"][:] = 0
+
+    class S1(_Stream):
+        cuda_stream = 111
+
+    class S2(_Stream):
+        cuda_stream = 222
+
+    for S in (S1, S2, S1):
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None, S=S: S())
+        stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 100, 32, 32, fresh_workspace=False)
+    assert [s for s, _ in used] == [111, 222, 111]
+    assert used[0][1] != used[1][1] and used[0][1] == used[2][1]
+
+
 def test_training_workspace_capacity_only_grows(stubbed):
     dev = torch.device("cpu")
     seen = []
