@@ -273,11 +273,22 @@ def _packed_rows(user, prepared, P, M_rest, device, verify):
                     refs.append(weakref.finalize(t, _packed_cache.pop, key, None))
                 except TypeError:
                     return rows          # not weak-referenceable: use the rows for this call only
-        _packed_cache[key] = {"rows": rows, "refs": refs}
+        ent = {"rows": rows, "refs": refs, "stream": None, "event": None}
+        if rows.is_cuda:
+            # the packing pass ran on the current stream; a frame queued later on ANOTHER stream must wait for it
+            cur = torch.cuda.current_stream(device)
+            ent["stream"] = cur.cuda_stream
+            ent["event"] = torch.cuda.Event()
+            ent["event"].record(cur)
+        _packed_cache[key] = ent
         return rows
     if verify and not torch.equal(ent["rows"], _pack_rows(P, M_rest, *prepared, device)):
         raise RuntimeError("fovgs: the packed model cache is stale (a model tensor was modified without bumping its version "
                            "counter); call fovgs.ops.invalidate_model_cache() after such writes")
+    if ent.get("event") is not None:
+        cur = torch.cuda.current_stream(device)
+        if cur.cuda_stream != ent["stream"]:
+            cur.wait_event(ent["event"])
     return ent["rows"]
 
 
