@@ -35,3 +35,15 @@ def test_reference_arm_times_the_cpu_port_on_a_bounded_sample():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "3 frames" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("fov_300k_800x600")
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: rank 0 alone runs the CPU port and prints the line; the other ranks exit 0 without work."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "mid",
+                        "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
