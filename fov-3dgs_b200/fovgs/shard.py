@@ -41,3 +41,17 @@ def aggregate_fps(table):
     total = float(table[:, 1].sum())
     slowest = float(table[:, 0].max())
     return total / (slowest * 1e-3) if slowest > 0 else 0.0
+
+
+def gather_images(image, dst=0, group=None):
+    """Rank `dst` receives every rank's rendered frame ([3,H,W] fp32, 24.9 MB at 1080p): one `gather` collective — NCCL over
+    NVLink on GPUs (device tensors never touch the host), gloo in the CPU tests.  Returns a [world,3,H,W] tensor on `dst`
+    (rank order = frame order of one round of the round-robin deal) and None elsewhere."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return image.unsqueeze(0)
+    rank = dist.get_rank(group)
+    image = image.contiguous()
+    out = torch.empty((world,) + tuple(image.shape), dtype=image.dtype, device=image.device) if rank == dst else None
+    dist.gather(image, list(out.unbind(0)) if rank == dst else None, dst=dst, group=group)
+    return out

@@ -79,9 +79,10 @@ def build_one(name, verbose=False):
     return so_path(name)
 
 
-# the variant bench.py --impl reference needs; __graft_entry__.build() builds only this one (about 3 minutes) unless
-# FOVGS_BUILD_ALL_REFS=1 — the other six (parity tools, goldens) take ~25 more minutes of compile time
-BENCH_VARIANTS = ("ref_fov_C",)
+# the variants bench.py --impl reference and the full-size parity tests (tests/test_gpu_fullsize_reference.py) need:
+# FOV (headline, config 3), OBB (config 2) and SUM (config 5).  __graft_entry__.build() builds only these (about 3 minutes
+# each when missing) unless FOVGS_BUILD_ALL_REFS=1 — the other four (parity tools, goldens) take ~15 more minutes
+BENCH_VARIANTS = ("ref_fov_C", "ref_obb_C", "ref_sum_C")
 
 
 def build_all(force=False, verbose=False, names=None):
@@ -98,6 +99,10 @@ def build_all(force=False, verbose=False, names=None):
         if force and os.path.isdir(os.path.join(OUT, name)):
             shutil.rmtree(os.path.join(OUT, name))
         built[name] = build_one(name, verbose=verbose)
+    if built.get("ref_fov_C"):
+        # machine code of the reference's two tile-level kernels, for oracle/ref_tile_tables.py (cuobjdump -xelf of the .so above)
+        import ref_tile_tables
+        ref_tile_tables.extract_cubin("ref_fov_C", force=force)
     return built
 
 

@@ -169,8 +169,10 @@ def test_fov_matches_reference_golden(scene_small, golden_dir, gi):
     assert np.array_equal(rg.cpu().numpy(), g["ranges"])
     assert np.abs(color.cpu().numpy() - g["color"]).max() <= IMG_TOL
     lvl, mn, gx, gy, bl = ops.fov_tile_tables(item, c["image_width"], c["image_height"])
-    assert np.array_equal(mn.cpu().numpy().view(np.int32), g["tile_min_ours"].view(np.int32))
-    assert np.array_equal(bl.cpu().numpy(), g["tile_blend_ours"])
+    # tile tables against the REFERENCE binary's own kernels (decoded by oracle/ref_tile_tables.py when the golden was made)
+    for ours, key in ((lvl, "tile_level_ref"), (mn, "tile_min_ref"), (gx, "tile_grad_x_ref"), (gy, "tile_grad_y_ref")):
+        assert np.array_equal(ours.cpu().numpy().view(np.int32), g[key].view(np.int32)), key
+    assert np.array_equal(bl.cpu().numpy(), g["tile_blend_ref"])
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -35,7 +35,10 @@ def _worker(rank, world, port, q):
     frames = shard.frames_for_rank(31, rank, world)
     ms = 10.0 * len(frames) * (1 + rank)          # rank 1 is slower
     table = shard.gather_timings(ms, len(frames))
-    q.put((rank, frames, table.tolist(), shard.aggregate_fps(table)))
+    imgs = shard.gather_images(torch.full((3, 4, 5), float(rank + 1)))
+    ok = (rank != 0 and imgs is None) or (rank == 0 and imgs.shape == (world, 3, 4, 5)
+                                          and all(bool((imgs[r] == r + 1).all()) for r in range(world)))
+    q.put((rank, frames, table.tolist(), shard.aggregate_fps(table), ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,3 +60,4 @@ def test_two_rank_gloo_gather():
     assert res[0][1] == list(range(0, 31, 2)) and res[1][1] == list(range(1, 31, 2))
     assert res[0][2] == res[1][2]                 # both ranks hold the same table
     assert res[0][3] == pytest.approx(31 / (10.0 * 15 * 2 * 1e-3))
+    assert res[0][4] and res[1][4]                # rank 0 holds both ranks' images, rank 1 holds none

@@ -124,11 +124,14 @@ def run_fov(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
                                               sc["highest_levels"], gaze, 0.05, True, rs)
             rep["lazy_img_max_abs"] = float((col_l - col_r).abs().max().item()); rep["lazy_stats"] = dict(ops.last_stats)
             if golden_dir and gi < 2:
-                lvl, mn, gx, gy, bl = ops.fov_tile_tables(item, W, H)
+                # per-tile tables from the REFERENCE binary's own kernels (oracle/ref_tile_tables.py), not from ours
+                import ref_tile_tables
+                tt = ref_tile_tables.reference_tile_tables(W, H, g, 0.05)
                 np.savez_compressed(os.path.join(golden_dir, f"fov_{tag}_g{gi}.npz"), gaze=np.array(g, np.float32),
                                     color=col_r.cpu().numpy(), radii=rad_r.cpu().numpy(), num_rendered=np.int64(n_r),
                                     point_list=br["point_list"].cpu().numpy(), ranges=ir["ranges"][: ((W + 15) // 16) * ((H + 15) // 16)].cpu().numpy(),
-                                    tile_level_ours=lvl.cpu().numpy(), tile_min_ours=mn.cpu().numpy(), tile_blend_ours=bl.cpu().numpy())
+                                    tile_level_ref=tt["tile_level"], tile_min_ref=tt["tile_min"], tile_grad_x_ref=tt["grad_x"],
+                                    tile_grad_y_ref=tt["grad_y"], tile_blend_ref=tt["blending"].astype(np.uint8))
             if do_time and gi == 0:
                 rep["time_ref"] = time_fn(lambda: ref_api.fov_forward(mod, sc, c, gaze))
                 rep["time_ours"] = time_fn(lambda: ops.forward_fov(sc["means3D"], sc["opacities4"], sc["scales"], sc["rotations"],
