@@ -91,6 +91,7 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&ws, bytes));
         fovgs_fov_fwd_args a;
         memset(&a, 0, sizeof(a));
+        a.struct_size = (uint32_t)sizeof(a); a.abi_version = FOVGS_VERSION;   /* FOVGS_ARGS_HEADER */
         a.cam.image_height = H; a.cam.image_width = W;
         a.cam.tanfovx = hf[0]; a.cam.tanfovy = hf[1];
         a.cam.scale_modifier = 1.0f; a.cam.sh_degree = hi[5];

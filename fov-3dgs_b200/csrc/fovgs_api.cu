@@ -28,10 +28,35 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace fovgs
 
+// the two-word header of every args struct (FOVGS_ARGS_HEADER): read before any other field
+template <class A>
+static int check_header(const A* a, const char* what) {
+    if (a->struct_size != (uint32_t)sizeof(A) || a->abi_version != (uint32_t)FOVGS_VERSION) {
+        snprintf(g_err, sizeof(g_err), "%s: args header mismatch (struct_size %u, abi_version %u; this library expects %u, %d): "
+                 "the caller was built against another include/fovgs.h", what, a->struct_size, a->abi_version, (unsigned)sizeof(A), FOVGS_VERSION);
+        return FOVGS_ERR_INVALID_ARG;
+    }
+    return 0;
+}
+
 extern "C" {
 
 const char* fovgs_last_error(void) { return g_err; }
 int fovgs_version(void) { return FOVGS_VERSION; }
+
+size_t fovgs_struct_size(int32_t id) {
+    switch (id) {
+        case FOVGS_STRUCT_CAMERA: return sizeof(fovgs_camera);
+        case FOVGS_STRUCT_FRAME_STATS: return sizeof(fovgs_frame_stats);
+        case FOVGS_STRUCT_FOV_FWD_ARGS: return sizeof(fovgs_fov_fwd_args);
+        case FOVGS_STRUCT_SMFR_FWD_ARGS: return sizeof(fovgs_smfr_fwd_args);
+        case FOVGS_STRUCT_MMFR_FWD_ARGS: return sizeof(fovgs_mmfr_fwd_args);
+        case FOVGS_STRUCT_PS1_FWD_ARGS: return sizeof(fovgs_ps1_fwd_args);
+        case FOVGS_STRUCT_PS1_BWD_ARGS: return sizeof(fovgs_ps1_bwd_args);
+        case FOVGS_STRUCT_ADAM_GROUP: return sizeof(fovgs_adam_group);
+        default: return 0;
+    }
+}
 
 size_t fovgs_workspace_bytes(int32_t P, int32_t W, int32_t H, int64_t max_instances, int32_t foveated, int32_t ps1_mode) {
     if (P < 0 || W <= 0 || H <= 0 || max_instances < 0) return 0;
@@ -50,6 +75,7 @@ static int check_cam(const fovgs_camera& c) {
 
 int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_header(a, "fovgs_forward_fov")) return r;
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
@@ -90,6 +116,7 @@ int fovgs_pack_color_rows(int32_t P, int32_t M_rest, const float* means3D, const
 
 int fovgs_forward_smfr(const fovgs_smfr_fwd_args* a, void* stream) {
     if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_header(a, "fovgs_forward_smfr")) return r;
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
@@ -117,6 +144,7 @@ int fovgs_forward_smfr(const fovgs_smfr_fwd_args* a, void* stream) {
 
 int fovgs_forward_mmfr(const fovgs_mmfr_fwd_args* a, void* stream) {
     if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_header(a, "fovgs_forward_mmfr")) return r;
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
@@ -144,6 +172,7 @@ int fovgs_forward_mmfr(const fovgs_mmfr_fwd_args* a, void* stream) {
 
 int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_header(a, "fovgs_forward_ps1")) return r;
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
@@ -181,6 +210,7 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
 
 int fovgs_backward_ps1(const fovgs_ps1_bwd_args* a, void* stream) {
     if (!a) return fail(FOVGS_ERR_INVALID_ARG, "null args%s");
+    if (int r = check_header(a, "fovgs_backward_ps1")) return r;
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     if (a->P == 0) return 0;

@@ -16,7 +16,19 @@ FOVGS_PS1_SUM = 1
 FOVGS_PS1_MAX = 2
 FOVGS_PS1_LWMC = 3
 
+FOVGS_VERSION = 200   # include/fovgs.h; every args struct carries it next to its own size (FOVGS_ARGS_HEADER)
+
 _f = C.c_void_p  # all device pointers travel as void*
+_HEADER = [("struct_size", C.c_uint32), ("abi_version", C.c_uint32)]
+
+
+def new_args(cls):
+    """An args struct with its two-word header filled in (FOVGS_ARGS_INIT of the C header)."""
+    a = cls()
+    a.struct_size = C.sizeof(cls)
+    a.abi_version = FOVGS_VERSION
+    return a
+
 
 
 class Camera(C.Structure):
@@ -48,7 +60,7 @@ class FrameStats(C.Structure):
 
 
 class FovFwdArgs(C.Structure):
-    _fields_ = [
+    _fields_ = _HEADER + [
         ("cam", Camera),
         ("P", C.c_int32),
         ("M_rest", C.c_int32),
@@ -74,7 +86,7 @@ class FovFwdArgs(C.Structure):
 
 
 class SmfrFwdArgs(C.Structure):
-    _fields_ = [
+    _fields_ = _HEADER + [
         ("cam", Camera),
         ("P", C.c_int32),
         ("M", C.c_int32),
@@ -98,7 +110,7 @@ class SmfrFwdArgs(C.Structure):
 
 
 class MmfrFwdArgs(C.Structure):
-    _fields_ = [
+    _fields_ = _HEADER + [
         ("cam", Camera),
         ("P", C.c_int32),
         ("M", C.c_int32),
@@ -122,7 +134,7 @@ class MmfrFwdArgs(C.Structure):
 
 
 class Ps1FwdArgs(C.Structure):
-    _fields_ = [
+    _fields_ = _HEADER + [
         ("cam", Camera),
         ("mode", C.c_int32),
         ("P", C.c_int32),
@@ -148,7 +160,7 @@ class Ps1FwdArgs(C.Structure):
 
 
 class Ps1BwdArgs(C.Structure):
-    _fields_ = [
+    _fields_ = _HEADER + [
         ("cam", Camera),
         ("P", C.c_int32),
         ("M", C.c_int32),
@@ -218,7 +230,11 @@ EXPORTS = (
     "fovgs_profile_read_frame",
     "fovgs_last_error",
     "fovgs_version",
+    "fovgs_struct_size",
 )
+
+# fovgs_struct_id -> the ctypes mirror in this file
+STRUCT_IDS = {0: Camera, 1: FrameStats, 2: FovFwdArgs, 3: SmfrFwdArgs, 4: MmfrFwdArgs, 5: Ps1FwdArgs, 6: Ps1BwdArgs, 7: AdamGroup}
 
 _lib = None
 
@@ -236,6 +252,13 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.fovgs_last_error.restype = C.c_char_p
     L.fovgs_version.restype = C.c_int
+    L.fovgs_struct_size.restype = C.c_size_t
+    L.fovgs_struct_size.argtypes = [C.c_int32]
+    if L.fovgs_version() != FOVGS_VERSION:
+        raise RuntimeError(f"libfovgs.so at {LIB_PATH} has ABI version {L.fovgs_version()}, this binding was written for {FOVGS_VERSION}: rebuild it")
+    for sid, cls in STRUCT_IDS.items():
+        if L.fovgs_struct_size(sid) != C.sizeof(cls):
+            raise RuntimeError(f"fovgs/_lib.py: {cls.__name__} is {C.sizeof(cls)} bytes, the library's struct is {L.fovgs_struct_size(sid)}")
     L.fovgs_workspace_bytes.restype = C.c_size_t
     L.fovgs_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     L.fovgs_forward_fov.argtypes = [C.POINTER(FovFwdArgs), C.c_void_p]

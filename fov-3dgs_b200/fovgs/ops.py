@@ -19,7 +19,7 @@ import weakref
 import torch
 
 from . import _lib
-from ._lib import Camera, FovFwdArgs, FrameStats, MmfrFwdArgs, Ps1BwdArgs, Ps1FwdArgs, SmfrFwdArgs, check, lib
+from ._lib import Camera, FovFwdArgs, FrameStats, MmfrFwdArgs, Ps1BwdArgs, Ps1FwdArgs, SmfrFwdArgs, check, lib, new_args
 
 MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
 # pruning-metric variants of the training rasterizer: SUM's workspace layout and backward, other statistics
@@ -332,7 +332,7 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
     packed = _packed_rows(user_model, (means3D, shs_rest, shs_dcs, opacities), P, M_rest, device, bool(rs.debug))
 
     def launch(item, stream):
-        a = FovFwdArgs()
+        a = new_args(FovFwdArgs)
         a.packed_color_rows = None if packed is None else packed.data_ptr()
         a.cam = cam
         a.P = P
@@ -404,7 +404,7 @@ def forward_smfr(means3D, opacities, scales, rotations, shs, highest_levels, gaz
     lists = {}
 
     def launch(item, stream):
-        a = SmfrFwdArgs()
+        a = new_args(SmfrFwdArgs)
         a.cam = cam
         a.P = P
         a.M = M
@@ -473,7 +473,7 @@ def forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArra
     lists = {}
 
     def launch(item, stream):
-        a = MmfrFwdArgs()
+        a = new_args(MmfrFwdArgs)
         a.cam = cam
         a.P = P
         a.M = M
@@ -545,7 +545,7 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
     extra = {}
 
     def launch(item, stream):
-        a = Ps1FwdArgs()
+        a = new_args(Ps1FwdArgs)
         a.cam = cam
         a.mode = _PS1_ABI_MODE[mode]
         a.loss_map = loss_map.data_ptr() if mode == MODE_LWMC else None
@@ -614,7 +614,7 @@ def backward_ps1(workspace_item, means3D, radii, scales, rotations, cov3D_precom
         if workspace_item is None:
             raise RuntimeError("backward_ps1 needs the workspace of the matching forward call")
         g = _prep(grad_out_color, "grad_out_color", device)
-        a = Ps1BwdArgs()
+        a = new_args(Ps1BwdArgs)
         a.cam = _camera(rs, device, keep)
         a.P = P
         a.M = M

@@ -730,3 +730,24 @@ def test_fullsize_gaze_changes_only_the_foveated_work(big_scene):
     (n2, _, radii2, _, _, _), _, _ = _run_fov(s, c, (0.75, 0.75), want_lists=True)
     both = (radii1 > 0) & (radii2 > 0)
     assert n1 != n2 and bool((radii1[both] == radii2[both]).all())
+
+
+def test_integration_binding_stub_renders_like_the_package(scene_small):
+    """The ctypes stub INTEGRATION.md quotes (examples/binding_stub.py) is executed as written: same image, radii and instance
+    count as the drop-in package on the same inputs."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("binding_stub", os.path.join(root, "examples", "binding_stub.py"))
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    s, c = scene_small
+    f = synth.add_foveation(s)
+    (n, color, radii, pl, rg, item), sc, rs = _run_fov(f, c, (0.4, 0.6))
+    cd = _cuda(c)
+    g = torch.tensor([0.4, 0.6], dtype=torch.float32, device="cuda")
+    e = torch.empty(0, device="cuda")
+    n2, color2, radii2 = stub.rasterize_gaussians_fov(sc["shs_dcs"], sc["highest_levels"], g, 0.05, True, torch.zeros(3, device="cuda"),
+                                                      sc["means3D"], e, sc["opacities4"], sc["scales"], sc["rotations"], 1.0, e,
+                                                      cd["viewmatrix"], cd["projmatrix"], c["tanfovx"], c["tanfovy"], c["image_height"],
+                                                      c["image_width"], sc["shs_rest"], 3, cd["campos"], False, False)
+    assert n2 == n and torch.equal(radii2, radii) and torch.equal(color2, color)
