@@ -365,6 +365,17 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     return cudaGetLastError();
 }
 
+int device_sm_count() {
+    static int sms[MAX_DEVICES] = {};
+    const int dev = current_device_ordinal();
+    if (sms[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
+
 #define STAGE_CHECK()                                          \
     do {                                                       \
         cudaError_t e_ = cudaGetLastError();                   \
@@ -379,13 +390,7 @@ template <int MODE>
 static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int W, int H, bool debug, cudaStream_t st) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const int T = gx * gy;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = device_sm_count();
     prof_mark(1, st);
     launch_pre(ws, in, (Mode)MODE, num_sms, st);      // + tile scan, by the last CTA to finish
     STAGE_CHECK();

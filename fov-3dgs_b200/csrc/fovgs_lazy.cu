@@ -886,8 +886,9 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
 
 cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T, Mode mode, cudaStream_t st) {
     const size_t smem = sizeof(LazySmem), smem_sum = sizeof(LazySmem) + sizeof(SumSmemExtra);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    bool* configured = once.slot();
+    if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(k_lazy_blend<MODE_FOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_OBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -902,7 +903,7 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_LWMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
         if (e != cudaSuccess) return e;
-        configured = true;
+        *configured = true;
     }
     if (mode == MODE_FOV) k_lazy_blend<MODE_FOV><<<T, 256, smem, st>>>(ws, in);
     else if (mode == MODE_SMFR) k_lazy_blend<MODE_SMFR><<<T, 256, smem, st>>>(ws, in);

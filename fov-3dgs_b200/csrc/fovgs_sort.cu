@@ -283,11 +283,12 @@ template <int CAP>
 static cudaError_t launch_class(const Workspace& ws, int grid, uint32_t* out_ranges, uint32_t* out_point_list, uint32_t nmin,
                                 cudaStream_t st) {
     const size_t smem = (size_t)2 * CAP * 8 + 8 * 256 * 4;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;       // per device (and per CAP instantiation)
+    bool* configured = once.slot();
+    if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tile_sort_smem<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        *configured = true;
     }
     k_tile_sort_smem<CAP><<<grid, 256, smem, st>>>(ws, out_ranges, out_point_list, nmin);
     return cudaGetLastError();

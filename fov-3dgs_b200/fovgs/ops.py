@@ -50,14 +50,10 @@ def set_deferred_check(on):
 
 
 def check_pending(device=None):
-    """Synchronise and validate every workspace whose statistics were not yet inspected (deferred mode)."""
+    """Synchronise and validate every frame whose statistics were not yet inspected (deferred mode)."""
     torch.cuda.synchronize(device)
-    for item in _pool.items.values():
-        if item["pending"]:
-            st = _stats_dict(item)
-            item["pending"] = False
-            if st["overflow"]:
-                raise RuntimeError(f"fovgs: a deferred frame overflowed its instance capacity ({st['num_rendered']} > {item['cap']})")
+    for key, item in list(_pool.items.items()):
+        _drain_ring(item, key, block=True)
 
 
 def _ptr(t):
@@ -76,6 +72,8 @@ def _prep(t, name, device, dtype=torch.float32, optional=False):
         raise RuntimeError(f"{name} must be a non-empty tensor")
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.device != device:
+        raise RuntimeError(f"{name} is on {t.device} but means3D is on {device}: all inputs must share one device")
     if t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()
@@ -103,24 +101,55 @@ def _camera(rs, device, keep):
     return cam
 
 
+_RING = 8   # per-workspace ring of pinned statistics slots: frames whose statistics may be un-inspected in deferred mode
+
+
 class _Pool:
     """Reusable workspaces for the inference paths, one per (device, mode, P, W, H, stream): one workspace is one in-flight
-    frame, frames queued on one stream are ordered, frames on different streams must not share scratch memory."""
+    frame, frames queued on one stream are ordered, frames on different streams must not share scratch memory.
+    Least-recently-used entries are dropped once the pool holds more than FOVGS_POOL_BYTES (default 24 GiB; the entry in use
+    is never dropped), so resolution sweeps, MMFR's four level models or evaluation during densification do not pin one
+    multi-GB workspace per configuration for the life of the process.  `release_workspaces()` empties it."""
 
     def __init__(self):
-        self.items = {}
+        import collections
+        self.items = collections.OrderedDict()
+        self.min_caps = {}          # capacities learnt from overflows (kept across evictions)
+        self.budget = int(float(os.environ.get("FOVGS_POOL_BYTES", 24 * 2 ** 30)))
 
     def get(self, device, mode, P, W, H, min_cap=0, stream=0):
         key = (device.index, mode, P, W, H, stream)
+        min_cap = max(min_cap, self.min_caps.get(key, 0))
         it = self.items.get(key)
         if it is None or it["cap"] < min_cap:
+            if it is not None:
+                _drain_ring(it, key, block=True, raise_on_overflow=False)
             cap = max(min_cap, _initial_capacity(P))
             it = _new_workspace(device, mode, P, W, H, cap)
+            it["key"] = key
             self.items[key] = it
+            total = sum(x["bytes"] for x in self.items.values())
+            for k in list(self.items):
+                if total <= self.budget or k == key:
+                    continue
+                old = self.items[k]
+                if any(old["ring_pending"]):
+                    continue                   # frames with un-inspected statistics: keep until they are checked
+                total -= old["bytes"]
+                del self.items[k]
+        self.items.move_to_end(key)
         return it
+
+    def require(self, key, cap):
+        self.min_caps[key] = max(self.min_caps.get(key, 0), int(cap))
 
     def clear(self):
         self.items.clear()
+
+
+def release_workspaces():
+    """Drops every pooled inference workspace (their memory returns to torch's caching allocator)."""
+    _pool.clear()
 
 
 def _initial_capacity(P):
@@ -136,21 +165,25 @@ def _new_workspace(device, mode, P, W, H, cap):
     if nbytes == 0:
         raise RuntimeError("fovgs_workspace_bytes rejected the frame configuration")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    stats = torch.zeros(16, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(16, dtype=torch.int32)
+    # _RING slots of 16 ints: slot 0 serves the blocking mode; deferred frames cycle through all of them, each guarded by a
+    # CUDA event recorded behind its 64-byte copy, so a slot is only read once its copy has landed and only reused once read
+    stats = torch.zeros((_RING, 16), dtype=torch.int32)
+    if torch.cuda.is_available():
+        stats = stats.pin_memory()
     # `stats_np` aliases the (pinned) host tensor: reading 16 ints through it costs ~1 us, indexing the tensor ~3 us each
     return {"ws": ws, "cap": cap, "bytes": nbytes, "stats": stats, "stats_np": stats.numpy(), "stats_ptr": stats.data_ptr(),
-            "ws_ptr": ws.data_ptr(), "pending": False}
+            "ws_ptr": ws.data_ptr(), "ring_events": [None] * _RING, "ring_pending": [False] * _RING, "ring_pos": 0, "key": None}
 
 
 _pool = _Pool()
 
 
-def _read_stats(item, stream):
-    check(lib().fovgs_read_stats_async(item["ws_ptr"], item["stats_ptr"], stream), "fovgs_read_stats_async")
+def _read_stats(item, stream, slot=0):
+    check(lib().fovgs_read_stats_async(item["ws_ptr"], item["stats_ptr"] + 64 * slot, stream), "fovgs_read_stats_async")
 
 
-def _stats_dict(item):
-    s = item["stats_np"].tolist()
+def _stats_dict(item, slot=0):
+    s = item["stats_np"][slot].tolist()
     return {
         "num_rendered": s[0] & 0xFFFFFFFF,
         "overflow": s[1],
@@ -167,10 +200,57 @@ def _stats_dict(item):
 last_stats = {}
 
 
+def _check_slot(item, key, slot, raise_on_overflow=True):
+    """Inspects one landed statistics slot of a deferred frame."""
+    item["ring_pending"][slot] = False
+    st = _stats_dict(item, slot)
+    if st["overflow"]:
+        # the frame that overflowed has already been handed out truncated — that cannot be undone, so it is reported; the
+        # pooled workspace grows to what the frame needed, so the caller's retry (and every later frame) fits
+        need = _round_capacity(int(st["num_rendered"] * 1.25) + 1024)
+        if key is not None:
+            _pool.require(key, need)
+        if raise_on_overflow:
+            raise RuntimeError(f"fovgs: a deferred frame overflowed its instance capacity ({st['num_rendered']} > {item['cap']}); "
+                               f"its image is incomplete — the workspace now grows to {need} instances, render the frame again")
+    if st["prefiltered_violations"] and raise_on_overflow:
+        raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen! "
+                           f"({st['prefiltered_violations']} Gaussians behind the near plane)")
+
+
+def _drain_ring(item, key, block, raise_on_overflow=True, only_slot=None):
+    """Checks pending deferred slots, oldest first: all of them when `block` (waiting for their events), otherwise only those
+    whose 64-byte copy has already landed (event query)."""
+    n = _RING
+    start = item["ring_pos"]
+    for i in range(n):
+        slot = (start + i) % n            # ring_pos is the NEXT slot to be written = the oldest one still held
+        if only_slot is not None and slot != only_slot:
+            continue
+        if not item["ring_pending"][slot]:
+            continue
+        ev = item["ring_events"][slot]
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            break                          # younger frames cannot have landed either
+        _check_slot(item, key, slot, raise_on_overflow)
+
+
 def _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace):
+    """Runs `launch(item)` with the tensor's device current (a tensor on another device than the current one would otherwise
+    get its kernels launched on a stream of the wrong device)."""
+    if device.type == "cuda" and torch.cuda.current_device() != device.index:
+        with torch.cuda.device(device):
+            return _run_with_capacity_impl(launch, device, mode, P, W, H, fresh_workspace)
+    return _run_with_capacity_impl(launch, device, mode, P, W, H, fresh_workspace)
+
+
+def _run_with_capacity_impl(launch, device, mode, P, W, H, fresh_workspace):
     """Runs `launch(item)`; on instance overflow grows the workspace and re-runs (no silent truncation)."""
     global last_stats
-    stream = torch.cuda.current_stream(device).cuda_stream
+    cur_stream = torch.cuda.current_stream(device)
+    stream = cur_stream.cuda_stream
     min_cap = 0
     while True:
         if fresh_workspace:
@@ -178,18 +258,29 @@ def _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace):
             item = _new_workspace(device, mode, P, W, H, cap)
         else:
             item = _pool.get(device, mode, P, W, H, min_cap, stream)
-            if _DEFERRED and item["pending"]:
-                # previous frame's statistics have long landed in pinned memory
-                st = _stats_dict(item)
-                if st["overflow"]:
-                    raise RuntimeError("fovgs: the previous frame overflowed its instance capacity "
-                                       f"({st['num_rendered']} > {item['cap']}); re-run without FOVGS_DEFERRED_CHECK")
+        if _DEFERRED and not fresh_workspace:
+            key = item["key"]
+            # statistics of earlier frames whose copies have landed; then make sure the slot this frame will use is free
+            _drain_ring(item, key, block=False)
+            slot = item["ring_pos"]
+            if item["ring_pending"][slot]:
+                _drain_ring(item, key, block=True, only_slot=slot)     # the host ran _RING frames ahead: wait for the oldest
+            if item is not _pool.items.get(key) or item["cap"] < _pool.min_caps.get(key, 0):
+                continue                                                # an overflow was learnt: take the grown workspace
+            launch(item, stream)
+            _read_stats(item, stream, slot)
+            ev = item["ring_events"][slot]
+            if ev is None:
+                ev = item["ring_events"][slot] = torch.cuda.Event()
+            ev.record(cur_stream)
+            item["ring_pending"][slot] = True
+            item["ring_pos"] = (slot + 1) % _RING
+            return item, None
+        if not fresh_workspace:
+            _drain_ring(item, item["key"], block=True)                  # frames left over from a deferred phase
         launch(item, stream)
         _read_stats(item, stream)
-        if _DEFERRED and not fresh_workspace:
-            item["pending"] = True
-            return item, None
-        torch.cuda.current_stream(device).synchronize()
+        cur_stream.synchronize()
         st = _stats_dict(item)
         last_stats = st
         if st["prefiltered_violations"]:
@@ -264,8 +355,15 @@ def _packed_rows(user, prepared, P, M_rest, device, verify):
             return None
         _packed_candidate[0] = None
         rows = _pack_rows(P, M_rest, *prepared, device)
+        # an in-place update bumped `_version`: the entry of the same tensor objects at the older version is dead weight
+        # (P * 256 bytes, 1.5 GB at 6 M Gaussians) — drop it now instead of waiting for four newer entries to push it out
+        ident = tuple(None if k is None else k[:2] for k in key)
+        for old in [k for k in _packed_cache if tuple(None if x is None else x[:2] for x in k) == ident]:
+            for r in _packed_cache.pop(old)["refs"]:
+                r.detach()
         if len(_packed_cache) >= 4:
-            _packed_cache.pop(next(iter(_packed_cache)))
+            for r in _packed_cache.pop(next(iter(_packed_cache)))["refs"]:
+                r.detach()
         refs = []
         for t in user:
             if t is not None:
@@ -289,7 +387,80 @@ def _packed_rows(user, prepared, P, M_rest, device, verify):
         cur = torch.cuda.current_stream(device)
         if cur.cuda_stream != ent["stream"]:
             cur.wait_event(ent["event"])
+            # the rows were allocated on another stream: tell the caching allocator this stream reads them too, so an evicted
+            # or finalized entry is not handed out again while a frame queued here is still gathering from it
+            ent["rows"].record_stream(cur)
     return ent["rows"]
+
+
+def _gaze_tensor(gazeArray, device):
+    gaze = gazeArray
+    if not isinstance(gaze, torch.Tensor):
+        gaze = torch.tensor([float(gaze[0]), float(gaze[1])], dtype=torch.float32)
+    if not gaze.is_cuda:
+        gaze = gaze.to(device, non_blocking=True)
+    return _prep(gaze, "gazeArray", device)
+
+
+# entry point, args struct and pool mode of the three foveated forwards (they share everything but a few fields)
+_FOV_KINDS = {
+    "fov": ("fovgs_forward_fov", FovFwdArgs, MODE_FOV),
+    "smfr": ("fovgs_forward_smfr", SmfrFwdArgs, MODE_SMFR),
+    "mmfr": ("fovgs_forward_mmfr", MmfrFwdArgs, MODE_MMFR),
+}
+
+
+def _forward_foveated(kind, fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists, keep):
+    """The marshalling the three foveated forwards share: camera block, outputs, workspace, optional sorted lists, launch through
+    the capacity protocol.  `fields`: the variant's own struct fields (name -> int / float / device pointer)."""
+    entry, Args, mode = _FOV_KINDS[kind]
+    device = means3D.device
+    rs = raster_settings
+    H, W = int(rs.image_height), int(rs.image_width)
+    P = means3D.size(0)
+    gaze = _gaze_tensor(gazeArray, device)
+    cam = _camera(rs, device, keep)
+    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    lists = {}
+    fn = getattr(lib(), entry)
+    a = new_args(Args)
+    a.cam = cam
+    a.P = P
+    a.means3D = means3D.data_ptr()
+    a.scales = scales.data_ptr()
+    a.rotations = rotations.data_ptr()
+    a.gaze = gaze.data_ptr()
+    a.alpha = float(alpha) if alpha is not None else 0.0
+    a.blending = int(bool(blending))
+    a.out_color = color.data_ptr()
+    a.radii = radii.data_ptr()
+    for k, v in fields.items():
+        setattr(a, k, v)
+
+    def launch(item, stream):
+        a.workspace = item["ws_ptr"]
+        a.workspace_bytes = item["bytes"]
+        a.max_instances = item["cap"]
+        if want_lists:
+            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
+            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
+            a.out_point_list = lists["point_list"].data_ptr()
+            a.out_ranges = lists["ranges"].data_ptr()
+        check(fn(C.byref(a), stream), entry)
+
+    item, st = _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace=False)
+    n = st["num_rendered"] if st is not None else -1
+    if want_lists:
+        return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item
+    return n, color, radii
+
+
+def _empty_frame(means3D, raster_settings):
+    device = means3D.device
+    H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+    return 0, torch.zeros((3, H, W), dtype=torch.float32, device=device), torch.zeros((0,), dtype=torch.int32, device=device)
 
 
 def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highest_levels, gazeArray, alpha, blending,
@@ -298,13 +469,9 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     device = means3D.device
-    rs = raster_settings
-    H, W = int(rs.image_height), int(rs.image_width)
     P = means3D.size(0)
     if P == 0:
-        z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
-        return 0, z, torch.zeros((0,), dtype=torch.int32, device=device)
-    keep = []
+        return _empty_frame(means3D, raster_settings)
     user_model = (means3D, shs_rest if (shs_rest is not None and shs_rest.numel()) else None, shs_dcs, opacities)
     means3D = _prep(means3D, "means3D", device)
     opacities = _prep(opacities, "opacities", device)
@@ -317,53 +484,12 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
     highest_levels = _prep(highest_levels, "highest_levels", device)
     if shs_dcs.numel() != P * 12 or highest_levels.numel() != P:
         raise RuntimeError("shs_dcs must be (P,4,3) and highest_levels (P,1)")
-    gaze = gazeArray
-    if not isinstance(gaze, torch.Tensor):
-        gaze = torch.tensor([float(gaze[0]), float(gaze[1])], dtype=torch.float32)
-    if not gaze.is_cuda:
-        gaze = gaze.to(device, non_blocking=True)
-    gaze = _prep(gaze, "gazeArray", device)
     M_rest = 0 if shs_rest is None else int(shs_rest.size(1))
-    cam = _camera(rs, device, keep)
-    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
-    radii = torch.empty((P,), dtype=torch.int32, device=device)
-    T = ((W + 15) // 16) * ((H + 15) // 16)
-    lists = {}
-    packed = _packed_rows(user_model, (means3D, shs_rest, shs_dcs, opacities), P, M_rest, device, bool(rs.debug))
-
-    def launch(item, stream):
-        a = new_args(FovFwdArgs)
-        a.packed_color_rows = None if packed is None else packed.data_ptr()
-        a.cam = cam
-        a.P = P
-        a.M_rest = M_rest
-        a.means3D = means3D.data_ptr()
-        a.opacities = opacities.data_ptr()
-        a.scales = scales.data_ptr()
-        a.rotations = rotations.data_ptr()
-        a.shs_rest = _ptr(shs_rest)
-        a.shs_dcs = shs_dcs.data_ptr()
-        a.highest_levels = highest_levels.data_ptr()
-        a.gaze = gaze.data_ptr()
-        a.alpha = float(alpha) if alpha is not None else 0.0
-        a.blending = int(bool(blending))
-        a.out_color = color.data_ptr()
-        a.radii = radii.data_ptr()
-        a.workspace = item["ws"].data_ptr()
-        a.workspace_bytes = item["bytes"]
-        a.max_instances = item["cap"]
-        if want_lists:
-            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
-            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
-            a.out_point_list = lists["point_list"].data_ptr()
-            a.out_ranges = lists["ranges"].data_ptr()
-        check(lib().fovgs_forward_fov(C.byref(a), stream), "fovgs_forward_fov")
-
-    item, st = _run_with_capacity(launch, device, MODE_FOV, P, W, H, fresh_workspace=False)
-    n = st["num_rendered"] if st is not None else -1
-    if want_lists:
-        return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item
-    return n, color, radii
+    packed = _packed_rows(user_model, (means3D, shs_rest, shs_dcs, opacities), P, M_rest, device, bool(raster_settings.debug))
+    fields = {"M_rest": M_rest, "opacities": opacities.data_ptr(), "shs_rest": _ptr(shs_rest), "shs_dcs": shs_dcs.data_ptr(),
+              "highest_levels": highest_levels.data_ptr(), "packed_color_rows": None if packed is None else packed.data_ptr()}
+    return _forward_foveated("fov", fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists,
+                             [opacities, shs_rest, shs_dcs, highest_levels, packed])
 
 
 def forward_smfr(means3D, opacities, scales, rotations, shs, highest_levels, gazeArray, alpha, blending, raster_settings,
@@ -373,13 +499,9 @@ def forward_smfr(means3D, opacities, scales, rotations, shs, highest_levels, gaz
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     device = means3D.device
-    rs = raster_settings
-    H, W = int(rs.image_height), int(rs.image_width)
     P = means3D.size(0)
     if P == 0:
-        z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
-        return 0, z, torch.zeros((0,), dtype=torch.int32, device=device)
-    keep = []
+        return _empty_frame(means3D, raster_settings)
     means3D = _prep(means3D, "means3D", device)
     opacities = _prep(opacities, "opacities", device)
     if opacities.numel() != P:
@@ -390,50 +512,9 @@ def forward_smfr(means3D, opacities, scales, rotations, shs, highest_levels, gaz
     highest_levels = _prep(highest_levels, "highest_levels", device)
     if highest_levels.numel() != P:
         raise RuntimeError("highest_levels must be (P,1)")
-    gaze = gazeArray
-    if not isinstance(gaze, torch.Tensor):
-        gaze = torch.tensor([float(gaze[0]), float(gaze[1])], dtype=torch.float32)
-    if not gaze.is_cuda:
-        gaze = gaze.to(device, non_blocking=True)
-    gaze = _prep(gaze, "gazeArray", device)
-    M = int(shs.size(1))
-    cam = _camera(rs, device, keep)
-    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
-    radii = torch.empty((P,), dtype=torch.int32, device=device)
-    T = ((W + 15) // 16) * ((H + 15) // 16)
-    lists = {}
-
-    def launch(item, stream):
-        a = new_args(SmfrFwdArgs)
-        a.cam = cam
-        a.P = P
-        a.M = M
-        a.means3D = means3D.data_ptr()
-        a.opacities = opacities.data_ptr()
-        a.scales = scales.data_ptr()
-        a.rotations = rotations.data_ptr()
-        a.shs = shs.data_ptr()
-        a.highest_levels = highest_levels.data_ptr()
-        a.gaze = gaze.data_ptr()
-        a.alpha = float(alpha) if alpha is not None else 0.0
-        a.blending = int(bool(blending))
-        a.out_color = color.data_ptr()
-        a.radii = radii.data_ptr()
-        a.workspace = item["ws"].data_ptr()
-        a.workspace_bytes = item["bytes"]
-        a.max_instances = item["cap"]
-        if want_lists:
-            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
-            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
-            a.out_point_list = lists["point_list"].data_ptr()
-            a.out_ranges = lists["ranges"].data_ptr()
-        check(lib().fovgs_forward_smfr(C.byref(a), stream), "fovgs_forward_smfr")
-
-    item, st = _run_with_capacity(launch, device, MODE_SMFR, P, W, H, fresh_workspace=False)
-    n = st["num_rendered"] if st is not None else -1
-    if want_lists:
-        return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item
-    return n, color, radii
+    fields = {"M": int(shs.size(1)), "opacities": opacities.data_ptr(), "shs": shs.data_ptr(), "highest_levels": highest_levels.data_ptr()}
+    return _forward_foveated("smfr", fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists,
+                             [opacities, shs, highest_levels])
 
 
 def forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArray, alpha, blending, raster_settings,
@@ -443,15 +524,11 @@ def forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArra
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     device = means3D.device
-    rs = raster_settings
-    H, W = int(rs.image_height), int(rs.image_width)
     P = means3D.size(0)
     if P == 0:
-        z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
-        return 0, z, torch.zeros((0,), dtype=torch.int32, device=device)
+        return _empty_frame(means3D, raster_settings)
     if cur_level is None:
         raise RuntimeError("cur_level must be given (0..3)")
-    keep = []
     means3D = _prep(means3D, "means3D", device)
     opacities = _prep(opacities, "opacities", device)
     if opacities.numel() != P:
@@ -459,50 +536,9 @@ def forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArra
     scales = _prep(scales, "scales", device)
     rotations = _prep(rotations, "rotations", device)
     shs = _prep(shs, "shs", device)
-    gaze = gazeArray
-    if not isinstance(gaze, torch.Tensor):
-        gaze = torch.tensor([float(gaze[0]), float(gaze[1])], dtype=torch.float32)
-    if not gaze.is_cuda:
-        gaze = gaze.to(device, non_blocking=True)
-    gaze = _prep(gaze, "gazeArray", device)
-    M = int(shs.size(1))
-    cam = _camera(rs, device, keep)
-    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
-    radii = torch.empty((P,), dtype=torch.int32, device=device)
-    T = ((W + 15) // 16) * ((H + 15) // 16)
-    lists = {}
-
-    def launch(item, stream):
-        a = new_args(MmfrFwdArgs)
-        a.cam = cam
-        a.P = P
-        a.M = M
-        a.means3D = means3D.data_ptr()
-        a.opacities = opacities.data_ptr()
-        a.scales = scales.data_ptr()
-        a.rotations = rotations.data_ptr()
-        a.shs = shs.data_ptr()
-        a.cur_level = float(cur_level)
-        a.gaze = gaze.data_ptr()
-        a.alpha = float(alpha) if alpha is not None else 0.0
-        a.blending = int(bool(blending))
-        a.out_color = color.data_ptr()
-        a.radii = radii.data_ptr()
-        a.workspace = item["ws"].data_ptr()
-        a.workspace_bytes = item["bytes"]
-        a.max_instances = item["cap"]
-        if want_lists:
-            lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
-            lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
-            a.out_point_list = lists["point_list"].data_ptr()
-            a.out_ranges = lists["ranges"].data_ptr()
-        check(lib().fovgs_forward_mmfr(C.byref(a), stream), "fovgs_forward_mmfr")
-
-    item, st = _run_with_capacity(launch, device, MODE_MMFR, P, W, H, fresh_workspace=False)
-    n = st["num_rendered"] if st is not None else -1
-    if want_lists:
-        return n, color, radii, lists["point_list"][: max(n, 0)], lists["ranges"], item
-    return n, color, radii
+    fields = {"M": int(shs.size(1)), "opacities": opacities.data_ptr(), "shs": shs.data_ptr(), "cur_level": float(cur_level)}
+    return _forward_foveated("mmfr", fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists,
+                             [opacities, shs])
 
 
 def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs, colors_precomp, raster_settings,

@@ -39,7 +39,31 @@ def lib():
         _lib.orc_forward_smfr.restype = C.c_int64
         _lib.orc_forward_mmfr.restype = C.c_int64
         _lib.orc_backward_ps1.restype = C.c_int
+        _lib.orc_ambiguous.restype = C.c_int64
     return _lib
+
+
+def set_ambiguity(on):
+    """Binning passes record the (tile, Gaussian) OBB decisions that depend on the last place of the eigenvector
+    normalisation (GPU: MUFU.RSQ, here: 1/sqrtf) — see the header of fovgs_oracle.c.  Read them with `ambiguous()`."""
+    lib().orc_set_ambiguity(1 if on else 0)
+
+
+def ambiguous():
+    """int64 keys (tile << 32 | Gaussian id) of the last binning pass's rsqrt-sensitive decisions (needs set_ambiguity(True))."""
+    L = lib()
+    n = int(L.orc_ambiguous(None, 0))
+    out = np.zeros(max(n, 1), np.uint64)
+    L.orc_ambiguous(out.ctypes.data_as(C.c_void_p), C.c_int64(n))
+    return out[:n].astype(np.int64)
+
+
+def instance_keys(point_list, ranges):
+    """int64 keys (tile << 32 | Gaussian id) of a sorted point list with its per-tile ranges."""
+    rg = np.asarray(ranges, np.int64)
+    n = np.maximum(rg[:, 1] - rg[:, 0], 0)
+    tile = np.repeat(np.arange(rg.shape[0], dtype=np.int64), n)
+    return (tile << 32) | np.asarray(point_list, np.int64)[: tile.size]
 
 
 def _cam(cam, sh_degree, bg=(0.0, 0.0, 0.0), scale_modifier=1.0):

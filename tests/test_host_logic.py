@@ -18,12 +18,35 @@ class _Stream:
         pass
 
 
+class _Event:
+    """Stand-in for torch.cuda.Event: `landed` says whether the 64-byte statistics copy behind it has completed."""
+    auto_land = True
+    waits = 0
+
+    def __init__(self):
+        self.landed = False
+
+    def record(self, stream=None):
+        self.landed = _Event.auto_land
+
+    def query(self):
+        return self.landed
+
+    def synchronize(self):
+        _Event.waits += 1
+        self.landed = True
+
+
 @pytest.fixture
 def stubbed(monkeypatch):
     """ops with a fake library: workspaces are tiny CPU tensors, `launch` is the test's own function."""
     fake = types.SimpleNamespace(fovgs_workspace_bytes=lambda *a: 1024, fovgs_read_stats_async=lambda *a: 0)
     monkeypatch.setattr(ops, "lib", lambda: fake)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    monkeypatch.setattr(_Event, "auto_land", True)
+    monkeypatch.setattr(_Event, "waits", 0)
     monkeypatch.setattr(ops, "_pool", ops._Pool())
     monkeypatch.setattr(ops, "_train_capacity_hint", {})
     monkeypatch.setattr(ops, "_DEFERRED", False)
@@ -47,9 +70,9 @@ def test_overflow_reruns_with_a_larger_workspace_and_never_truncates(stubbed):
         caps.append(item["cap"])
         need = 5_000_000
         item["stats_np"][:] = 0
-        item["stats_np"][0] = need
-        item["stats_np"][1] = 1 if item["cap"] < need else 0
-        item["stats_np"][2] = 77
+        item["stats_np"][0, 0] = need
+        item["stats_np"][0, 1] = 1 if item["cap"] < need else 0
+        item["stats_np"][0, 2] = 77
 
     item, st = stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 1000, 64, 64, fresh_workspace=False)
     assert len(caps) == 2 and caps[0] == 1 << 20 and caps[1] >= 5_000_000 * 1.25 and caps[1] % (1 << 22) == 0
@@ -90,8 +113,8 @@ def test_training_workspace_capacity_only_grows(stubbed):
         def launch(item, stream):
             seen.append(item["cap"])
             item["stats_np"][:] = 0
-            item["stats_np"][0] = n
-            item["stats_np"][1] = 1 if item["cap"] < n else 0
+            item["stats_np"][0, 0] = n
+            item["stats_np"][0, 1] = 1 if item["cap"] < n else 0
         return launch
 
     stubbed._run_with_capacity(launch_n(9_000_000), dev, ops.MODE_SUM, 1000, 64, 64, fresh_workspace=True)
@@ -105,7 +128,7 @@ def test_prefiltered_violation_and_deferred_overflow_raise(stubbed):
 
     def bad_prefilter(item, stream):
         item["stats_np"][:] = 0
-        item["stats_np"][8] = 3
+        item["stats_np"][0, 8] = 3
 
     with pytest.raises(RuntimeError, match="Point is filtered although prefiltered is set"):
         stubbed._run_with_capacity(bad_prefilter, dev, ops.MODE_OBB, 10, 32, 32, fresh_workspace=False)
@@ -113,16 +136,77 @@ def test_prefiltered_violation_and_deferred_overflow_raise(stubbed):
     stubbed.set_deferred_check(True)
     try:
         def overflowing(item, stream):
-            item["stats_np"][:] = 0
-            item["stats_np"][0] = 1 << 30
-            item["stats_np"][1] = 1
+            slot = item["ring_pos"]
+            item["stats_np"][slot] = 0
+            item["stats_np"][slot, 0] = 30_000_000
+            item["stats_np"][slot, 1] = 1 if item["cap"] < 30_000_000 else 0
 
         item, st = stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
-        assert st is None and item["pending"]                               # not inspected yet
-        with pytest.raises(RuntimeError, match="previous frame overflowed"):
+        assert st is None and item["ring_pending"][0]                       # not inspected yet
+        with pytest.raises(RuntimeError, match="deferred frame overflowed"):
             stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        # the overflow was learnt: the pooled workspace has grown, the retry and every later frame fit and nothing raises
+        item2, _ = stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert item2 is not item and item2["cap"] >= 30_000_000
+        stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        stubbed.check_pending()
     finally:
         stubbed.set_deferred_check(False)
+
+
+def test_deferred_statistics_are_only_read_after_their_copy_landed(stubbed, monkeypatch):
+    """the host may run ahead of the GPU.  A frame's slot is inspected only once the event behind its 64-byte copy
+    says it has landed, every frame has its own slot (a ring), and an overflow in ANY frame is seen — not only the last one."""
+    dev = torch.device("cpu")
+    frame = [0]
+
+    def launch(item, stream):
+        slot = item["ring_pos"]
+        item["stats_np"][slot] = 0
+        item["stats_np"][slot, 0] = 30_000_000 if frame[0] == 2 else 1000
+        item["stats_np"][slot, 1] = 1 if (frame[0] == 2 and item["cap"] < 30_000_000) else 0
+        frame[0] += 1
+
+    stubbed.set_deferred_check(True)
+    try:
+        monkeypatch.setattr(_Event, "auto_land", False)                     # the GPU is behind: no copy has landed
+        items = [stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)[0] for _ in range(ops._RING)]
+        item = items[0]
+        assert all(it is item for it in items) and all(item["ring_pending"]) and _Event.waits == 0
+        # frame 2 overflowed, but nothing may be concluded yet; the ring is full, so the next call waits for the OLDEST slot only
+        stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert _Event.waits == 1
+        stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert _Event.waits == 2
+        with pytest.raises(RuntimeError, match="deferred frame overflowed"):  # slot 2 comes up: frame 2's overflow is seen
+            stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert ops._pool.min_caps[item["key"]] >= 30_000_000
+        # copies land: later frames are checked without blocking, on the grown workspace
+        monkeypatch.setattr(_Event, "auto_land", True)
+        w = _Event.waits
+        it2, _ = stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert it2["cap"] >= 30_000_000
+        stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
+        assert _Event.waits <= w + ops._RING        # only the old workspace's ring was drained (blocking) when it was replaced
+    finally:
+        stubbed.set_deferred_check(False)
+
+
+def test_pool_evicts_least_recently_used_workspaces(stubbed, monkeypatch):
+    dev = torch.device("cpu")
+    monkeypatch.setattr(ops._pool, "budget", 3 * 1024)          # the fake library sizes every workspace at 1024 bytes
+
+    def launch(item, stream):
+        item["stats_np"][:] = 0
+
+    for P in (10, 20, 30, 40, 50):
+        stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, P, 32, 32, fresh_workspace=False)
+    assert [k[2] for k in ops._pool.items] == [30, 40, 50]
+    stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 30, 32, 32, fresh_workspace=False)      # touch: 30 becomes most recent
+    stubbed._run_with_capacity(launch, dev, ops.MODE_FOV, 60, 32, 32, fresh_workspace=False)
+    assert [k[2] for k in ops._pool.items] == [50, 30, 60]
+    ops.release_workspaces()
+    assert len(ops._pool.items) == 0
 
 
 def test_packed_model_cache_state_machine(monkeypatch):
@@ -188,8 +272,8 @@ def test_no_grad_calls_skip_function_apply_and_grad_calls_do_not():
 
 
 def test_stats_dict_reads_unsigned_counters():
-    item = {"stats_np": np.zeros(16, np.int32)}
-    item["stats_np"][0] = -1                                                # 0xFFFFFFFF instances as int32
-    item["stats_np"][2] = 5
+    item = {"stats_np": np.zeros((1, 16), np.int32)}
+    item["stats_np"][0, 0] = -1                                             # 0xFFFFFFFF instances as int32
+    item["stats_np"][0, 2] = 5
     st = ops._stats_dict(item)
     assert st["num_rendered"] == 0xFFFFFFFF and st["num_visible"] == 5 and st["overflow"] == 0
