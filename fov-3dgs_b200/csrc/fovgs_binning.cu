@@ -123,6 +123,10 @@ __device__ __forceinline__ bool project_splat_cov(const CamParams& cam, float mx
 #ifndef PRE_TICKET
 #define PRE_TICKET 64
 #endif
+#ifndef PRE_UNROLL
+#define PRE_UNROLL 2
+#endif
+constexpr int PRE_UNROLL_N = PRE_UNROLL;   // unroll factor of phase B's round loop
 #ifndef SCAT_U
 #define SCAT_U 8
 #endif
@@ -135,24 +139,27 @@ constexpr uint32_t WCHUNK = PRE_WCHUNK;   // staging slots a warp reserves per g
 constexpr uint32_t VCHUNK = 128;   // visible-list slots a warp reserves per global atomic
 constexpr int SHW = 65;            // k_color: floats per staged Gaussian (64 + 1 pad: conflict-free lane-strided reads)
 
+// Per-owner data of phase B, packed so that a candidate lane fetches its owner's parameters with five 16-byte shared loads
+// instead of ~20 scalar ones (lanes of one owner broadcast; phase B is instruction-bound).
 struct WarpSmem {
-    float px[32], py[32], e1x[32], e1y[32], e2x[32], e2y[32], l1[32], l2[32], hl1[32], rw[32];
-    float mnx[32], mxx[32], mny[32], mxy[32];   // extents of the OBB's corners (tile-axis separations of the OBB test)
-    uint32_t dbits[32];
-    int x0[32], y0[32], w[32];
-    uint32_t pref[33];
-    uint32_t gid[32];            // Gaussian id handled by each lane in phases A-C
+    float4 oc[32];               // px, py, e1x, e1y
+    float4 oe[32];               // e2x, e2y, g1, g2:  g_k = len_k + 8 (|e_kx| + |e_ky|)  (reach of tile + OBB along eigen-axis k)
+    float4 ox[32];               // extents of the OBB's corners (tile-axis separations of the OBB test): mnx, mxx, mny, mxy
+    int4 orc[32];                // candidate rectangle: first candidate index (exclusive scan), width, x0, y0
+    uint4 ok[32];                // 1/width (float bits), flags (hcode | single << 8), depth bits, Gaussian id
+    float4 og[32];               // conic (x, y, z) and highest level: parked here across phase B, written out by phase C
+    int rad[32];                 // radius, likewise
+    float l1[32], l2[32], hl1[32];   // only the exact OBB test / the non-integral level test read these
     uint32_t queue[64];          // ids that survived the conservative screen cull, waiting for a full warp of work
     uint32_t nzlist[32];         // lane of the k-th Gaussian with a non-empty candidate rectangle
     uint32_t cnt[32];            // != 0: at least one candidate tile survived (the Gaussian is visible)
-    uint32_t hcode[32];          // FOV: highest_level + 1 when it is one of 1..4 (level-code fast path), else 0
-    uint32_t single[32];         // the ORIGINAL rect is one tile: no OBB test (rasterizer_impl.cu:302-314)
 };
 
 struct ScanSmem {
     uint32_t warp_sums[32];
     uint32_t carry, maxv;
     uint32_t bucket_cnt[33], bucket_base[33];
+    uint32_t bucket_cnt2[68], bucket_base2[68];   // the same by (tile kind, size class): kind 1 = blending tile, classes 34..67
     int is_last;
 };
 
@@ -177,7 +184,8 @@ __device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s);
 
 template <int MODE>
 __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs in) {
-    __shared__ PreSmem sm;
+    extern __shared__ __align__(16) unsigned char pre_smem_raw[];      // sizeof(PreSmem) > 48 KB: opt-in dynamic shared memory
+    PreSmem& sm = *reinterpret_cast<PreSmem*>(pre_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const int n = (int)(sizeof(CamParams) / 4);
@@ -322,7 +330,6 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         __syncwarp();
         if (qn > 32) { const uint32_t v = (32 + lane < (int)qn) ? wm.queue[32 + lane] : 0u; __syncwarp(); wm.queue[lane] = v; }
         qn = qn > 32 ? qn - 32 : 0;
-        wm.gid[lane] = (uint32_t)idx;
         // ---------------- phase A: projection (lane = Gaussian) ----------------
         Splat s;
         float c3[6];
@@ -342,6 +349,8 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
             }
         }
         uint32_t tnum = 0;
+        uint32_t okx = 0, oky = 0, okz = 0;
+        int rcw = 0, rcx = 0, rcy = 0;
         if (ok) {
             const bool single0 = ((uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0)) == 1u;
             int cx0 = s.x0, cy0 = s.y0, cx1 = s.x1, cy1 = s.y1;
@@ -381,14 +390,23 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
             }
             const int cw = max(cx1 - cx0, 0), ch = max(cy1 - cy0, 0);
             tnum = (uint32_t)cw * (uint32_t)ch;
-            wm.single[lane] = single0;
-            wm.px[lane] = s.px; wm.py[lane] = s.py;
-            wm.e1x[lane] = s.e1x; wm.e1y[lane] = s.e1y; wm.e2x[lane] = s.e2x; wm.e2y[lane] = s.e2y;
+            wm.oc[lane] = make_float4(s.px, s.py, s.e1x, s.e1y);
+            wm.oe[lane] = make_float4(s.e2x, s.e2y, s.len1 + 8.0f * (fabsf(s.e1x) + fabsf(s.e1y)),
+                                      s.len2 + 8.0f * (fabsf(s.e2x) + fabsf(s.e2y)));
+            wm.ox[lane] = make_float4(e_mnx, e_mxx, e_mny, e_mxy);
             wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
-            wm.mnx[lane] = e_mnx; wm.mxx[lane] = e_mxx; wm.mny[lane] = e_mny; wm.mxy[lane] = e_mxy;
-            wm.dbits[lane] = __float_as_uint(s.depth);
-            wm.x0[lane] = cx0; wm.y0[lane] = cy0; wm.w[lane] = cw; wm.rw[lane] = 1.0f / (float)max(cw, 1);
-            if (is_foveated(MODE)) { wm.hl1[lane] = FA(hl, 1.0f); wm.hcode[lane] = hcode; }
+            wm.og[lane] = make_float4(s.conx, s.cony, s.conz, hl);
+            wm.rad[lane] = s.radius;
+            if (is_foveated(MODE)) wm.hl1[lane] = FA(hl, 1.0f);
+            if (MODE == MODE_SUM) {
+                // kept for the backward pass; only ever read for Gaussians that end up visible
+#pragma unroll
+                for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
+            }
+            okx = __float_as_uint(1.0f / (float)max(cw, 1));
+            oky = hcode | (single0 ? 256u : 0u);
+            okz = __float_as_uint(s.depth);
+            rcw = cw; rcx = cx0; rcy = cy0;
         }
         wm.cnt[lane] = 0;
         // exclusive scan of the candidate counts over the warp; compact list of non-empty owners
@@ -399,46 +417,66 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const unsigned nz = __ballot_sync(0xffffffffu, tnum > 0);
         cand_total += total;
-        wm.pref[lane] = my_start;
-        if (lane == 31) wm.pref[32] = total;
+        wm.orc[lane] = make_int4((int)my_start, rcw, rcx, rcy);
+        wm.ok[lane] = make_uint4(okx, oky, okz, (uint32_t)idx);
         if (tnum > 0) wm.nzlist[__popc(nz & lt_mask)] = (uint32_t)lane;
         __syncwarp();
 
         // ---------------- phase B: candidate tiles (lane = candidate), 32 per round ----------------
         uint32_t owners_before = 0;   // non-empty owners whose range starts before the current window
-#pragma unroll 2   // two rounds share no registers: the staging stores of round r need not drain before round r+1 starts
+#pragma unroll PRE_UNROLL_N   // two rounds share no registers: the staging stores of round r need not drain before round r+1 starts
         for (uint32_t r = 0; r < total; r += 32) {
             const uint32_t c = r + lane;
             const bool valid = c < total;
             // heads: window positions at which a non-empty owner's range starts
             const unsigned hbit = (tnum > 0 && my_start >= r && my_start < r + 32) ? (1u << (my_start - r)) : 0u;
             const unsigned H = __reduce_or_sync(0xffffffffu, hbit);
-            bool pass = false, single = false;
+            bool pass = false;
             uint32_t tile = 0, owner = 0;
+            uint4 ko = make_uint4(0u, 0u, 0u, 0u);
             if (valid) {
                 owner = wm.nzlist[owners_before + __popc(H & le_mask) - 1];
-                const int t = (int)(c - wm.pref[owner]);
-                const int w = wm.w[owner];
-                int q = (int)(((float)t + 0.5f) * wm.rw[owner]);
+                const int4 rc = wm.orc[owner];
+                ko = wm.ok[owner];
+                const int t = (int)c - rc.x;
+                const int w = rc.y;
+                int q = (int)(((float)t + 0.5f) * __uint_as_float(ko.x));
                 int rem = t - q * w;
                 if (rem < 0) { q--; rem += w; } else if (rem >= w) { q++; rem -= w; }
-                const int ty = wm.y0[owner] + q;
-                const int tx = wm.x0[owner] + rem;
+                const int ty = rc.w + q;
+                const int tx = rc.z + rem;
                 tile = (uint32_t)ty * gx + tx;
-                single = wm.single[owner] != 0;
                 pass = true;
                 if (is_foveated(MODE)) {
-                    const uint32_t hc = wm.hcode[owner];
+                    const uint32_t hc = ko.y & 0xffu;
                     if (MODE == MODE_MMFR) pass = hc ? (sm.lvl_code[tile] == 1) : (ws.tile_skip[tile] == 0);
                     else pass = hc ? (hc >= (uint32_t)sm.lvl_code[tile]) : (ws.tile_min[tile] < wm.hl1[owner]);
                 }
-                if (pass && !single) {
-                    const float cx = wm.px[owner], cy = wm.py[owner];
-                    const float e1x = wm.e1x[owner], e1y = wm.e1y[owner], e2x = wm.e2x[owner], e2y = wm.e2y[owner];
-                    const float l1 = wm.l1[owner], l2 = wm.l2[owner];
+                if (pass && !(ko.y & 256u)) {
+                    // OBB separating-axis test (auxiliary.h:80-168).  The two tile-axis separations are evaluated exactly as the
+                    // reference does (corner extents per splat, see obb_hits_tile_ext).  The two eigen-axis separations compare
+                    // the min / max over the tile's four corners of dot(corner - centre, e_k) with +-len_k; those are affine in
+                    // the tile centre: min/max = dot(tile centre - centre, e_k) -+ 8 (|e_kx| + |e_ky|).  So
+                    //     t_k = |dot(d, e_k)| - g_k,  g_k = len_k + 8 (|e_kx| + |e_ky|)
+                    // decides axis k except within the fp32 rounding of either formulation (a few ulp of |d| terms, bounded by
+                    // eps below); only candidates inside that band — about one in 10^4 — run the reference's corner-by-corner
+                    // arithmetic, so every decision is the reference's decision, bit for bit.
+                    const float4 pc = wm.oc[owner];
+                    const float4 pe = wm.oe[owner];
+                    const float4 px4 = wm.ox[owner];
                     const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
-                    pass = obb_hits_tile_ext(wm.mnx[owner], wm.mxx[owner], wm.mny[owner], wm.mxy[owner], cx, cy, e1x, e1y, e2x, e2y,
-                                             l1, l2, tcx, tcy);
+                    if (FS(px4.y, tcx) < -8.0f || FS(px4.x, tcx) > 8.0f || FS(px4.w, tcy) < -8.0f || FS(px4.z, tcy) > 8.0f) {
+                        pass = false;
+                    } else {
+                        const float dx = tcx - pc.x, dy = tcy - pc.y;
+                        const float t1 = fabsf(fmaf(pc.z, dx, pc.w * dy)) - pe.z;
+                        const float t2 = fabsf(fmaf(pe.x, dx, pe.y * dy)) - pe.w;
+                        const float eps = 4e-6f * (fabsf(dx) + fabsf(dy) + 16.0f);
+                        if (t1 > eps || t2 > eps) pass = false;                        // separated along an eigen-axis, surely
+                        else if (!(t1 < -eps && t2 < -eps))                            // inside the rounding band (or NaN): exact
+                            pass = obb_hits_tile_ext(px4.x, px4.y, px4.z, px4.w, pc.x, pc.y, pc.z, pc.w, pe.x, pe.y, wm.l1[owner],
+                                                     wm.l2[owner], tcx, tcy);
+                    }
                 }
                 // RED (no return value).  Measured alternative: taking the returned rank here so that the scatter needs no
                 // atomics costs k_pre +0.05 ms (even with the dependent store deferred by a round) and saves the scatter
@@ -468,7 +506,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                     const uint32_t pos = chunk_base + chunk_used + __popc(passmask & lt_mask);
                     if (pos < stage_cap) {
                         ws.stage_tile[pos] = tile;
-                        ws.stage_key[pos] = ((uint64_t)wm.dbits[owner] << 32) | wm.gid[owner];
+                        ws.stage_key[pos] = ((uint64_t)ko.z << 32) | ko.w;
                     }
                 }
                 chunk_used += np;
@@ -481,7 +519,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         // ---------------- phase C: per-Gaussian outputs; colour work is queued for k_color ----------------
         const uint32_t count = ok ? wm.cnt[lane] : 0u;
         const bool visible = (idx < in.P) && count > 0;
-        if (idx < in.P) in.radii[idx] = count ? s.radius : 0;
+        if (idx < in.P) in.radii[idx] = count ? wm.rad[lane] : 0;
         const unsigned vismask = __ballot_sync(0xffffffffu, visible);
         const uint32_t nv = __popc(vismask);
         visible_total += nv;
@@ -489,16 +527,15 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         if (visible) {
             constexpr int R = rec_size(MODE);
             float4* rec = ws.rec + (size_t)R * idx;
-            rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
+            const float4 pc = wm.oc[lane];
+            const float4 g = wm.og[lane];
+            const float depth = __uint_as_float(wm.ok[lane].z);
+            rec[0] = make_float4(pc.x, pc.y, g.x, g.y);
             if (is_foveated(MODE)) {
-                rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
+                rec[1] = make_float4(g.z, g.w, depth, 0.0f);
                 lv = (uint32_t)(FOV_LEVELS - 1) << 8;   // all levels
             } else {
-                rec[1] = make_float4(s.conz, in.opacities[idx], s.depth, 0.0f);
-                if (MODE == MODE_SUM) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
-                }
+                rec[1] = make_float4(g.z, in.opacities[idx], depth, 0.0f);
             }
         }
         if (nv) {
@@ -875,6 +912,7 @@ __device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s.carry = 0; s.maxv = 0; }
     if (threadIdx.x < 33) s.bucket_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 68) s.bucket_cnt2[threadIdx.x] = 0;
     __syncthreads();
     uint32_t local_max = 0;
     for (int base = 0; base < T; base += NT) {
@@ -882,9 +920,10 @@ __device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s) {
         const uint32_t v = (i < T) ? __ldcg(&ws.tile_count[(size_t)i * CSTRIDE]) : 0u;
         local_max = max(local_max, v);
         {   // size-class histogram, one shared atomic per distinct class in the warp (a few classes hold most tiles)
-            const int cls = (i < T) ? (v ? 32 - __clz(v) : 0) : 33 + lane;
+            const int kind = (i < T && ws.tile_blend != nullptr && ws.tile_blend[i]) ? 1 : 0;
+            const int cls = (i < T) ? (v ? 32 - __clz(v) : 0) + 34 * kind : 68 + lane;
             const unsigned peers = __match_any_sync(0xffffffffu, cls);
-            if (i < T && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s.bucket_cnt[cls], (uint32_t)__popc(peers));
+            if (i < T && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s.bucket_cnt2[cls], (uint32_t)__popc(peers));
         }
         uint32_t x = v;
 #pragma unroll
@@ -923,32 +962,69 @@ __device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s) {
         ws.hdr->stats.max_tile_instances = s.maxv;
         // tile order for the per-tile kernels: descending power-of-two size class (longest-processing-time-first)
         uint32_t run = 0;
-        for (int b = 32; b >= 0; b--) { s.bucket_base[b] = run; run += s.bucket_cnt[b]; ws.hdr->cum_class[b] = run; }
+#pragma unroll 1
+        for (int b = 32; b >= 0; b--) {
+            s.bucket_cnt[b] = s.bucket_cnt2[b] + s.bucket_cnt2[b + 34];
+            s.bucket_base[b] = run; run += s.bucket_cnt[b]; ws.hdr->cum_class[b] = run;
+        }
         ws.hdr->cum_class[33] = 0;
+        // second order for the lazy blend kernels: blending tiles (kind 1) first, each kind by descending class
+        run = 0;
+#pragma unroll 1
+        for (int k = 1; k >= 0; k--) {
+            const uint32_t at = run;
+#pragma unroll 1
+            for (int b = 32; b >= 0; b--) { s.bucket_base2[b + 34 * k] = run; run += s.bucket_cnt2[b + 34 * k]; }
+            ws.hdr->lazy_count[k] = run - at;
+        }
     }
     __syncthreads();
     for (int base = 0; base < T; base += NT) {
         const int i = base + threadIdx.x;
         const uint32_t c = (i < T) ? __ldcg(&ws.tile_count[(size_t)i * CSTRIDE]) : 0u;
+        const int kind = (i < T && ws.tile_blend != nullptr && ws.tile_blend[i]) ? 1 : 0;
         const int cls = (i < T) ? (c ? 32 - __clz(c) : 0) : 33 + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, cls);
-        const unsigned lower = peers & ((1u << lane) - 1u);
-        uint32_t pos = 0;
-        if (i < T && lower == 0) pos = atomicAdd(&s.bucket_base[cls], (uint32_t)__popc(peers));
-        pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1) + __popc(lower);
-        if (i < T) ws.tile_order[pos] = (uint32_t)i;
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, cls);
+            const unsigned lower = peers & ((1u << lane) - 1u);
+            uint32_t pos = 0;
+            if (i < T && lower == 0) pos = atomicAdd(&s.bucket_base[cls], (uint32_t)__popc(peers));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1) + __popc(lower);
+            if (i < T) ws.tile_order[pos] = (uint32_t)i;
+        }
+        {
+            const int cls2 = (i < T) ? cls + 34 * kind : 68 + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, cls2);
+            const unsigned lower = peers & ((1u << lane) - 1u);
+            uint32_t pos = 0;
+            if (i < T && lower == 0) pos = atomicAdd(&s.bucket_base2[cls2], (uint32_t)__popc(peers));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1) + __popc(lower);
+            if (i < T) ws.tile_order2[pos] = (uint32_t)i;
+        }
     }
 }
 
 cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
     const int need = (in.P + PB - 1) / PB;
     const int grid = max(1, min(need, min(num_sms * PRE_CTAS, (int)STAGE_MAX_BLOCKS)));
+    const size_t smem = sizeof(PreSmem);
+    static PerDeviceOnce once;
+    bool* configured = once.slot();
+    if (!*configured) {
+        cudaError_t e;
+#define PRE_SET(K)                                                                              \
+        e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e != cudaSuccess) return e;
+        PRE_SET(k_pre<MODE_OBB>) PRE_SET(k_pre<MODE_SUM>) PRE_SET(k_pre<MODE_FOV>) PRE_SET(k_pre<MODE_SMFR>) PRE_SET(k_pre<MODE_MMFR>)
+#undef PRE_SET
+        *configured = true;
+    }
     switch (mode) {
-        case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, 0, st>>>(ws, in); break;
-        case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, 0, st>>>(ws, in); break;
-        case MODE_SMFR: k_pre<MODE_SMFR><<<grid, PB, 0, st>>>(ws, in); break;
-        case MODE_MMFR: k_pre<MODE_MMFR><<<grid, PB, 0, st>>>(ws, in); break;
-        default: k_pre<MODE_FOV><<<grid, PB, 0, st>>>(ws, in); break;
+        case MODE_OBB: k_pre<MODE_OBB><<<grid, PB, smem, st>>>(ws, in); break;
+        case MODE_SUM: k_pre<MODE_SUM><<<grid, PB, smem, st>>>(ws, in); break;
+        case MODE_SMFR: k_pre<MODE_SMFR><<<grid, PB, smem, st>>>(ws, in); break;
+        case MODE_MMFR: k_pre<MODE_MMFR><<<grid, PB, smem, st>>>(ws, in); break;
+        default: k_pre<MODE_FOV><<<grid, PB, smem, st>>>(ws, in); break;
     }
     return cudaGetLastError();
 }

@@ -231,6 +231,8 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->pre_done = 0;
             h->pre_chunk = 0;
             h->vis_cursor = 0;
+            h->lazy_ticket[0] = h->lazy_ticket[1] = 0;
+            h->lazy_count[0] = h->lazy_count[1] = 0;
         }
         if (i < FOV_LEVELS * 4) (&h->lvl_bbox[0][0])[i] = ((i & 3) < 2) ? 0x7fffffff : -1;
     }
@@ -297,6 +299,7 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
     ws.tile_offset = (uint32_t*)take((T + 1) * 4);
     ws.tile_cursor = (uint32_t*)take(T * 4 * CSTRIDE);
     ws.tile_order = (uint32_t*)take(T * 4);
+    ws.tile_order2 = (uint32_t*)take(T * 4);
     if (is_foveated(mode)) {
         ws.tile_level = (float*)take(T * 4);
         ws.tile_min = (float*)take(T * 4);

@@ -54,6 +54,9 @@ struct LazySmem {
     uint32_t bucket_cur[256];
     uint32_t wsum[8];
     unsigned long long vary;
+    uint32_t ticket;        // index of the tile this CTA is working on (persistent kernel: drawn from FrameHeader::lazy_ticket)
+    uint32_t consumed;      // frame statistics of the current tile, kept here instead of in registers that live across the
+    uint32_t kept[8];       //   whole tile: instances staged (thread 0) / (warp, splat) pairs that passed block_may_touch
     uint8_t widx[8][256];   // per warp: batch slots whose footprint can reach the warp's 8x4 pixel block
 };
 
@@ -398,8 +401,7 @@ __device__ __forceinline__ const uint64_t* lazy_global_sort(LazySmem& sm, uint64
 template <int KIND, int R, class PIX>
 __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& ws, const uint64_t* sk, const uint32_t m,
                                                  PIX& px, const float pixx, const float pixy, const float blkx,
-                                                 const float blky, const int S1, const int S2, uint32_t& consumed,
-                                                 uint32_t& kept) {
+                                                 const float blky, const int S1, const int S2) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4 r0, r1, r2, r3;
     bool valid;
@@ -424,7 +426,7 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
         }
         __syncthreads();
         const int lim = (int)min(256u, m - b0);
-        consumed += (uint32_t)lim;
+        if (tid == 0) sm.consumed += (uint32_t)lim;
         if (b0 + 256 < m) fetch(b0 + 256 + tid);
         if (__all_sync(0xffffffffu, px.done)) continue;
         uint32_t cnt = 0;
@@ -442,7 +444,7 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
             cnt += __popc(mk);
         }
         __syncwarp();
-        kept += cnt;
+        if (lane == 0) sm.kept[warp] += cnt;
         // four falloff exponents are evaluated together (independent shared loads + FMAs in flight), then applied in
         // list order: the per-pixel sequence of operations is unchanged
         uint32_t k = 0;
@@ -464,6 +466,10 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
 // ---- front-to-back producer of sorted key groups for one tile --------------------------------------------------------
 // `consume(sk, m, last)` is called by the whole CTA with m sorted keys in shared memory, groups in depth order; `last` says
 // no key follows.  It returns true (uniformly) when the tile needs nothing more; the keys behind are then never sorted.
+// One loop, ONE sort site and ONE consume site: the three sources of a group (the whole small tile, the next run of MSD
+// buckets, the next slice of an over-long bucket that was ordered in global memory) only differ in how the keys reach
+// shared memory — the compositing code, which is most of the kernel, is instantiated once (it used to be inlined at three
+// call sites: 170 KB of SASS per instantiation).
 template <class CONSUME>
 __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspace& ws, const int tile, CONSUME&& consume) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -472,138 +478,147 @@ __device__ __forceinline__ void lazy_for_each_group(LazySmem& sm, const Workspac
     const uint32_t n = send - sbeg;
     if (n == 0) return;
     const uint64_t* __restrict__ gA = ws.keysA + sbeg;
-    if (n <= LAZY_DIRECT_MAX) {
-#pragma unroll 4
-        for (uint32_t i = tid; i < n; i += 256) sm.keys[0][i] = gA[i];
-        __syncthreads();
-        const int cur = lazy_sort_group(sm, n);
-        consume(sm.keys[cur], n, true);
-        return;
-    }
-    // ---- MSD partition of the tile's keys by their highest varying depth byte ----
     uint64_t* gB = ws.keysB + sbeg;
-    constexpr int MU = LAZY_MU;   // keys in flight per thread in the partition passes (L2 round trips overlap)
-    // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile).  The position is
-    // guessed from the first 2048 keys (the scatter left them in arbitrary order) and verified for free by the histogram
-    // pass, which ORs the differences of ALL keys; a wrong guess (never seen in practice) repeats the histogram.
-    const uint64_t k0 = gA[0];
-    auto digit_shift = [](uint32_t vhi) { return vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32; };
-    if (tid == 0) sm.vary = 0ull;
-    __syncthreads();
-    {
-        uint64_t v = 0;
-        uint64_t k[MU];
-#pragma unroll
-        for (int u = 0; u < MU; u++) { const uint32_t i = tid + u * 256; k[u] = (i < n) ? gA[i] : k0; }
-#pragma unroll
-        for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
-    }
-    __syncthreads();
-    int shift = digit_shift((uint32_t)(sm.vary >> 32));
-    for (;;) {
-        sm.bucket_cur[tid] = 0;
+    const bool direct = n <= LAZY_DIRECT_MAX;
+    if (!direct) {
+        // ---- MSD partition of the tile's keys by their highest varying depth byte ----
+        constexpr int MU = LAZY_MU;   // keys in flight per thread in the partition passes (L2 round trips overlap)
+        // digit = 8 bits ending at the highest varying depth bit (all higher bits are equal inside the tile).  The position is
+        // guessed from the first 2048 keys (the scatter left them in arbitrary order) and verified for free by the histogram
+        // pass, which ORs the differences of ALL keys; a wrong guess (never seen in practice) repeats the histogram.
+        const uint64_t k0 = gA[0];
+        auto digit_shift = [](uint32_t vhi) { return vhi ? max(32, 32 + (31 - __clz(vhi)) - 7) : 32; };
+        if (tid == 0) sm.vary = 0ull;
         __syncthreads();
-        uint64_t v = 0;
+        {
+            uint64_t v = 0;
+            uint64_t k[MU];
+#pragma unroll
+            for (int u = 0; u < MU; u++) { const uint32_t i = tid + u * 256; k[u] = (i < n) ? gA[i] : k0; }
+#pragma unroll
+            for (int u = 0; u < MU; u++) v |= (k[u] ^ k0);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
+        }
+        __syncthreads();
+        int shift = digit_shift((uint32_t)(sm.vary >> 32));
+        for (;;) {
+            sm.bucket_cur[tid] = 0;
+            __syncthreads();
+            uint64_t v = 0;
+            for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
+                uint64_t k[MU];
+#pragma unroll
+                for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : k0; }
+#pragma unroll
+                for (int u = 0; u < MU; u++) {
+                    v |= (k[u] ^ k0);
+                    if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
+            __syncthreads();
+            const int exact = digit_shift((uint32_t)(sm.vary >> 32));
+            if (exact == shift) break;
+            shift = exact;          // uniform over the CTA: sm.vary is complete after the barrier
+            __syncthreads();
+        }
+        {   // exclusive scan of the 256 bucket sizes
+            const uint32_t c = sm.bucket_cur[tid];
+            uint32_t x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) sm.wsum[tid >> 5] = x;
+            __syncthreads();
+            uint32_t base = x - c;
+            for (int w = 0; w < (tid >> 5); w++) base += sm.wsum[w];
+            sm.bucket_off[tid] = base;
+            if (tid == 255) sm.bucket_off[256] = base + c;
+            sm.bucket_cur[tid] = base;
+        }
+        __syncthreads();
         for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
             uint64_t k[MU];
 #pragma unroll
-            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : k0; }
+            for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
 #pragma unroll
             for (int u = 0; u < MU; u++) {
-                v |= (k[u] ^ k0);
-                if (i0 + u * 256 < n) atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+                if (i0 + u * 256 < n) {
+                    const uint32_t pos = atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
+                    gB[pos] = k[u];
+                }
             }
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicOr(&sm.vary, (unsigned long long)v);
-        __syncthreads();
-        const int exact = digit_shift((uint32_t)(sm.vary >> 32));
-        if (exact == shift) break;
-        shift = exact;          // uniform over the CTA: sm.vary is complete after the barrier
-        __syncthreads();
+        __syncthreads();   // gB is read below by this CTA only
     }
-    {   // exclusive scan of the 256 bucket sizes
-        const uint32_t c = sm.bucket_cur[tid];
-        uint32_t x = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) sm.wsum[tid >> 5] = x;
-        __syncthreads();
-        uint32_t base = x - c;
-        for (int w = 0; w < (tid >> 5); w++) base += sm.wsum[w];
-        sm.bucket_off[tid] = base;
-        if (tid == 255) sm.bucket_off[256] = base + c;
-        sm.bucket_cur[tid] = base;
-    }
-    __syncthreads();
-    for (uint32_t i0 = tid; i0 < n; i0 += 256 * MU) {
-        uint64_t k[MU];
-#pragma unroll
-        for (int u = 0; u < MU; u++) { const uint32_t i = i0 + u * 256; k[u] = (i < n) ? gA[i] : 0ull; }
-#pragma unroll
-        for (int u = 0; u < MU; u++) {
-            if (i0 + u * 256 < n) {
-                const uint32_t pos = atomicAdd(&sm.bucket_cur[(k[u] >> shift) & 0xff], 1u);
-                gB[pos] = k[u];
-            }
-        }
-    }
-    __syncthreads();   // gB is read below by this CTA only
-    // ---- front-to-back over groups of buckets ----
-    int b = 0;
-    bool all_done = false;
+    // ---- front to back: one group per iteration ----
+    int b = 0;                               // next MSD bucket
     // group size grows geometrically: a tile that saturates within its nearest few hundred splats sorts only those, a tile that
     // needs everything pays at most a few extra group boundaries
     uint32_t gcap = LAZY_FIRST_GROUP;
-    while (b < 256 && !all_done) {
-        const uint32_t g0 = sm.bucket_off[b];
-        // buckets [b, e) fit the group together: bucket_off is monotone, so the fitting ones form a prefix — count them
-        int e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= gcap);
-        if (e == b && gcap < (uint32_t)LCAP)   // the next bucket alone exceeds the small cap: take what the buffer holds
-            e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= (uint32_t)LCAP);
-        gcap = min(gcap * 2u, (uint32_t)LCAP);
-        if (e == b) {
-            // one bucket larger than the shared buffer (>= 2048 keys agreeing in all depth bits above `shift`):
-            // order it completely with the block radix sort on the global ping-pong ranges (this tile's slice of
-            // keysA is free scratch after the partition), then hand it over in LCAP-sized slices.
-            const uint32_t bs = sm.bucket_off[b + 1] - g0;
-            const uint64_t* sorted = lazy_global_sort(sm, gB + g0, const_cast<uint64_t*>(gA) + g0, bs);
-            for (uint32_t c0 = 0; c0 < bs && !all_done; c0 += LCAP) {
-                const uint32_t m = min((uint32_t)LCAP, bs - c0);
-                for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = sorted[c0 + i];
-                __syncthreads();
-                all_done = consume(sm.keys[0], m, g0 + c0 + m == n);
-                __syncthreads();
-            }
-            b = b + 1;
+    const uint64_t* big = nullptr;           // an over-long bucket, completely ordered in global memory, handed over in slices
+    uint32_t big_n = 0, big_at = 0, big_g0 = 0;
+    bool first = true;
+    for (;;) {
+        const uint64_t* src;                 // where the group's keys come from
+        uint32_t m, end_pos;                 // group size, position of its end inside the tile's list
+        bool presorted = false;
+        if (direct) {
+            if (!first) break;
+            src = gA; m = n; end_pos = n;
+        } else if (big != nullptr) {
+            m = min((uint32_t)LCAP, big_n - big_at);
+            src = big + big_at; end_pos = big_g0 + big_at + m; presorted = true;
+            big_at += m;
+            if (big_at >= big_n) { big = nullptr; b++; }
         } else {
-            const uint32_t m = sm.bucket_off[e] - g0;
-            if (m) {
-#pragma unroll 4
-                for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = gB[g0 + i];
-                __syncthreads();
-                const int cur = lazy_sort_group(sm, m);
-                all_done = consume(sm.keys[cur], m, g0 + m == n);
-                __syncthreads();
+            if (b >= 256) break;
+            const uint32_t g0 = sm.bucket_off[b];
+            // buckets [b, e) fit the group together: bucket_off is monotone, so the fitting ones form a prefix — count them
+            int e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= gcap);
+            if (e == b && gcap < (uint32_t)LCAP)   // the next bucket alone exceeds the small cap: take what the buffer holds
+                e = b + __syncthreads_count(tid >= b && sm.bucket_off[tid + 1] - g0 <= (uint32_t)LCAP);
+            gcap = min(gcap * 2u, (uint32_t)LCAP);
+            if (e == b) {
+                // one bucket larger than the shared buffer (>= 2048 keys agreeing in all depth bits above `shift`):
+                // order it completely with the block radix sort on the global ping-pong ranges (this tile's slice of
+                // keysA is free scratch after the partition), then hand it over in LCAP-sized slices.
+                big_n = sm.bucket_off[b + 1] - g0;
+                big = lazy_global_sort(sm, gB + g0, const_cast<uint64_t*>(gA) + g0, big_n);
+                big_at = 0; big_g0 = g0;
+                continue;
             }
+            m = sm.bucket_off[e] - g0;
             b = e;
+            if (m == 0) continue;
+            src = gB + g0; end_pos = g0 + m;
         }
+        first = false;
+#pragma unroll 4
+        for (uint32_t i = tid; i < m; i += 256) sm.keys[0][i] = src[i];
+        __syncthreads();
+        const int cur = presorted ? 0 : lazy_sort_group(sm, m);
+        const bool all_done = consume(sm.keys[cur], m, end_pos == n);
+        __syncthreads();
+        if (all_done) break;
     }
 }
 
 template <int KIND, int R, class PIX>
 __device__ __forceinline__ void lazy_tile(LazySmem& sm, const Workspace& ws, const int tile, PIX& px, const float pixx,
                                           const float pixy, const float blkx, const float blky, const int S1, const int S2) {
-    uint32_t consumed = 0, kept = 0;
+    if (threadIdx.x < 8) sm.kept[threadIdx.x] = 0;
+    if (threadIdx.x == 8) sm.consumed = 0;
+    // (the producer's first block barrier orders these stores before any use)
     lazy_for_each_group(sm, ws, tile, [&](const uint64_t* sk, uint32_t m, bool) {
-        return lazy_blend_group<KIND, R>(sm, ws, sk, m, px, pixx, pixy, blkx, blky, S1, S2, consumed, kept);
+        return lazy_blend_group<KIND, R>(sm, ws, sk, m, px, pixx, pixy, blkx, blky, S1, S2);
     });
-    if (threadIdx.x == 0 && consumed) atomicAdd(&ws.hdr->stats.reserved[0], consumed);
-    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);   // (warp, splat) pairs that passed block_may_touch
+    __syncthreads();
+    if (threadIdx.x == 0 && sm.consumed) atomicAdd(&ws.hdr->stats.reserved[0], sm.consumed);
+    if (threadIdx.x < 8 && sm.kept[threadIdx.x]) atomicAdd(&ws.hdr->stats.reserved[1], sm.kept[threadIdx.x]);   // (warp, splat) pairs that passed block_may_touch
 }
 
 // ---- training variant (SUM/forward.cu:298-430) on the lazy producer ---------------------------------------------------
@@ -766,13 +781,16 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
     if (lane == 0 && kept) atomicAdd(&ws.hdr->stats.reserved[1], kept);
 }
 
-template <int MODE, int STAT = STAT_SUM>
-__global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, FrameInputs in) {
-    extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
-    LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
+// ---- one tile: per-pixel state, the lazy producer, the epilogue -------------------------------------------------------
+// BK (foveated modes): 0 = the tile is a plain tile, 1 = a blending tile.  It is a COMPILE-TIME parameter: plain tiles
+// (83 % of a frame) are compiled without the two-level compositing state (PixFovBlend: 12 words against PixFov's 5), the
+// reference makes the same split (renderCUDA at 32 registers, renderCUDA_blending at 40: FOV/cuda_rasterizer/forward.cu:490-609
+// vs :262-476).
+template <int MODE, int STAT, int BK>
+__device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_raw, const Workspace& ws, const FrameInputs& in,
+                                              const int tile) {
     const FrameHeader* __restrict__ hdr = ws.hdr;
     const int W = hdr->cam.W, H = hdr->cam.H, gx = hdr->cam.grid_x;
-    const int tile = (int)ws.tile_order[blockIdx.x];
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x;
 #ifdef FOVGS_TILE_TIMING
@@ -792,7 +810,6 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
     const bool inside = pxi < W && pyi < H;
     const uint32_t pix_id = (uint32_t)W * pyi + pxi;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
     const size_t HW = (size_t)H * W;
     if (is_foveated(MODE)) {
         if (MODE == MODE_MMFR && ws.tile_skip[tile]) {
@@ -800,12 +817,11 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
             if (inside) { in.out_color[pix_id] = 0.f; in.out_color[HW + pix_id] = 0.f; in.out_color[2 * HW + pix_id] = 0.f; }
             return;
         }
-        const bool blending = ws.tile_blend[tile] != 0;
         const float tile_level_f = ws.tile_min[tile];
         const int L1 = (int)tile_level_f;
         constexpr int R = rec_size(MODE);
         const int S1 = (MODE == MODE_FOV) ? 2 + L1 : 2;   // SMFR / MMFR: the one shared (opacity, r, g, b) record
-        if (MODE == MODE_MMFR && blending) {
+        if (MODE == MODE_MMFR && BK) {
             // mmfr_pcheck_obb/cuda_rasterizer/forward.cu:255-418: one composite, weighted by this level's share of the
             // smoothstep; pixels whose level estimate belongs to the other level of the pair do nothing at all
             const float cur_level = hdr->cur_level;
@@ -817,6 +833,7 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
             if (xr < 0.0f && (float)L1i != cur_level) px.done = true;
             lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
             if (inside) {
+                const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
                 const float x = fmaxf(0.0f, fminf(1.0f, xr));
                 const float m3 = FM(x, FM(x, -3.0f));
                 const float nb = FF(x, FM(x, FA(x, x)), m3);
@@ -826,13 +843,12 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
                 in.out_color[HW + pix_id] = FM(FF(bg1, px.T, px.C1), used);
                 in.out_color[2 * HW + pix_id] = FM(FF(bg2, px.T, px.C2), used);
             }
-            return;
-        }
-        if (!blending) {
+        } else if (!BK) {
             PixFov px;
             px.init(inside);
             lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
             if (inside) {
+                const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
                 in.out_color[pix_id] = FF(bg0, px.T, px.C0);
                 in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);
                 in.out_color[2 * HW + pix_id] = FF(bg2, px.T, px.C2);
@@ -845,6 +861,7 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
             px.init(inside, est, L2, FA(tile_level_f, 1.0f));
             lazy_tile<(MODE == MODE_SMFR) ? 3 : 2, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, (MODE == MODE_FOV) ? S1 + 1 : S1);
             if (inside) {
+                const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
                 const float A0 = FF(bg0, px.T1, px.A0), A1 = FF(bg1, px.T1, px.A1), A2 = FF(bg2, px.T1, px.A2);
                 const float B0 = FF(bg0, px.T2, px.B0), B1 = FF(bg1, px.T2, px.B1), B2 = FF(bg2, px.T2, px.B2);
                 const float v = FS(est, FA((float)L1, kStartBlendL));
@@ -859,12 +876,13 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
             }
         }
     } else if (MODE == MODE_SUM) {
-        SumSmemExtra& sx = *reinterpret_cast<SumSmemExtra*>(lazy_smem_raw + sizeof(LazySmem));
+        SumSmemExtra& sx = *reinterpret_cast<SumSmemExtra*>(smem_raw + sizeof(LazySmem));
         float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
         uint32_t last_contributor = 0;
         int max_idx = 0;
         lazy_tile_sum<STAT>(sm, sx, ws, in, tile, inside, pixx, pixy, blkx, blky, T, C0, C1, C2, last_contributor, max_idx);
         if (inside) {
+            const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
             if (STAT == STAT_LWMC) atomicAdd(&in.contributions[max_idx], in.loss_map[pix_id]);
             ws.final_T[pix_id] = T;
             ws.n_contrib[pix_id] = last_contributor;
@@ -877,6 +895,7 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
         px.init(inside);
         lazy_tile<0, REC_PS1>(sm, ws, tile, px, pixx, pixy, blkx, blky, 0, 0);
         if (inside) {
+            const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
             in.out_color[pix_id] = FF(bg0, px.T, px.C0);
             in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);
             in.out_color[2 * HW + pix_id] = FF(bg2, px.T, px.C2);
@@ -884,35 +903,94 @@ __global__ void __launch_bounds__(256, LAZY_CTAS) k_lazy_blend(Workspace ws, Fra
     }
 }
 
+// ---- the kernel: persistent CTAs draw tiles of ONE kind, heaviest first, from a ticket counter ---------------------------
+// A foveated frame launches it twice: BK = 1 (blending tiles) then BK = 0 (plain tiles).  The two launches are independent
+// (disjoint tiles, disjoint pixels), so the second is a programmatic dependent launch: the first calls
+// griddepcontrol.launch_dependents on entry, and the plain-tile CTAs move onto the SMs as the blending-tile CTAs run out
+// of tickets and exit — no idle tail between them.  The second grid's CTAs execute griddepcontrol.wait before THEY exit, so
+// the stream (next stage, next frame) only proceeds once both grids are complete and flushed.
+#ifndef LAZY_CTAS_BLEND
+#define LAZY_CTAS_BLEND 3      // blending-tile instantiations: 80 registers
+#endif
+template <int MODE, int STAT = STAT_SUM, int BK = 0>
+__global__ void __launch_bounds__(256, BK ? LAZY_CTAS_BLEND : LAZY_CTAS) k_lazy_blend(Workspace ws, FrameInputs in, int pdl) {
+    extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
+    LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
+    if (pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    FrameHeader* hdr = ws.hdr;
+    // tile_order2 = [blending tiles, heaviest first][plain tiles, heaviest first]
+    const uint32_t count = hdr->lazy_count[BK];
+    const uint32_t base = BK ? 0u : hdr->lazy_count[1];
+    for (;;) {
+        if (threadIdx.x == 0) sm.ticket = atomicAdd(&hdr->lazy_ticket[BK], 1u);
+        __syncthreads();
+        const uint32_t t = sm.ticket;
+        if (t >= count) break;
+        lazy_one_tile<MODE, STAT, BK>(sm, lazy_smem_raw, ws, in, (int)ws.tile_order2[base + t]);
+        __syncthreads();      // the tile's shared memory (and sm.ticket) is free again
+    }
+    if (pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <class K>
+static cudaError_t launch_lazy_kernel(K kernel, int grid, size_t smem, cudaStream_t st, bool dependent, const Workspace& ws,
+                                      const FrameInputs& in, int pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (dependent) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, ws, in, pdl);
+}
+
+bool g_no_pdl = false;   // fovgs_set_option(FOVGS_OPT_NO_PDL, 1): the two blend launches of a foveated frame run back to back
+
 cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T, Mode mode, cudaStream_t st) {
     const size_t smem = sizeof(LazySmem), smem_sum = sizeof(LazySmem) + sizeof(SumSmemExtra);
     static PerDeviceOnce once;
     bool* configured = once.slot();
     if (!*configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_lazy_blend<MODE_FOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e;
+#define LAZY_SET(K, BYTES)                                                                          \
+        e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_OBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SMFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_MMFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_lazy_blend<MODE_SUM, STAT_LWMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum);
-        if (e != cudaSuccess) return e;
+        LAZY_SET((k_lazy_blend<MODE_FOV, STAT_SUM, 0>), smem) LAZY_SET((k_lazy_blend<MODE_FOV, STAT_SUM, 1>), smem)
+        LAZY_SET((k_lazy_blend<MODE_SMFR, STAT_SUM, 0>), smem) LAZY_SET((k_lazy_blend<MODE_SMFR, STAT_SUM, 1>), smem)
+        LAZY_SET((k_lazy_blend<MODE_MMFR, STAT_SUM, 0>), smem) LAZY_SET((k_lazy_blend<MODE_MMFR, STAT_SUM, 1>), smem)
+        LAZY_SET((k_lazy_blend<MODE_OBB, STAT_SUM, 0>), smem)
+        LAZY_SET((k_lazy_blend<MODE_SUM, STAT_SUM, 0>), smem_sum) LAZY_SET((k_lazy_blend<MODE_SUM, STAT_MAX, 0>), smem_sum)
+        LAZY_SET((k_lazy_blend<MODE_SUM, STAT_LWMC, 0>), smem_sum)
+#undef LAZY_SET
         *configured = true;
     }
-    if (mode == MODE_FOV) k_lazy_blend<MODE_FOV><<<T, 256, smem, st>>>(ws, in);
-    else if (mode == MODE_SMFR) k_lazy_blend<MODE_SMFR><<<T, 256, smem, st>>>(ws, in);
-    else if (mode == MODE_MMFR) k_lazy_blend<MODE_MMFR><<<T, 256, smem, st>>>(ws, in);
-    else if (mode == MODE_SUM && in.stat == STAT_MAX) k_lazy_blend<MODE_SUM, STAT_MAX><<<T, 256, smem_sum, st>>>(ws, in);
-    else if (mode == MODE_SUM && in.stat == STAT_LWMC) k_lazy_blend<MODE_SUM, STAT_LWMC><<<T, 256, smem_sum, st>>>(ws, in);
-    else if (mode == MODE_SUM) k_lazy_blend<MODE_SUM, STAT_SUM><<<T, 256, smem_sum, st>>>(ws, in);
-    else k_lazy_blend<MODE_OBB><<<T, 256, smem, st>>>(ws, in);
-    return cudaGetLastError();
+    const int sms = device_sm_count();
+    const int grid0 = max(1, min(T, sms * LAZY_CTAS)), grid1 = max(1, min(T, sms * LAZY_CTAS_BLEND));
+    if (is_foveated(mode)) {
+        // blending tiles first (each costs two composites), then the plain tiles as a programmatic dependent launch
+        const bool pdl = !g_no_pdl;
+        cudaError_t e;
+        if (mode == MODE_FOV) e = launch_lazy_kernel(k_lazy_blend<MODE_FOV, STAT_SUM, 1>, grid1, smem, st, false, ws, in, pdl ? 1 : 0);
+        else if (mode == MODE_SMFR) e = launch_lazy_kernel(k_lazy_blend<MODE_SMFR, STAT_SUM, 1>, grid1, smem, st, false, ws, in, pdl ? 1 : 0);
+        else e = launch_lazy_kernel(k_lazy_blend<MODE_MMFR, STAT_SUM, 1>, grid1, smem, st, false, ws, in, pdl ? 1 : 0);
+        if (e != cudaSuccess) return e;
+        if (mode == MODE_FOV) e = launch_lazy_kernel(k_lazy_blend<MODE_FOV, STAT_SUM, 0>, grid0, smem, st, pdl, ws, in, pdl ? 2 : 0);
+        else if (mode == MODE_SMFR) e = launch_lazy_kernel(k_lazy_blend<MODE_SMFR, STAT_SUM, 0>, grid0, smem, st, pdl, ws, in, pdl ? 2 : 0);
+        else e = launch_lazy_kernel(k_lazy_blend<MODE_MMFR, STAT_SUM, 0>, grid0, smem, st, pdl, ws, in, pdl ? 2 : 0);
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    cudaError_t e;
+    if (mode == MODE_SUM && in.stat == STAT_MAX) e = launch_lazy_kernel(k_lazy_blend<MODE_SUM, STAT_MAX, 0>, grid0, smem_sum, st, false, ws, in, 0);
+    else if (mode == MODE_SUM && in.stat == STAT_LWMC) e = launch_lazy_kernel(k_lazy_blend<MODE_SUM, STAT_LWMC, 0>, grid0, smem_sum, st, false, ws, in, 0);
+    else if (mode == MODE_SUM) e = launch_lazy_kernel(k_lazy_blend<MODE_SUM, STAT_SUM, 0>, grid0, smem_sum, st, false, ws, in, 0);
+    else e = launch_lazy_kernel(k_lazy_blend<MODE_OBB, STAT_SUM, 0>, grid0, smem, st, false, ws, in, 0);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace fovgs

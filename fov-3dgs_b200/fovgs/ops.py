@@ -636,16 +636,19 @@ def backward_ps1(workspace_item, means3D, radii, scales, rotations, cov3D_precom
     shs = _prep(shs, "shs", device, optional=True)
     colors_precomp = _prep(colors_precomp, "colors_precomp", device, optional=True)
     M = 0 if shs is None else int(shs.size(1))
-    opts = dict(dtype=torch.float32, device=device)
-    dL_dmeans3D = torch.zeros((P, 3), **opts)
-    dL_dmeans2D = torch.zeros((P, 3), **opts)
-    dL_dcolors = torch.zeros((P, 3), **opts)
-    dL_dconic = torch.zeros((P, 2, 2), **opts)
-    dL_dopacity = torch.zeros((P, 1), **opts)
-    dL_dcov3D = torch.zeros((P, 6), **opts)
-    dL_dsh = torch.zeros((P, M, 3), **opts)
-    dL_dscales = torch.zeros((P, 3), **opts)
-    dL_drotations = torch.zeros((P, 4), **opts)
+    # The reference zero-fills nine gradient tensors with nine launches (SUM/rasterize_points.cu:171-179; 300 B per Gaussian).
+    # Here they are nine views of ONE zero-filled slab: one allocation, one memset (blocks start on 256-byte boundaries: the
+    # per-Gaussian kernel writes dL/dsh rows with 16-byte bulk stores).
+    widths = (3, 3, 3, 4, 1, 6, 3 * M, 3, 4)      # means3D, means2D, colors, conic, opacity, cov3D, sh, scales, rotations
+    offs, total = [], 0
+    for w in widths:
+        offs.append(total)
+        total += (P * w + 63) // 64 * 64
+    slab = torch.zeros((max(total, 1),), dtype=torch.float32, device=device)
+    view = lambda i, shape: slab[offs[i]:offs[i] + P * widths[i]].view(shape)
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors = view(0, (P, 3)), view(1, (P, 3)), view(2, (P, 3))
+    dL_dconic, dL_dopacity, dL_dcov3D = view(3, (P, 2, 2)), view(4, (P, 1)), view(5, (P, 6))
+    dL_dsh, dL_dscales, dL_drotations = view(6, (P, M, 3)), view(7, (P, 3)), view(8, (P, 4))
     if P != 0:
         if workspace_item is None:
             raise RuntimeError("backward_ps1 needs the workspace of the matching forward call")
@@ -662,7 +665,7 @@ def backward_ps1(workspace_item, means3D, radii, scales, rotations, cov3D_precom
         a.colors_precomp = _ptr(colors_precomp)
         a.radii = radii.contiguous().data_ptr()
         a.dL_dout_color = g.data_ptr()
-        a.workspace = workspace_item["ws"].data_ptr()
+        a.workspace = workspace_item["ws_ptr"]
         a.workspace_bytes = workspace_item["bytes"]
         a.max_instances = workspace_item["cap"]
         a.dL_dmeans2D = dL_dmeans2D.data_ptr()

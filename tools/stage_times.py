@@ -15,7 +15,11 @@ def main():
     ap.add_argument("--variant", default="sum"); ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--size", default="big"); ap.add_argument("--backward", action="store_true")
     ap.add_argument("--split", default="0", help="comma list of FOVGS_OPT_SPLIT_STAGES settings to run, e.g. 0,1")
+    ap.add_argument("--no-pdl", action="store_true", help="FOVGS_OPT_NO_PDL: the two blend launches run back to back")
     a = ap.parse_args()
+    if a.no_pdl:
+        from fovgs._lib import lib
+        assert lib().fovgs_set_option(3, 1) == 0
     if a.size == "big": scn = synth.make_scene_bicycle(6000000, 1); cams = synth.ring_cameras(30)
     else: scn = synth.make_scene_bicycle(300000, 1, log_scale_mu=-3.6); cams = synth.ring_cameras(30, 800, 600)
     bg = torch.zeros(3, device="cuda")
