@@ -147,8 +147,6 @@ struct WarpSmem {
     float4 ox[32];               // extents of the OBB's corners (tile-axis separations of the OBB test): mnx, mxx, mny, mxy
     int4 orc[32];                // candidate rectangle: first candidate index (exclusive scan), width, x0, y0
     uint4 ok[32];                // 1/width (float bits), flags (hcode | single << 8), depth bits, Gaussian id
-    float4 og[32];               // conic (x, y, z) and highest level: parked here across phase B, written out by phase C
-    int rad[32];                 // radius, likewise
     float l1[32], l2[32], hl1[32];   // only the exact OBB test / the non-integral level test read these
     uint32_t queue[64];          // ids that survived the conservative screen cull, waiting for a full warp of work
     uint32_t nzlist[32];         // lane of the k-th Gaussian with a non-empty candidate rectangle
@@ -174,7 +172,7 @@ struct PreSmem {
     // FOV: per tile the smallest h in {1,2,3,4} with tile_min < h (5: none).  A Gaussian with integral highest_level passes
     // `tile_min < highest_level + 1` (rasterizer_impl.cu:307,344) iff highest_level + 1 >= code: the per-candidate level
     // test reads one shared byte instead of gathering a float through L1.
-    uint8_t lvl_code[LC_MAX];
+    alignas(16) uint8_t lvl_code[LC_MAX];
     WarpSmem w[WPB];
     ScanSmem scan;
 };
@@ -205,16 +203,11 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
             sm.cull_k = fmaxf(n0, fmaxf(n1, n2)) * fmaxf(fxk, fyk) * 1.001f;
         }
         if (is_foveated(MODE)) {
+            // per-tile level codes (written by k_tile_infos): 16 bytes per load, two independent loads per thread at 1080p
             const int T = ws.hdr->tiles;
             if (T <= LC_MAX)
-                for (int i = tid; i < T; i += PB) {
-                    if (MODE == MODE_MMFR) {
-                        sm.lvl_code[i] = ws.tile_skip[i] ? 5 : 1;      // every Gaussian carries code 1: passes iff not skipped
-                    } else {
-                        const float tm = ws.tile_min[i];
-                        sm.lvl_code[i] = (uint8_t)((tm < 1.0f) ? 1 : (tm < 2.0f) ? 2 : (tm < 3.0f) ? 3 : (tm < 4.0f) ? 4 : 5);
-                    }
-                }
+                for (int i = tid * 16; i < T; i += PB * 16)
+                    *reinterpret_cast<uint4*>(&sm.lvl_code[i]) = *reinterpret_cast<const uint4*>(&ws.tile_code[i]);
         }
     }
     __syncthreads();   // the only block barrier: from here on warps never wait for each other
@@ -395,8 +388,6 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                                       s.len2 + 8.0f * (fabsf(s.e2x) + fabsf(s.e2y)));
             wm.ox[lane] = make_float4(e_mnx, e_mxx, e_mny, e_mxy);
             wm.l1[lane] = s.len1; wm.l2[lane] = s.len2;
-            wm.og[lane] = make_float4(s.conx, s.cony, s.conz, hl);
-            wm.rad[lane] = s.radius;
             if (is_foveated(MODE)) wm.hl1[lane] = FA(hl, 1.0f);
             if (MODE == MODE_SUM) {
                 // kept for the backward pass; only ever read for Gaussians that end up visible
@@ -519,7 +510,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         // ---------------- phase C: per-Gaussian outputs; colour work is queued for k_color ----------------
         const uint32_t count = ok ? wm.cnt[lane] : 0u;
         const bool visible = (idx < in.P) && count > 0;
-        if (idx < in.P) in.radii[idx] = count ? wm.rad[lane] : 0;
+        if (idx < in.P) in.radii[idx] = count ? s.radius : 0;
         const unsigned vismask = __ballot_sync(0xffffffffu, visible);
         const uint32_t nv = __popc(vismask);
         visible_total += nv;
@@ -527,15 +518,12 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         if (visible) {
             constexpr int R = rec_size(MODE);
             float4* rec = ws.rec + (size_t)R * idx;
-            const float4 pc = wm.oc[lane];
-            const float4 g = wm.og[lane];
-            const float depth = __uint_as_float(wm.ok[lane].z);
-            rec[0] = make_float4(pc.x, pc.y, g.x, g.y);
+            rec[0] = make_float4(s.px, s.py, s.conx, s.cony);
             if (is_foveated(MODE)) {
-                rec[1] = make_float4(g.z, g.w, depth, 0.0f);
+                rec[1] = make_float4(s.conz, hl, s.depth, 0.0f);
                 lv = (uint32_t)(FOV_LEVELS - 1) << 8;   // all levels
             } else {
-                rec[1] = make_float4(g.z, in.opacities[idx], depth, 0.0f);
+                rec[1] = make_float4(s.conz, in.opacities[idx], s.depth, 0.0f);
             }
         }
         if (nv) {

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                     const float power = gauss_power(a.z, a.w, sB[j].x, dx, dy);
                     if (power > 0.0f || power < -4.5f) continue;
                     const float4 c = sC[j];
-                    const float alpha = fminf(0.99f, FM(c.x, expf(power)));
+                    const float alpha = fminf(0.99f, FM(c.x, BLEND_EXP(power)));
                     if (alpha < 1.0f / 255.0f) continue;
                     const float test_T = FM(T, FS(1.0f, alpha));
                     if (test_T < 0.0001f) { done = true; continue; }
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                     const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
                     const float power = gauss_power(a.z, a.w, b.x, dx, dy);
                     if (power > 0.0f || power < -4.5f) continue;
-                    const float e = expf(power);
+                    const float e = BLEND_EXP(power);
                     if (SMFR) {
                         // naive_pcheck_obb/cuda_rasterizer/forward.cu:383-430: one alpha for both levels; a live L1 drops
                         // the entry for both when alpha < 1/255, a finished L1 lets it through to L2 untested
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             const float power = gauss_power(a.z, a.w, b.x, dx, dy);
             if (power > 0.0f || power < -4.5f) continue;
             if (MODE == MODE_SUM && stat == STAT_MAX) atomicAdd(&in.gaussians_count[sId[j]], 1);
-            const float alpha = fminf(0.99f, FM(b.y, expf(power)));
+            const float alpha = fminf(0.99f, FM(b.y, BLEND_EXP(power)));
             if (alpha < 1.0f / 255.0f) continue;
             const float test_T = FM(T, FS(1.0f, alpha));
             if (test_T < 0.0001f) { done = true; continue; }

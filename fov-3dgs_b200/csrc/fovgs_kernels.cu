@@ -112,7 +112,7 @@ __global__ void k_tile_infos(int T, const float* __restrict__ tile_levels, const
                              const int tile_height_num, float* __restrict__ grad_y, float* __restrict__ grad_x,
                              float* __restrict__ tile_level_min, uint8_t* __restrict__ tile_blendings,
                              FrameHeader* __restrict__ hdr, const int mmfr, const float cur_level,
-                             uint8_t* __restrict__ tile_skips) {
+                             uint8_t* __restrict__ tile_skips, uint8_t* __restrict__ tile_code) {
     auto idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool blend = false, skip = false;
     if (idx < (uint64_t)T) {
@@ -148,6 +148,10 @@ __global__ void k_tile_infos(int T, const float* __restrict__ tile_levels, const
         float tile_min_i = float(int(tile_min));
         blend = ((tile_min - tile_min_i) > kStartBlend && (tile_min_i < (FOV_LEVELS - 1)));
         tile_blendings[idx] = blend ? 1 : 0;
+        // k_pre's per-candidate level test as one byte: the smallest h in {1,2,3,4} with tile_min < h (5: none); a Gaussian
+        // whose highest level is an integer l passes `tile_min < l + 1` iff l + 1 >= code.  MMFR: 1 = tile of this call, 5 = skipped.
+        tile_code[idx] = mmfr ? (uint8_t)(skip ? 5 : 1)
+                              : (uint8_t)((tile_min < 1.0f) ? 1 : (tile_min < 2.0f) ? 2 : (tile_min < 3.0f) ? 3 : (tile_min < 4.0f) ? 4 : 5);
         grad_y[idx] = gy;
         grad_x[idx] = gx;
     }
@@ -306,6 +310,7 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
         ws.tile_gx = (float*)take(T * 4);
         ws.tile_gy = (float*)take(T * 4);
         ws.tile_blend = (uint8_t*)take(T);
+        ws.tile_code = (uint8_t*)take((T + 15) / 16 * 16);
         if (mode == MODE_MMFR) ws.tile_skip = (uint8_t*)take(T);   // after the tables every foveated layout shares
     }
     ws.rec = (float4*)take((size_t)P * 16 * rec_size(mode));
@@ -363,7 +368,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     if (is_foveated(mode)) {
         k_tile_levels<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, gaze, a.W, a.H, a.gx, alpha);
         k_tile_infos<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, a.gx, a.gy, ws.tile_gy, ws.tile_gx, ws.tile_min,
-                                                     ws.tile_blend, ws.hdr, mode == MODE_MMFR ? 1 : 0, cur_level, ws.tile_skip);
+                                                     ws.tile_blend, ws.hdr, mode == MODE_MMFR ? 1 : 0, cur_level, ws.tile_skip, ws.tile_code);
     }
     return cudaGetLastError();
 }

@@ -20,6 +20,7 @@
 // + fovgs_blend.cu).
 #include <type_traits>
 #include "fovgs_internal.cuh"
+#include "fovgs_tma.cuh"
 
 namespace fovgs {
 
@@ -27,7 +28,24 @@ namespace fovgs {
 __device__ uint32_t g_tile_times[4 * 65536];
 #endif
 
-constexpr int LCAP = 2048;
+#ifndef LAZY_LCAP
+#define LAZY_LCAP 1024          // keys of one sorted group held in shared memory (two buffers of LCAP u64); A/B: 2048 is 3 % slower
+#endif
+constexpr int LCAP = LAZY_LCAP;
+// How a 256-batch of blend records (3-4 float4 per sorted instance, gathered by Gaussian id) reaches shared memory:
+//   0  register-staged: LDG into registers, STS after the barrier; LAZY_PREFETCH=1 loads the next batch one batch ahead
+//      (12-16 live registers across the compositing loop), LAZY_PREFETCH=0 loads it when it is needed (latency exposed)
+//      [default: LAZY_STAGE 0 with LAZY_PREFETCH 0 — measured fastest, see profiles/README.md "staging A/B"]
+//   1  cp.async (LDGSTS), double buffered: the next batch flies global -> shared while the current one is composited,
+//      no registers, no STS; costs a second 16 KB staging buffer per CTA (less L1 left for the gathers)
+//   2  cp.async.bulk (TMA, UBLKCP) + one mbarrier per buffer, double buffered: same data flow through the bulk-copy engine
+#ifndef LAZY_STAGE
+#define LAZY_STAGE 0
+#endif
+#ifndef LAZY_PREFETCH
+#define LAZY_PREFETCH 0
+#endif
+constexpr int NSTAGE = LAZY_STAGE ? 2 : 1;
 #ifndef LAZY_FIRST_GROUP
 #define LAZY_FIRST_GROUP 512u   // first sorted group of a partitioned tile; doubles up to LCAP
 #endif
@@ -38,7 +56,7 @@ constexpr int LCAP = 2048;
 #define LAZY_MU 8
 #endif
 #ifndef LAZY_DIRECT_MAX
-#define LAZY_DIRECT_MAX 2048u    // tiles up to this many instances are sorted whole in shared memory (<= LCAP)
+#define LAZY_DIRECT_MAX ((uint32_t)LAZY_LCAP)    // tiles up to this many instances are sorted whole in shared memory (<= LCAP)
 #endif
 constexpr float kStartBlendL = 0.5f;
 
@@ -48,8 +66,10 @@ struct LazySmem {
     uint64_t keys[2][LCAP];
     union {                 // a tile alternates sort and composite phases (block barriers in between): one footprint
         SortScratch srt;
-        BlendStage bl;
+        BlendStage bl[NSTAGE];
     };
+    alignas(8) uint64_t bar[2];   // LAZY_STAGE 2: completion barrier of each staging buffer
+    uint32_t stage_parity;        // LAZY_STAGE 2: phase bits of the two barriers (they live as long as the kernel, across groups and tiles)
     uint32_t bucket_off[257];
     uint32_t bucket_cur[256];
     uint32_t wsum[8];
@@ -72,7 +92,11 @@ __device__ __forceinline__ bool block_may_touch(const float4 a, const float conz
     if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
     const float A = a.z, B = a.w, C = conz;
     const float tau = fminf(4.5f, __logf(255.0f * op));
-    const float iA = __frcp_rn(A), iC = __frcp_rn(C);
+    // MUFU.RCP (1 ulp) instead of the IEEE reciprocal (8 instructions each): the clamped parabola minimum moves by second order
+    // in the error of t, far inside the slack of the final comparison
+    float iA, iC;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(A));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iC) : "f"(C));
     auto edge_x = [&](float ex) {   // dx fixed
         const float t = fminf(fmaxf(-B * ex * iC, dy0), dy1);
         return 0.5f * A * ex * ex + B * ex * t + 0.5f * C * t * t;
@@ -92,18 +116,18 @@ struct PixPS1 {      // OBB/forward.cu:251-384
     float T, C0, C1, C2;
     bool done;
     __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
-    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.bl.sA[j];
+    __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
+        const float4 a = bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, bl.sB[j].x, dx, dy);
     }
     // One divergent region per splat (the falloff cut, which most lanes fail); the two rarer outcomes inside it — alpha below
     // 1/255, pixel saturated — are selects, not branches: same values, no reconvergence barriers in the inner loop.
-    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
+    __device__ __forceinline__ void apply(const BlendStage& bl, int j, float power) {
         if (done || power > 0.0f || power < -4.5f) return;
-        const float4 b = sm.bl.sB[j];
-        const float4 c = sm.bl.sC[j];
-        const float alpha = fminf(0.99f, FM(b.y, expf(power)));
+        const float4 b = bl.sB[j];
+        const float4 c = bl.sC[j];
+        const float alpha = fminf(0.99f, FM(b.y, BLEND_EXP(power)));
         const float test_T = FM(T, FS(1.0f, alpha));
         const bool vis = !(alpha < 1.0f / 255.0f);
         const bool fin = vis && test_T < 0.0001f;
@@ -118,15 +142,15 @@ struct PixFov {      // FOV/forward.cu:490-609
     float T, C0, C1, C2;
     bool done;
     __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
-    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.bl.sA[j];
+    __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
+        const float4 a = bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, bl.sB[j].x, dx, dy);
     }
-    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {   // see PixPS1::apply
+    __device__ __forceinline__ void apply(const BlendStage& bl, int j, float power) {   // see PixPS1::apply
         if (done || power > 0.0f || power < -4.5f) return;
-        const float4 c = sm.bl.sC[j];
-        const float alpha = fminf(0.99f, FM(c.x, expf(power)));
+        const float4 c = bl.sC[j];
+        const float alpha = fminf(0.99f, FM(c.x, BLEND_EXP(power)));
         const float test_T = FM(T, FS(1.0f, alpha));
         const bool vis = !(alpha < 1.0f / 255.0f);
         const bool fin = vis && test_T < 0.0001f;
@@ -144,17 +168,17 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
         T1 = T2 = 1.0f; A0 = A1 = A2 = B0 = B1 = B2 = 0.f; L2_f = l2f;
         L1_done = est > (float)L2; L2_done = false; done = !inside;
     }
-    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.bl.sA[j];
+    __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
+        const float4 a = bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, bl.sB[j].x, dx, dy);
     }
-    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {   // selects, not branches: see PixPS1::apply
+    __device__ __forceinline__ void apply(const BlendStage& bl, int j, float power) {   // selects, not branches: see PixPS1::apply
         if (done || power > 0.0f || power < -4.5f) return;
-        const float4 b = sm.bl.sB[j];
-        const float4 c1 = sm.bl.sC[j];
-        const float4 c2 = sm.bl.sD[j];
-        const float e = expf(power);
+        const float4 b = bl.sB[j];
+        const float4 c1 = bl.sC[j];
+        const float4 c2 = bl.sD[j];
+        const float e = BLEND_EXP(power);
         {
             const float alpha1 = fminf(0.99f, FM(c1.x, e));
             const float test_T1 = FM(T1, FS(1.0f, alpha1));
@@ -188,16 +212,16 @@ struct PixSmfrBlend {  // naive_pcheck_obb/cuda_rasterizer/forward.cu:262-440: o
         T1 = T2 = 1.0f; A0 = A1 = A2 = B0 = B1 = B2 = 0.f; L2_f = l2f;
         L1_done = est > (float)L2; L2_done = false; done = !inside;
     }
-    __device__ __forceinline__ float power(const LazySmem& sm, int j, float pixx, float pixy) const {
-        const float4 a = sm.bl.sA[j];
+    __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
+        const float4 a = bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
-        return gauss_power(a.z, a.w, sm.bl.sB[j].x, dx, dy);
+        return gauss_power(a.z, a.w, bl.sB[j].x, dx, dy);
     }
-    __device__ __forceinline__ void apply(const LazySmem& sm, int j, float power) {
+    __device__ __forceinline__ void apply(const BlendStage& bl, int j, float power) {
         if (power > 0.0f || power < -4.5f) return;
-        const float4 b = sm.bl.sB[j];
-        const float4 c = sm.bl.sC[j];
-        const float alpha1 = fminf(0.99f, FM(c.x, expf(power)));
+        const float4 b = bl.sB[j];
+        const float4 c = bl.sC[j];
+        const float alpha1 = fminf(0.99f, FM(c.x, BLEND_EXP(power)));
         if (!L1_done) {
             // a live L1 drops the entry for BOTH levels (:403-405); once L1 is done the alpha test no longer applies
             if (alpha1 < 1.0f / 255.0f) return;
@@ -403,6 +427,9 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
                                                  PIX& px, const float pixx, const float pixy, const float blkx,
                                                  const float blky, const int S1, const int S2) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* __restrict__ wl = sm.widx[warp];
+    const uint32_t* __restrict__ wl4 = reinterpret_cast<const uint32_t*>(sm.widx[warp]);
+#if LAZY_STAGE == 0
     float4 r0, r1, r2, r3;
     bool valid;
     auto fetch = [&](uint32_t pos) {
@@ -415,19 +442,75 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
             if (KIND == 2) r3 = rec[S2];
         }
     };
-    fetch(tid);
-    uint8_t* __restrict__ wl = sm.widx[warp];
-    const uint32_t* __restrict__ wl4 = reinterpret_cast<const uint32_t*>(sm.widx[warp]);
-    for (uint32_t b0 = 0; b0 < m; b0 += 256) {
-        if (__syncthreads_count(px.done) == 256) return true;
+    if (LAZY_PREFETCH) fetch(tid);
+#else
+    // asynchronous staging: thread t copies the records of instance b0 + t straight into slot t of a staging buffer
+    uint32_t parity = sm.stage_parity;      // LAZY_STAGE 2: phase bits of the two mbarriers (uniform over the CTA)
+    auto issue = [&](uint32_t b0, int buf) {
+        const uint32_t pos = b0 + tid;
+        BlendStage& st = sm.bl[buf];
+        const bool valid = pos < m;
+        const float4* __restrict__ rec = nullptr;
+        if (valid) rec = ws.rec + (size_t)R * (uint32_t)sk[pos];
+        const float4* __restrict__ c1 = (KIND == 0) ? rec + 2 : rec + S1;
+#if LAZY_STAGE == 1
         if (valid) {
-            sm.bl.sA[tid] = r0; sm.bl.sB[tid] = r1; sm.bl.sC[tid] = r2;
-            if (KIND == 2) sm.bl.sD[tid] = r3;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&st.sA[tid])), "l"(rec) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&st.sB[tid])), "l"(rec + 1) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&st.sC[tid])), "l"(c1) : "memory");
+            if (KIND == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&st.sD[tid])), "l"(rec + S2) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+        mbar_arrive_expect_tx(&sm.bar[buf], valid ? (KIND == 2 ? 64u : 48u) : 0u);
+        if (valid) {
+            bulk_g2s(&st.sA[tid], rec, 16, &sm.bar[buf]);
+            bulk_g2s(&st.sB[tid], rec + 1, 16, &sm.bar[buf]);
+            bulk_g2s(&st.sC[tid], c1, 16, &sm.bar[buf]);
+            if (KIND == 2) bulk_g2s(&st.sD[tid], rec + S2, 16, &sm.bar[buf]);
+        }
+#endif
+    };
+    auto wait_for = [&](int buf) {
+#if LAZY_STAGE == 1
+        (void)buf;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#else
+        mbar_wait(&sm.bar[buf], (parity >> buf) & 1u);
+        parity ^= 1u << buf;
+#endif
+    };
+#if LAZY_STAGE == 2
+    fence_proxy_async_smem();     // the sort scratch (generic-proxy stores) shares this memory with the staging buffers
+#endif
+    issue(0, 0);
+#endif
+    int buf = 0;
+    for (uint32_t b0 = 0; b0 < m; b0 += 256) {
+#if LAZY_STAGE != 0
+        wait_for(buf);                                              // this thread's copies of the current batch have landed
+        if (__syncthreads_count(px.done) == 256) {                  // ... everybody's: nothing is in flight at this point
+            if (tid == 0) sm.stage_parity = parity;                 // (read again after the caller's block barrier)
+            return true;
+        }
+        if (b0 + 256 < m) issue(b0 + 256, buf ^ 1);                 // next batch -> the buffer the previous batch has left
+#else
+        if (__syncthreads_count(px.done) == 256) return true;
+        if (!LAZY_PREFETCH) fetch(b0 + tid);
+        if (valid) {
+            sm.bl[0].sA[tid] = r0; sm.bl[0].sB[tid] = r1; sm.bl[0].sC[tid] = r2;
+            if (KIND == 2) sm.bl[0].sD[tid] = r3;
         }
         __syncthreads();
+#endif
+        const BlendStage& bl = sm.bl[buf];
         const int lim = (int)min(256u, m - b0);
         if (tid == 0) sm.consumed += (uint32_t)lim;
-        if (b0 + 256 < m) fetch(b0 + 256 + tid);
+#if LAZY_STAGE == 0
+        if (LAZY_PREFETCH && b0 + 256 < m) fetch(b0 + 256 + tid);
+#else
+        buf ^= 1;
+#endif
         if (__all_sync(0xffffffffu, px.done)) continue;
         uint32_t cnt = 0;
         for (int jb = 0; jb < lim; jb += 32) {
@@ -435,9 +518,9 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
             bool keep = false;
             if (j < lim) {
                 // SMFR blending tiles composite level L2 whatever the alpha once L1 is done: only the -4.5 bound holds
-                const float op = (KIND == 0) ? sm.bl.sB[j].y : (KIND == 1) ? sm.bl.sC[j].x :
-                                 (KIND == 2) ? fmaxf(sm.bl.sC[j].x, sm.bl.sD[j].x) : 1.0f;
-                keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, op, blkx, blky);
+                const float op = (KIND == 0) ? bl.sB[j].y : (KIND == 1) ? bl.sC[j].x :
+                                 (KIND == 2) ? fmaxf(bl.sC[j].x, bl.sD[j].x) : 1.0f;
+                keep = block_may_touch(bl.sA[j], bl.sB[j].x, op, blkx, blky);
             }
             const unsigned mk = __ballot_sync(0xffffffffu, keep);
             if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
@@ -451,15 +534,18 @@ __device__ __forceinline__ bool lazy_blend_group(LazySmem& sm, const Workspace& 
         for (; !px.done && k + 3 < cnt; k += 4) {
             const uint32_t q = wl4[k >> 2];
             const int j0 = q & 0xff, j1 = (q >> 8) & 0xff, j2 = (q >> 16) & 0xff, j3 = q >> 24;
-            const float p0 = px.power(sm, j0, pixx, pixy), p1 = px.power(sm, j1, pixx, pixy);
-            const float p2 = px.power(sm, j2, pixx, pixy), p3 = px.power(sm, j3, pixx, pixy);
-            px.apply(sm, j0, p0);
-            if (!px.done) px.apply(sm, j1, p1);
-            if (!px.done) px.apply(sm, j2, p2);
-            if (!px.done) px.apply(sm, j3, p3);
+            const float p0 = px.power(bl, j0, pixx, pixy), p1 = px.power(bl, j1, pixx, pixy);
+            const float p2 = px.power(bl, j2, pixx, pixy), p3 = px.power(bl, j3, pixx, pixy);
+            px.apply(bl, j0, p0);
+            if (!px.done) px.apply(bl, j1, p1);
+            if (!px.done) px.apply(bl, j2, p2);
+            if (!px.done) px.apply(bl, j3, p3);
         }
-        for (; !px.done && k < cnt; k++) { const int j = wl[k]; px.apply(sm, j, px.power(sm, j, pixx, pixy)); }
+        for (; !px.done && k < cnt; k++) { const int j = wl[k]; px.apply(bl, j, px.power(bl, j, pixx, pixy)); }
     }
+#if LAZY_STAGE != 0
+    if (tid == 0) sm.stage_parity = parity;
+#endif
     return false;
 }
 
@@ -669,7 +755,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
             if (tid < lim) {
                 const uint32_t id = plist[b0 + tid];
                 const float4* __restrict__ rec = ws.rec + (size_t)REC_PS1 * id;
-                sm.bl.sA[tid] = rec[0]; sm.bl.sB[tid] = rec[1]; sm.bl.sC[tid] = rec[2];
+                sm.bl[0].sA[tid] = rec[0]; sm.bl[0].sB[tid] = rec[1]; sm.bl[0].sC[tid] = rec[2];
                 sx.ids[tid] = (int)id;
                 if (STAT != STAT_MAX) atomicAdd(&in.gaussians_count[id], 1);   // counted when the batch is staged, as in the reference
             }
@@ -683,7 +769,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     const int j = jb + lane;
                     bool keep = false;
                     // MAX counts entries that pass the falloff cut whatever their alpha: opacity 1 leaves only the -4.5 bound
-                    if (j < lim) keep = block_may_touch(sm.bl.sA[j], sm.bl.sB[j].x, STAT == STAT_MAX ? 1.0f : sm.bl.sB[j].y, blkx, blky);
+                    if (j < lim) keep = block_may_touch(sm.bl[0].sA[j], sm.bl[0].sB[j].x, STAT == STAT_MAX ? 1.0f : sm.bl[0].sB[j].y, blkx, blky);
                     const unsigned mk = __ballot_sync(0xffffffffu, keep);
                     if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
                     cnt += __popc(mk);
@@ -697,8 +783,8 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     if (!done && !(power > 0.0f || power < -4.5f)) {
                         in_cut = true;
                         // the two rarer outcomes (alpha below 1/255, pixel saturated) are selects, not branches
-                        const float4 c = sm.bl.sC[j];
-                        const float alpha = fminf(0.99f, FM(sm.bl.sB[j].y, expf(power)));
+                        const float4 c = sm.bl[0].sC[j];
+                        const float alpha = fminf(0.99f, FM(sm.bl[0].sB[j].y, BLEND_EXP(power)));
                         const float test_T = FM(T, FS(1.0f, alpha));
                         const bool vis = !(alpha < 1.0f / 255.0f);
                         const bool fin = vis && test_T < 0.0001f;
@@ -739,8 +825,8 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     }
                 };
                 auto power_of = [&](const int j) {
-                    const float4 a = sm.bl.sA[j];
-                    return gauss_power(a.z, a.w, sm.bl.sB[j].x, FS(a.x, pixx), FS(a.y, pixy));
+                    const float4 a = sm.bl[0].sA[j];
+                    return gauss_power(a.z, a.w, sm.bl[0].sB[j].x, FS(a.x, pixx), FS(a.y, pixy));
                 };
                 // four falloff exponents in flight (independent of T), then applied in list order
                 const uint32_t* __restrict__ wl4 = reinterpret_cast<const uint32_t*>(wl);
@@ -876,7 +962,9 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
             }
         }
     } else if (MODE == MODE_SUM) {
-        SumSmemExtra& sx = *reinterpret_cast<SumSmemExtra*>(smem_raw + sizeof(LazySmem));
+        // the training family stages through bl[0] only: with two staging buffers its per-batch scratch lives in the second one
+        SumSmemExtra& sx = (NSTAGE == 2) ? *reinterpret_cast<SumSmemExtra*>(&sm.bl[NSTAGE - 1])
+                                         : *reinterpret_cast<SumSmemExtra*>(smem_raw + sizeof(LazySmem));
         float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
         uint32_t last_contributor = 0;
         int max_idx = 0;
@@ -910,22 +998,36 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
 // of tickets and exit — no idle tail between them.  The second grid's CTAs execute griddepcontrol.wait before THEY exit, so
 // the stream (next stage, next frame) only proceeds once both grids are complete and flushed.
 #ifndef LAZY_CTAS_BLEND
-#define LAZY_CTAS_BLEND 3      // blending-tile instantiations: 80 registers
+#define LAZY_CTAS_BLEND 4      // blending-tile instantiations (A/B: 3 CTAs/SM at 80 registers is 3 % slower)
 #endif
 template <int MODE, int STAT = STAT_SUM, int BK = 0>
 __global__ void __launch_bounds__(256, BK ? LAZY_CTAS_BLEND : LAZY_CTAS) k_lazy_blend(Workspace ws, FrameInputs in, int pdl) {
     extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
     LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
     if (pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#if LAZY_STAGE == 2
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar[0], 256);
+        mbar_init(&sm.bar[1], 256);
+        sm.stage_parity = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+#endif
     FrameHeader* hdr = ws.hdr;
     // tile_order2 = [blending tiles, heaviest first][plain tiles, heaviest first]
     const uint32_t count = hdr->lazy_count[BK];
     const uint32_t base = BK ? 0u : hdr->lazy_count[1];
+    // thread 0 always holds the NEXT ticket: it is requested when a tile starts and first looked at when the tile is done, so
+    // the L2 round trip of the atomic never sits between two tiles (a CTA over-draws one ticket at the end; harmless)
+    uint32_t next = 0;
+    if (threadIdx.x == 0) next = atomicAdd(&hdr->lazy_ticket[BK], 1u);
     for (;;) {
-        if (threadIdx.x == 0) sm.ticket = atomicAdd(&hdr->lazy_ticket[BK], 1u);
+        if (threadIdx.x == 0) sm.ticket = next;
         __syncthreads();
         const uint32_t t = sm.ticket;
         if (t >= count) break;
+        if (threadIdx.x == 0) next = atomicAdd(&hdr->lazy_ticket[BK], 1u);
         lazy_one_tile<MODE, STAT, BK>(sm, lazy_smem_raw, ws, in, (int)ws.tile_order2[base + t]);
         __syncthreads();      // the tile's shared memory (and sm.ticket) is free again
     }
@@ -953,7 +1055,8 @@ static cudaError_t launch_lazy_kernel(K kernel, int grid, size_t smem, cudaStrea
 bool g_no_pdl = false;   // fovgs_set_option(FOVGS_OPT_NO_PDL, 1): the two blend launches of a foveated frame run back to back
 
 cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T, Mode mode, cudaStream_t st) {
-    const size_t smem = sizeof(LazySmem), smem_sum = sizeof(LazySmem) + sizeof(SumSmemExtra);
+    static_assert(sizeof(SumSmemExtra) <= sizeof(BlendStage), "SumSmemExtra must fit the second staging buffer");
+    const size_t smem = sizeof(LazySmem), smem_sum = sizeof(LazySmem) + (NSTAGE == 2 ? 0 : sizeof(SumSmemExtra));
     static PerDeviceOnce once;
     bool* configured = once.slot();
     if (!*configured) {
