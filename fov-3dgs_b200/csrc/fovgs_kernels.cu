@@ -235,6 +235,8 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->pre_done = 0;
             h->pre_chunk = 0;
             h->vis_cursor = 0;
+            h->exp_consts[0] = __uint_as_float(0x3bbb989du);
+            h->exp_consts[1] = 252.0f;
             h->lazy_ticket[0] = h->lazy_ticket[1] = 0;
             h->lazy_count[0] = h->lazy_count[1] = 0;
         }

@@ -112,10 +112,11 @@ __device__ __forceinline__ bool block_may_touch(const float4 a, const float conz
 }
 
 // ---- per-pixel compositing state (identical arithmetic to k_blend) -------------------------------------------------
-struct PixPS1 {      // OBB/forward.cu:251-384
+struct PixPS1 {
+    BlendExpConsts ek;      // OBB/forward.cu:251-384
     float T, C0, C1, C2;
     bool done;
-    __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
+    __device__ __forceinline__ void init(bool inside, const float* ec) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; ek.load(ec); }
     __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
         const float4 a = bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
@@ -127,7 +128,7 @@ struct PixPS1 {      // OBB/forward.cu:251-384
         if (done || power > 0.0f || power < -4.5f) return;
         const float4 b = bl.sB[j];
         const float4 c = bl.sC[j];
-        const float alpha = fminf(0.99f, FM(b.y, BLEND_EXP(power)));
+        const float alpha = fminf(0.99f, FM(b.y, blend_exp(power, ek)));
         const float test_T = FM(T, FS(1.0f, alpha));
         const bool vis = !(alpha < 1.0f / 255.0f);
         const bool fin = vis && test_T < 0.0001f;
@@ -138,10 +139,11 @@ struct PixPS1 {      // OBB/forward.cu:251-384
         done = fin;
     }
 };
-struct PixFov {      // FOV/forward.cu:490-609
+struct PixFov {
+    BlendExpConsts ek;      // FOV/forward.cu:490-609
     float T, C0, C1, C2;
     bool done;
-    __device__ __forceinline__ void init(bool inside) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; }
+    __device__ __forceinline__ void init(bool inside, const float* ec) { T = 1.0f; C0 = C1 = C2 = 0.f; done = !inside; ek.load(ec); }
     __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
         const float4 a = bl.sA[j];
         const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
@@ -150,7 +152,7 @@ struct PixFov {      // FOV/forward.cu:490-609
     __device__ __forceinline__ void apply(const BlendStage& bl, int j, float power) {   // see PixPS1::apply
         if (done || power > 0.0f || power < -4.5f) return;
         const float4 c = bl.sC[j];
-        const float alpha = fminf(0.99f, FM(c.x, BLEND_EXP(power)));
+        const float alpha = fminf(0.99f, FM(c.x, blend_exp(power, ek)));
         const float test_T = FM(T, FS(1.0f, alpha));
         const bool vis = !(alpha < 1.0f / 255.0f);
         const bool fin = vis && test_T < 0.0001f;
@@ -161,12 +163,14 @@ struct PixFov {      // FOV/forward.cu:490-609
         done = fin;
     }
 };
-struct PixFovBlend {  // FOV/forward.cu:262-476
+struct PixFovBlend {
+    BlendExpConsts ek;  // FOV/forward.cu:262-476
     float T1, T2, A0, A1, A2, B0, B1, B2, L2_f;
     bool L1_done, L2_done, done;
-    __device__ __forceinline__ void init(bool inside, float est, int L2, float l2f) {
+    __device__ __forceinline__ void init(bool inside, float est, int L2, float l2f, const float* ec) {
         T1 = T2 = 1.0f; A0 = A1 = A2 = B0 = B1 = B2 = 0.f; L2_f = l2f;
         L1_done = est > (float)L2; L2_done = false; done = !inside;
+        ek.load(ec);
     }
     __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
         const float4 a = bl.sA[j];
@@ -178,7 +182,7 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
         const float4 b = bl.sB[j];
         const float4 c1 = bl.sC[j];
         const float4 c2 = bl.sD[j];
-        const float e = BLEND_EXP(power);
+        const float e = blend_exp(power, ek);
         {
             const float alpha1 = fminf(0.99f, FM(c1.x, e));
             const float test_T1 = FM(T1, FS(1.0f, alpha1));
@@ -205,12 +209,14 @@ struct PixFovBlend {  // FOV/forward.cu:262-476
     }
 };
 
-struct PixSmfrBlend {  // naive_pcheck_obb/cuda_rasterizer/forward.cu:262-440: one alpha for both levels
+struct PixSmfrBlend {
+    BlendExpConsts ek;  // naive_pcheck_obb/cuda_rasterizer/forward.cu:262-440: one alpha for both levels
     float T1, T2, A0, A1, A2, B0, B1, B2, L2_f;
     bool L1_done, L2_done, done;
-    __device__ __forceinline__ void init(bool inside, float est, int L2, float l2f) {
+    __device__ __forceinline__ void init(bool inside, float est, int L2, float l2f, const float* ec) {
         T1 = T2 = 1.0f; A0 = A1 = A2 = B0 = B1 = B2 = 0.f; L2_f = l2f;
         L1_done = est > (float)L2; L2_done = false; done = !inside;
+        ek.load(ec);
     }
     __device__ __forceinline__ float power(const BlendStage& bl, int j, float pixx, float pixy) const {
         const float4 a = bl.sA[j];
@@ -221,7 +227,7 @@ struct PixSmfrBlend {  // naive_pcheck_obb/cuda_rasterizer/forward.cu:262-440: o
         if (power > 0.0f || power < -4.5f) return;
         const float4 b = bl.sB[j];
         const float4 c = bl.sC[j];
-        const float alpha1 = fminf(0.99f, FM(c.x, BLEND_EXP(power)));
+        const float alpha1 = fminf(0.99f, FM(c.x, blend_exp(power, ek)));
         if (!L1_done) {
             // a live L1 drops the entry for BOTH levels (:403-405); once L1 is done the alpha test no longer applies
             if (alpha1 < 1.0f / 255.0f) return;
@@ -915,7 +921,7 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
             const int L1i = (int)est;
             const float xr = FM(FS(est, FA((float)L1i, kStartBlendL)), 2.0f);   // (est - (L1 + start_blend)) / blend_width
             PixFov px;
-            px.init(inside);
+            px.init(inside, hdr->exp_consts);
             if (xr < 0.0f && (float)L1i != cur_level) px.done = true;
             lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
             if (inside) {
@@ -931,7 +937,7 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
             }
         } else if (!BK) {
             PixFov px;
-            px.init(inside);
+            px.init(inside, hdr->exp_consts);
             lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
             if (inside) {
                 const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
@@ -944,7 +950,7 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
             const float dxl = (float)lxi, dyl = (float)lyi;
             const float est = FF(FF(dxl, ws.tile_gx[tile], FM(dyl, ws.tile_gy[tile])), 0.0625f, tile_level_f);
             typename std::conditional<MODE == MODE_SMFR, PixSmfrBlend, PixFovBlend>::type px;
-            px.init(inside, est, L2, FA(tile_level_f, 1.0f));
+            px.init(inside, est, L2, FA(tile_level_f, 1.0f), hdr->exp_consts);
             lazy_tile<(MODE == MODE_SMFR) ? 3 : 2, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, (MODE == MODE_FOV) ? S1 + 1 : S1);
             if (inside) {
                 const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
@@ -980,7 +986,7 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
         }
     } else {
         PixPS1 px;
-        px.init(inside);
+        px.init(inside, hdr->exp_consts);
         lazy_tile<0, REC_PS1>(sm, ws, tile, px, pixx, pixy, blkx, blky, 0, 0);
         if (inside) {
             const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
@@ -1097,6 +1103,32 @@ cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T,
 }
 
 }  // namespace fovgs
+
+// ---- test support: blend_exp against libdevice expf, bit for bit, over a range of float bit patterns ---------------------
+namespace fovgs {
+__global__ void k_expf_check(uint32_t lo, uint32_t hi, unsigned long long* mismatches, const float* consts) {
+    BlendExpConsts ek;
+    ek.load(consts);
+    unsigned long long bad = 0;
+    const uint64_t n = (uint64_t)hi - lo + 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(lo + (uint32_t)i);
+        bad += __float_as_uint(expf(x)) != __float_as_uint(blend_exp(x, ek));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace fovgs
+extern "C" int fovgs_debug_expf_mismatches(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches_dev, void* stream) {
+    if (!mismatches_dev || hi_bits < lo_bits) return FOVGS_ERR_INVALID_ARG;
+    // the two constants travel through device memory (one word after the counter's 8 bytes is not available: use a static buffer)
+    static float* consts = nullptr;
+    if (!consts) {
+        const uint32_t h[2] = {0x3bbb989du, 0x437c0000u};
+        if (cudaMalloc(&consts, 8) != cudaSuccess || cudaMemcpy(consts, h, 8, cudaMemcpyHostToDevice) != cudaSuccess) return FOVGS_ERR_CUDA;
+    }
+    fovgs::k_expf_check<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(lo_bits, hi_bits, mismatches_dev, consts);
+    return cudaGetLastError() == cudaSuccess ? 0 : FOVGS_ERR_CUDA;
+}
 
 #ifdef FOVGS_TILE_TIMING
 extern "C" int fovgs_debug_tile_times(uint32_t* host_out, int tiles) {

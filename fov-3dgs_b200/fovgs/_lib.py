@@ -231,6 +231,7 @@ EXPORTS = (
     "fovgs_last_error",
     "fovgs_version",
     "fovgs_struct_size",
+    "fovgs_debug_expf_mismatches",
 )
 
 # fovgs_struct_id -> the ctypes mirror in this file
@@ -283,6 +284,8 @@ def lib():
     L.fovgs_fov_tile_tables.argtypes = [_f, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_ps1_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, C.c_void_p]
     L.fovgs_fov_geometry.argtypes = [_f, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f, _f, C.c_void_p]
+    L.fovgs_debug_expf_mismatches.argtypes = [C.c_uint32, C.c_uint32, _f, C.c_void_p]
+    L.fovgs_debug_expf_mismatches.restype = C.c_int
     L.fovgs_set_option.argtypes = [C.c_int32, C.c_int32]
     L.fovgs_set_option.restype = C.c_int
     L.fovgs_profile_enable.argtypes = [C.c_int32]

@@ -751,3 +751,20 @@ def test_integration_binding_stub_renders_like_the_package(scene_small):
                                                       cd["viewmatrix"], cd["projmatrix"], c["tanfovx"], c["tanfovy"], c["image_height"],
                                                       c["image_width"], sc["shs_rest"], 3, cd["campos"], False, False)
     assert n2 == n and torch.equal(radii2, radii) and torch.equal(color2, color)
+
+
+def test_blend_exp_is_bit_identical_to_expf():
+    """The blend kernels' exp (libdevice expf's sequence with its constants hoisted into registers) against expf itself: every
+    float of the blend's domain [-4.5, -0.0] (1.08e9 bit patterns), the positive range up to 4.5, and the whole finite negative /
+    positive ranges in 2^24-pattern windows."""
+    from fovgs._lib import lib
+    L = lib()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ranges = [(0x80000000, 0xC0900000), (0x00000000, 0x40900000)]
+    ranges += [(b, b + (1 << 24) - 1) for b in range(0xC0900000, 0xFF800000 - (1 << 24), 1 << 27)]
+    ranges += [(b, b + (1 << 24) - 1) for b in range(0x40900000, 0x7F800000 - (1 << 24), 1 << 27)]
+    for lo, hi in ranges:
+        assert L.fovgs_debug_expf_mismatches(lo, hi, bad.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
