@@ -96,6 +96,7 @@ int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     in.shs = a->M_rest > 0 ? a->shs_rest : nullptr; in.shs_dcs = a->shs_dcs; in.highest_levels = a->highest_levels;
     in.radii = a->radii; in.out_color = a->out_color;
     in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    in.early_stats_host = a->early_stats_host; in.early_stats_event = a->early_stats_event;
     in.packed_rows = (a->M_rest <= 15) ? a->packed_color_rows : nullptr;
     e = launch_forward(ws, in, W, H, MODE_FOV, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_fov");
@@ -137,6 +138,7 @@ int fovgs_forward_smfr(const fovgs_smfr_fwd_args* a, void* stream) {
     in.shs = a->shs; in.highest_levels = a->highest_levels;
     in.radii = a->radii; in.out_color = a->out_color;
     in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    in.early_stats_host = a->early_stats_host; in.early_stats_event = a->early_stats_event;
     e = launch_forward(ws, in, W, H, MODE_SMFR, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_smfr");
     return 0;
@@ -165,6 +167,7 @@ int fovgs_forward_mmfr(const fovgs_mmfr_fwd_args* a, void* stream) {
     in.shs = a->shs;
     in.radii = a->radii; in.out_color = a->out_color;
     in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    in.early_stats_host = a->early_stats_host; in.early_stats_event = a->early_stats_event;
     e = launch_forward(ws, in, W, H, MODE_MMFR, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_mmfr");
     return 0;
@@ -203,6 +206,7 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     in.loss_map = a->loss_map;
     in.stat = a->mode == FOVGS_PS1_MAX ? STAT_MAX : (a->mode == FOVGS_PS1_LWMC ? STAT_LWMC : STAT_SUM);
     in.out_color = a->out_color; in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
+    in.early_stats_host = a->early_stats_host; in.early_stats_event = a->early_stats_event;
     e = launch_forward(ws, in, W, H, mode, a->cam.debug != 0, st);
     if (e != cudaSuccess) return fail_cuda(e, "forward_ps1");
     return 0;

@@ -404,6 +404,15 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     prof_mark(1, st);
     launch_pre(ws, in, (Mode)MODE, num_sms, st);      // + tile scan, by the last CTA to finish
     STAGE_CHECK();
+    if (in.early_stats_host != nullptr) {
+        // instance count, overflow flag, visible count are final here: the host can have them a third of the way into the frame
+        cudaError_t e_ = cudaMemcpyAsync(in.early_stats_host, ws.hdr, sizeof(fovgs_frame_stats), cudaMemcpyDeviceToHost, st);
+        if (e_ != cudaSuccess) return e_;
+        if (in.early_stats_event != nullptr) {
+            e_ = cudaEventRecord((cudaEvent_t)in.early_stats_event, st);
+            if (e_ != cudaSuccess) return e_;
+        }
+    }
     prof_mark(2, st);
     launch_color(ws, in, (Mode)MODE, num_sms, st);
     STAGE_CHECK();

@@ -16,7 +16,7 @@ FOVGS_PS1_SUM = 1
 FOVGS_PS1_MAX = 2
 FOVGS_PS1_LWMC = 3
 
-FOVGS_VERSION = 200   # include/fovgs.h; every args struct carries it next to its own size (FOVGS_ARGS_HEADER)
+FOVGS_VERSION = 201   # include/fovgs.h; every args struct carries it next to its own size (FOVGS_ARGS_HEADER)
 
 _f = C.c_void_p  # all device pointers travel as void*
 _HEADER = [("struct_size", C.c_uint32), ("abi_version", C.c_uint32)]
@@ -82,6 +82,8 @@ class FovFwdArgs(C.Structure):
         ("out_point_list", _f),
         ("out_ranges", _f),
         ("packed_color_rows", _f),
+        ("early_stats_host", _f),
+        ("early_stats_event", _f),
     ]
 
 
@@ -106,6 +108,8 @@ class SmfrFwdArgs(C.Structure):
         ("max_instances", C.c_int64),
         ("out_point_list", _f),
         ("out_ranges", _f),
+        ("early_stats_host", _f),
+        ("early_stats_event", _f),
     ]
 
 
@@ -130,6 +134,8 @@ class MmfrFwdArgs(C.Structure):
         ("max_instances", C.c_int64),
         ("out_point_list", _f),
         ("out_ranges", _f),
+        ("early_stats_host", _f),
+        ("early_stats_event", _f),
     ]
 
 
@@ -156,6 +162,8 @@ class Ps1FwdArgs(C.Structure):
         ("out_point_list", _f),
         ("out_ranges", _f),
         ("loss_map", _f),
+        ("early_stats_host", _f),
+        ("early_stats_event", _f),
     ]
 
 

@@ -30,6 +30,12 @@ _TRAIN_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC)
 _PS1_ABI_MODE = {MODE_OBB: _lib.FOVGS_PS1_OBB, MODE_SUM: _lib.FOVGS_PS1_SUM, MODE_MAX: _lib.FOVGS_PS1_MAX,
                  MODE_LWMC: _lib.FOVGS_PS1_LWMC}
 _DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
+# Blocking (default) mode waits for the statistics the library copies out right after the binning stage (instance count,
+# overflow flag: final a third of the way into the frame) — not for the end of the frame: the call returns with a validated
+# instance count while colour / scatter / blend are still running, and an overflow is repaired (the frame re-runs into the same
+# outputs, stream-ordered) before anybody can have consumed it.  The blend stage's own counters (`blend_consumed`,
+# `blend_block_pairs`) are only final at the end of the frame: FOVGS_FULL_STATS=1 / set_full_stats(True) waits for them.
+_FULL_STATS = os.environ.get("FOVGS_FULL_STATS", "0") == "1"
 
 
 def set_full_sort(on):
@@ -40,6 +46,12 @@ def set_full_sort(on):
 def set_no_tma(on):
     """Colour stage: use register-staged cooperative loads instead of TMA bulk copies (debug / comparison)."""
     check(lib().fovgs_set_option(2, 1 if on else 0), "fovgs_set_option")
+
+
+def set_full_stats(on):
+    """Blocking mode: wait for the end of the frame so that `last_stats` also carries the blend stage's counters."""
+    global _FULL_STATS
+    _FULL_STATS = bool(on)
 
 
 def set_deferred_check(on):
@@ -172,7 +184,19 @@ def _new_workspace(device, mode, P, W, H, cap):
         stats = stats.pin_memory()
     # `stats_np` aliases the (pinned) host tensor: reading 16 ints through it costs ~1 us, indexing the tensor ~3 us each
     return {"ws": ws, "cap": cap, "bytes": nbytes, "stats": stats, "stats_np": stats.numpy(), "stats_ptr": stats.data_ptr(),
-            "ws_ptr": ws.data_ptr(), "ring_events": [None] * _RING, "ring_pending": [False] * _RING, "ring_pos": 0, "key": None}
+            "ws_ptr": ws.data_ptr(), "ring_events": [None] * _RING, "ring_pending": [False] * _RING, "ring_pos": 0, "key": None,
+            "early_event": None, "early_handle": None}
+
+
+def _early_event(item, stream_obj):
+    """The CUDA event the library records behind the early statistics copy (created on first use: torch creates the underlying
+    cudaEvent_t lazily, at its first record)."""
+    ev = item["early_event"]
+    if ev is None:
+        ev = item["early_event"] = torch.cuda.Event()
+        ev.record(stream_obj)
+        item["early_handle"] = int(ev.cuda_event)
+    return ev
 
 
 _pool = _Pool()
@@ -267,6 +291,7 @@ def _run_with_capacity_impl(launch, device, mode, P, W, H, fresh_workspace):
                 _drain_ring(item, key, block=True, only_slot=slot)     # the host ran _RING frames ahead: wait for the oldest
             if item is not _pool.items.get(key) or item["cap"] < _pool.min_caps.get(key, 0):
                 continue                                                # an overflow was learnt: take the grown workspace
+            item["early"] = None
             launch(item, stream)
             _read_stats(item, stream, slot)
             ev = item["ring_events"][slot]
@@ -278,9 +303,16 @@ def _run_with_capacity_impl(launch, device, mode, P, W, H, fresh_workspace):
             return item, None
         if not fresh_workspace:
             _drain_ring(item, item["key"], block=True)                  # frames left over from a deferred phase
-        launch(item, stream)
-        _read_stats(item, stream)
-        cur_stream.synchronize()
+        if _FULL_STATS or not hasattr(cur_stream, "cuda_stream") or not torch.cuda.is_available():
+            item["early"] = None
+            launch(item, stream)
+            _read_stats(item, stream)
+            cur_stream.synchronize()
+        else:
+            ev = _early_event(item, cur_stream)
+            item["early"] = (item["stats_ptr"], item["early_handle"])   # launch() passes these to the library
+            launch(item, stream)
+            ev.synchronize()                                            # binning done, statistics landed; the frame runs on
         st = _stats_dict(item)
         last_stats = st
         if st["prefiltered_violations"]:
@@ -443,6 +475,8 @@ def _forward_foveated(kind, fields, means3D, scales, rotations, gazeArray, alpha
         a.workspace = item["ws_ptr"]
         a.workspace_bytes = item["bytes"]
         a.max_instances = item["cap"]
+        early = item.get("early")
+        a.early_stats_host, a.early_stats_event = early if early else (None, None)
         if want_lists:
             lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
             lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)
@@ -601,9 +635,11 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
             extra["contrib"] = torch.zeros((P,), dtype=torch.float32, device=device)
             a.gaussians_count = extra["gcount"].data_ptr()
             a.contributions = extra["contrib"].data_ptr()
-        a.workspace = item["ws"].data_ptr()
+        a.workspace = item["ws_ptr"]
         a.workspace_bytes = item["bytes"]
         a.max_instances = item["cap"]
+        early = item.get("early")
+        a.early_stats_host, a.early_stats_event = early if early else (None, None)
         if want_lists:
             lists["point_list"] = torch.zeros((item["cap"],), dtype=torch.int32, device=device)
             lists["ranges"] = torch.zeros((T, 2), dtype=torch.int32, device=device)

@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "fov-3dgs_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 from fovgs import ops, synth  # noqa: E402
+ops.set_full_stats(True)   # these tools print the blend stage's counters: wait for the end of each frame
 import ref_api  # noqa: E402
 
 

@@ -6,6 +6,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "fov-3dgs_b200"))
 from fovgs import ops, synth  # noqa: E402
+ops.set_full_stats(True)   # these tools print the blend stage's counters: wait for the end of each frame
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from parity_gpu import to_cuda, settings  # noqa: E402
 
