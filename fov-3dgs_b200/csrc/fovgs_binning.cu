@@ -272,13 +272,18 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                         const float sm_ = fmaxf(fabsf(sx), fmaxf(fabsf(sy), fabsf(sz))) * fabsf(cam.scale_modifier) * rn;
                         lam3 = sm_ * sm_;
                     }
-                    const float kt = cull_k / tz;
+                    // MUFU-approximate reciprocal / square root (1-2 ulp): this is the CONSERVATIVE bound, its 1 % and 1e-5 slack
+                    // factors dwarf them; the exact projection below keeps its IEEE operations
+                    float rtz, pw, sq2;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rtz) : "f"(tz));
+                    const float kt = cull_k * rtz;
                     const float lam2 = 2.0f * kt * kt * lam3 * 1.01f + 0.62f;
-                    const float rb = 3.01f * sqrtf(lam2) + 2.0f;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq2) : "f"(lam2));
+                    const float rb = 3.01f * sq2 + 2.0f;
                     const float hx = xform_row(cam.proj, 0, mx, my, mz);
                     const float hy = xform_row(cam.proj, 1, mx, my, mz);
                     const float hw = xform_row(cam.proj, 3, mx, my, mz);
-                    const float pw = __frcp_rn(FA(hw, 0.0000001f));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(FA(hw, 0.0000001f)));
                     const float px = ((FM(hx, pw) + 1.0f) * (float)cam.W - 1.0f) * 0.5f;
                     const float py = ((FM(hy, pw) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
                     const float ex = rb + 1.0f + 1e-5f * fabsf(px), ey = rb + 1.0f + 1e-5f * fabsf(py);

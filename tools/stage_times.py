@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--variant", default="sum"); ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--size", default="big"); ap.add_argument("--backward", action="store_true")
     ap.add_argument("--split", default="0", help="comma list of FOVGS_OPT_SPLIT_STAGES settings to run, e.g. 0,1")
+    ap.add_argument("--first", type=int, default=0, help="index of the first measured frame (bench.py frame numbering: camera f%30, gaze f%9)")
     ap.add_argument("--no-pdl", action="store_true", help="FOVGS_OPT_NO_PDL: the two blend launches run back to back")
     a = ap.parse_args()
     if a.no_pdl:
@@ -35,7 +36,8 @@ def main():
 
 def run(a, sc, cams, bg, ev, split):
     fwd_ms, bwd_ms = [], []
-    for f in range(a.frames + 2):
+    for i in range(a.frames + 2):
+        f = max(a.first - 2, 0) + i if a.first >= 2 else i
         c = to_cuda(cams[f % 30]); rs = settings(c, sc["sh_degree"], bg)
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
@@ -54,7 +56,7 @@ def run(a, sc, cams, bg, ev, split):
             e1.record()
             ops.backward_ps1(out[3], sc["means3D"], out[2], sc["scales"], sc["rotations"], None, sc["shs"], None, rs, g)
         e2.record(); torch.cuda.synchronize()
-        if f >= 2: fwd_ms.append(e0.elapsed_time(e1)); bwd_ms.append(e1.elapsed_time(e2))
+        if i >= 2: fwd_ms.append(e0.elapsed_time(e1)); bwd_ms.append(e1.elapsed_time(e2))
     st = ops.profile_read_all()[2:]
     mean = {k: float(np.mean([s[k] for s in st])) for k in ops.STAGE_NAMES}
     print("split", split, "variant", a.variant, "fwd_ms_mean", np.mean(fwd_ms), "bwd_ms_mean", np.mean(bwd_ms), "stages", {k: round(v, 4) for k, v in mean.items()}, "stats", ops.last_stats)
