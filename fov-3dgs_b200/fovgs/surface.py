@@ -127,7 +127,7 @@ def _fov_rasterize_gaussians(means3D, means2D, shs_rest, colors_precomp, opaciti
 class _FovGaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
-        self.raster_settings = raster_settings
+        object.__setattr__(self, "raster_settings", raster_settings)   # a plain attribute: nn.Module.__setattr__ costs ~6 us per frame
 
     def markVisible(self, positions):
         return _mark_visible(self.raster_settings, positions)
@@ -203,7 +203,7 @@ def _smfr_rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, 
 class _SmfrGaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
-        self.raster_settings = raster_settings
+        object.__setattr__(self, "raster_settings", raster_settings)   # a plain attribute: nn.Module.__setattr__ costs ~6 us per frame
 
     def markVisible(self, positions):
         return _mark_visible(self.raster_settings, positions)
@@ -279,7 +279,7 @@ def _mmfr_rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, 
 class _MmfrGaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
-        self.raster_settings = raster_settings
+        object.__setattr__(self, "raster_settings", raster_settings)   # a plain attribute: nn.Module.__setattr__ costs ~6 us per frame
 
     def markVisible(self, positions):
         return _mark_visible(self.raster_settings, positions)
@@ -399,7 +399,7 @@ def _make_ps1_api(mode: int):
         class GaussianRasterizer(nn.Module):
             def __init__(self, raster_settings):
                 super().__init__()
-                self.raster_settings = raster_settings
+                object.__setattr__(self, "raster_settings", raster_settings)   # a plain attribute: nn.Module.__setattr__ costs ~6 us per frame
 
             def markVisible(self, positions):
                 return _mark_visible(self.raster_settings, positions)
@@ -427,7 +427,7 @@ def _make_ps1_api(mode: int):
     class GaussianRasterizer(nn.Module):
         def __init__(self, raster_settings):
             super().__init__()
-            self.raster_settings = raster_settings
+            object.__setattr__(self, "raster_settings", raster_settings)   # a plain attribute: nn.Module.__setattr__ costs ~6 us per frame
 
         def markVisible(self, positions):
             return _mark_visible(self.raster_settings, positions)
