@@ -181,7 +181,6 @@ struct PixFovBlend {
         if (done || power > 0.0f || power < -4.5f) return;
         const float4 b = bl.sB[j];
         const float4 c1 = bl.sC[j];
-        const float4 c2 = bl.sD[j];
         const float e = blend_exp(power, ek);
         {
             const float alpha1 = fminf(0.99f, FM(c1.x, e));
@@ -194,10 +193,13 @@ struct PixFovBlend {
             T1 = acc ? test_T1 : T1;
             L1_done = L1_done || fin;
         }
-        {
+        // the splat belongs to level L2 only when highest_level + 1 >= L2 (FOV/forward.cu:425): a property of the SPLAT, the same
+        // for every lane still here, so this branch never diverges — and three in five Gaussians carry highest level 0
+        if (!(FA(b.y, 1.0f) < L2_f)) {
+            const float4 c2 = bl.sD[j];
             const float alpha2 = fminf(0.99f, FM(c2.x, e));
             const float test_T2 = FM(T2, FS(1.0f, alpha2));
-            const bool vis = !L2_done && !((alpha2 < 1.0f / 255.0f) || (FA(b.y, 1.0f) < L2_f));
+            const bool vis = !L2_done && !(alpha2 < 1.0f / 255.0f);
             const bool fin = vis && test_T2 < 0.0001f;
             const bool acc = vis && !fin;
             const float w = FM(alpha2, T2);
