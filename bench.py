@@ -730,7 +730,7 @@ def main():
             "clocks": res["clocks"],
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                     "mode": "default drop-in call: every call returns with its validated instance count (host waits for the "
-                            "statistics the library copies out after the binning stage)"},
+                            "statistics the library copies out after the tile scan)"},
         }
         if res.get("extra") is not None:
             line["extra"] = res["extra"]

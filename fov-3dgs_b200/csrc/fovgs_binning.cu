@@ -13,8 +13,8 @@
 //              profiles/r1_launches_fov_6M_reference.csv).  Surviving (tile, depth|id) instances are counted per tile (RED
 //              on 256-byte-strided counters) and staged densely in per-warp 512-slot chunks.  Phase C: radii, geometry
 //              records, visible list.  Replaces preprocessCUDA + InclusiveSum x2 + filter/OBB_test + duplicateWithKeys.
-//   tile scan  exclusive scan of the tile histogram (= the reference's `ranges`, no identifyTileRanges), run by the LAST
-//              CTA of k_pre to finish (ticket counter), so it costs no launch and no idle GPU.
+//   k_tile_scan  exclusive scan of the tile histogram (= the reference's `ranges`, no identifyTileRanges) + tile orders, one
+//              CTA; the colour kernel is its programmatic dependent launch and runs beside it (nothing there needs the scan).
 //   k_color_tma  SH colours of the visible Gaussians (TMA bulk gathers; packed 256-byte model rows for foveated models);
 //              k_color is the register-staged fallback.  Replaces compute_fov_colors / computeColorFromSH.
 //   k_scatter  staged instances -> their tiles' segments (cursor atomics; trivially balanced: one thread per instance).
@@ -153,14 +153,6 @@ struct WarpSmem {
     uint32_t cnt[32];            // != 0: at least one candidate tile survived (the Gaussian is visible)
 };
 
-struct ScanSmem {
-    uint32_t warp_sums[32];
-    uint32_t carry, maxv;
-    uint32_t bucket_cnt[33], bucket_base[33];
-    uint32_t bucket_cnt2[68], bucket_base2[68];   // the same by (tile kind, size class): kind 1 = blending tile, classes 34..67
-    int is_last;
-};
-
 constexpr int LC_MAX = 16384;      // tiles whose level code fits the shared table (1080p: 8160)
 constexpr int PRE_CHUNK = PRE_TICKET;   // Gaussians per work ticket of k_pre
 static_assert(PRE_CHUNK % 32 == 0 && PRE_CHUNK <= 256, "ticket = whole batches; its inputs are prefetched by one warp");
@@ -174,11 +166,7 @@ struct PreSmem {
     // test reads one shared byte instead of gathering a float through L1.
     alignas(16) uint8_t lvl_code[LC_MAX];
     WarpSmem w[WPB];
-    ScanSmem scan;
 };
-
-template <int NT>
-__device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s);
 
 template <int MODE>
 __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs in) {
@@ -561,15 +549,7 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
     }
     if (lane == 0 && visible_total) atomicAdd(&ws.hdr->stats.num_visible, visible_total);
     if (lane == 0 && cand_total) atomicAdd(&ws.hdr->stats.reserved[2], cand_total);   // candidate tiles enumerated
-    // ---- the last CTA to get here scans the tile histogram (threadFenceReduction pattern) ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sm.scan.is_last = (atomicAdd(&ws.hdr->pre_done, 1u) == gridDim.x - 1) ? 1 : 0;
-    __syncthreads();
-    if (sm.scan.is_last) {
-        __threadfence();
-        tile_scan_block<PB>(ws, ws.hdr->tiles, sm.scan);
-    }
+    // (the tile histogram is scanned by k_tile_scan, which runs beside the colour kernel that follows)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -716,21 +696,15 @@ __device__ __forceinline__ void scatter_role(const Workspace& ws, const uint32_t
     for (uint32_t i0 = t; i0 < n; i0 += nthreads * U) {
         const uint32_t nx = i0 + nthreads * U;
         if (nx < n) load(nx, ntl, nk);
-        uint32_t off[U], r[U];
+        // cursors start at their tile's offset (tile scan), so the atomic returns the slot: per instance one divergent
+        // ATOMG and one divergent 8-byte store; the kernel is bound by those LSU wavefronts, not by HBM
+        uint32_t slot[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (tl[u] != TILE_INVALID) {
-                off[u] = ws.tile_offset[tl[u]];
-                r[u] = atomicAdd(&ws.tile_cursor[(size_t)tl[u] * CSTRIDE], 1u);
-            }
-        }
+        for (int u = 0; u < U; u++)
+            if (tl[u] != TILE_INVALID) slot[u] = atomicAdd(&ws.tile_cursor[(size_t)tl[u] * CSTRIDE], 1u);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (tl[u] != TILE_INVALID) {
-                const uint32_t slot = off[u] + r[u];
-                if (slot < cap) ws.keysA[slot] = k[u];
-            }
-        }
+        for (int u = 0; u < U; u++)
+            if (tl[u] != TILE_INVALID && slot[u] < cap) ws.keysA[slot[u]] = k[u];
 #pragma unroll
         for (int u = 0; u < U; u++) { tl[u] = ntl[u]; k[u] = nk[u]; }
     }
@@ -871,6 +845,7 @@ __device__ __forceinline__ void color_tma_role(const Workspace& ws, const FrameI
         }
         __syncwarp();   // all generic-proxy reads of the slots are done before the next round's bulk copies overwrite them
     }
+    pdl_wait();   // second of the (k_tile_scan, colour) pair, see k_color_tma
 }
 
 // Measured and dropped: running the colour gathers and the scatter as two warp roles of ONE launch.  Alone they take
@@ -893,108 +868,222 @@ __global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs
     __syncthreads();
     color_tma_role<MODE>(ws, in, shs_floats, &tbuf[warp][0][0], &bars[warp], blockIdx.x * CW + warp, gridDim.x * CW, campos_s,
                          deg_s, M_s);
+    pdl_wait();   // second of the (k_tile_scan, colour) pair: the stream goes on only when the scan is complete as well
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Tile scan: exclusive prefix sum of the per-tile histogram by ONE CTA of NT threads (the last CTA of k_pre); publishes N,
-// the overflow flag and the heavy-first tile order.  Counters are read with ld.cg: they were only ever touched by L2 atomics.
+// k_tile_scan: one CTA of 1024 threads turns the per-tile histogram k_pre left into
+//   tile_offset (exclusive scan = the reference's `ranges`; no identifyTileRanges), tile_cursor (the scatter allocates
+//   slots straight from it), num_rendered / overflow / max_tile_instances, cum_class, and the heavy-first tile orders
+//   (tile_order2: blending tiles first, each kind by descending power-of-two size class; tile_order: by class only, written
+//   when the full-sort path will run).
+// Nothing in the colour stage needs any of this, so the kernel is the FIRST of a programmatic-dependent-launch pair with the
+// colour kernel: it triggers the dependent launch on entry, the colour CTAs fill the other 147 SMs at once and the scan
+// hides behind the colour gathers (as the last CTA of k_pre it held the whole GPU idle for ~65 us per frame: 256 threads,
+// 32 dependent round trips to L2-resident counters that sit 256 bytes apart, three match/atomic sequences per tile).
+// Organised around round trips: a thread owns 8 consecutive tiles and requests its 8 counters before it uses one (1080p:
+// 8160 tiles = one sweep).  The counting sorts use no atomics: per sweep every warp ranks its items per class with
+// `match.any` into its own row of a [warp][class] table, one block scan over the table (class-major, warp-minor) turns the
+// rows into bases.  Counters are read with ld.cg: they were only ever touched by L2 atomics.
 // ------------------------------------------------------------------------------------------------------------------
-template <int NT>
-__device__ void tile_scan_block(const Workspace& ws, int T, ScanSmem& s) {
-    constexpr int NW = NT / 32;
+constexpr int SCAN_NT = 1024, SCAN_NW = SCAN_NT / 32, SCAN_IT = 8;
+constexpr int SCAN_BINS = 68;      // (kind, class): class = 32 - clz(n) in [0, 32] (0: empty), bin = class + 34 * kind
+struct ScanSmem {
+    uint32_t warp_sums[SCAN_NW];
+    uint32_t carry, maxv;
+    uint32_t table[SCAN_BINS][SCAN_NW];     // [bin][warp]: counts, then bases of tile_order2
+    uint32_t table1[34][SCAN_NW];           // the same for tile_order (both kinds merged)
+    uint32_t bin_total[SCAN_BINS];
+};
+
+// exclusive block scan of one value per thread (SCAN_NT threads); returns the exclusive prefix, *total = the block's sum
+__device__ __forceinline__ uint32_t scan_block_excl(uint32_t x, uint32_t* warp_sums, uint32_t* total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { s.carry = 0; s.maxv = 0; }
-    if (threadIdx.x < 33) s.bucket_cnt[threadIdx.x] = 0;
-    if (threadIdx.x < 68) s.bucket_cnt2[threadIdx.x] = 0;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    __syncthreads();                         // warp_sums may still be read by the previous call
+    if (lane == 31) warp_sums[wid] = incl;
     __syncthreads();
+    uint32_t w = warp_sums[lane];            // SCAN_NW == 32: one value per lane
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+    *total = __shfl_sync(0xffffffffu, wi, 31);
+    const uint32_t wbase = __shfl_sync(0xffffffffu, wi - w, wid);
+    return wbase + incl - x;
+}
+
+__global__ void __launch_bounds__(SCAN_NT, 1) k_tile_scan(FrameHeader* hdr, const uint32_t* __restrict__ tile_count,
+                                                          uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ tile_cursor,
+                                                          uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_order2,
+                                                          const uint8_t* __restrict__ tile_blend, uint32_t stage_cap,
+                                                          int want_order1) {
+    static_assert(SCAN_NW == 32, "scan_block_excl assumes 32 warps");
+    __shared__ ScanSmem s;
+    pdl_trigger();                           // the colour kernel may start now: it shares nothing with this one
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int T = hdr->tiles;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int i = tid; i < SCAN_BINS * SCAN_NW; i += SCAN_NT) (&s.table[0][0])[i] = 0;
+    for (int i = tid; i < 34 * SCAN_NW; i += SCAN_NT) (&s.table1[0][0])[i] = 0;
+    if (tid == 0) { s.carry = 0; s.maxv = 0; }
+    __syncthreads();
+    auto load = [&](int i0, uint32_t* v, int* bin) {
+#pragma unroll
+        for (int u = 0; u < SCAN_IT; u++) v[u] = (i0 + u < T) ? __ldcg(&tile_count[(size_t)(i0 + u) * CSTRIDE]) : 0u;
+        unsigned long long kinds = 0ull;     // 8 tile_blend bytes (sub-buffers are 256-byte aligned, i0 is a multiple of 8)
+        if (tile_blend != nullptr) {
+            if (i0 + SCAN_IT <= T) kinds = *reinterpret_cast<const unsigned long long*>(tile_blend + i0);
+            else
+                for (int u = 0; u < SCAN_IT; u++)
+                    if (i0 + u < T) kinds |= (unsigned long long)tile_blend[i0 + u] << (8 * u);
+        }
+#pragma unroll
+        for (int u = 0; u < SCAN_IT; u++) {
+            const int cls = v[u] ? 32 - __clz(v[u]) : 0;
+            bin[u] = (i0 + u < T) ? cls + (((kinds >> (8 * u)) & 0xffull) ? 34 : 0) : -1;
+        }
+    };
+    // ---- pass A: offsets, cursors, per-(warp, bin) counts ----
     uint32_t local_max = 0;
-    for (int base = 0; base < T; base += NT) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = (i < T) ? __ldcg(&ws.tile_count[(size_t)i * CSTRIDE]) : 0u;
-        local_max = max(local_max, v);
-        {   // size-class histogram, one shared atomic per distinct class in the warp (a few classes hold most tiles)
-            const int kind = (i < T && ws.tile_blend != nullptr && ws.tile_blend[i]) ? 1 : 0;
-            const int cls = (i < T) ? (v ? 32 - __clz(v) : 0) + 34 * kind : 68 + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, cls);
-            if (i < T && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s.bucket_cnt2[cls], (uint32_t)__popc(peers));
-        }
-        uint32_t x = v;
+    for (int base = 0; base < T; base += SCAN_NT * SCAN_IT) {
+        const int i0 = base + tid * SCAN_IT;
+        uint32_t v[SCAN_IT];
+        int bin[SCAN_IT];
+        load(i0, v, bin);
+        uint32_t sum = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s.warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = (lane < NW) ? s.warp_sums[lane] : 0u;
+        for (int u = 0; u < SCAN_IT; u++) { sum += v[u]; local_max = max(local_max, v[u]); }
+        uint32_t total;
+        uint32_t off = scan_block_excl(sum, s.warp_sums, &total) + s.carry;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
+        for (int u = 0; u < SCAN_IT; u++) {
+            if (i0 + u < T) { tile_offset[i0 + u] = off; tile_cursor[(size_t)(i0 + u) * CSTRIDE] = off; }
+            off += v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < SCAN_IT; u++) {
+            const int b = bin[u] >= 0 ? bin[u] : SCAN_BINS + lane;      // idle lanes: singleton groups
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            if (bin[u] >= 0 && (peers & lt_mask) == 0) s.table[b][wid] += (uint32_t)__popc(peers);   // the group's first lane owns the row entry
+            if (want_order1) {
+                const int b1 = bin[u] >= 0 ? bin[u] % 34 : 34 + lane;
+                const unsigned peers1 = __match_any_sync(0xffffffffu, b1);
+                if (bin[u] >= 0 && (peers1 & lt_mask) == 0) s.table1[b1][wid] += (uint32_t)__popc(peers1);
             }
-            if (lane < NW) s.warp_sums[lane] = w;
+            __syncwarp();
         }
         __syncthreads();
-        const uint32_t carry = s.carry;
-        const uint32_t incl = x + (wid ? s.warp_sums[wid - 1] : 0u) + carry;
-        if (i < T) ws.tile_offset[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == NT - 1) s.carry = incl;
+        if (tid == 0) s.carry += total;
         __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if (lane == 0) atomicMax(&s.maxv, local_max);
+    if (lane == 0 && local_max) atomicMax(&s.maxv, local_max);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // ---- bases: exclusive scan over the tables in output order (bins descending — blending kind first —, warps ascending) ----
+    {
+        // tile_order2: flat entry f = r * 32 + w, r = 0..67 <-> bin 67 - r  (bins 67..34: blending tiles by descending class)
+        uint32_t c[3], excl_total;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int f = tid * 3 + k;
+            c[k] = (f < SCAN_BINS * SCAN_NW) ? s.table[SCAN_BINS - 1 - (f >> 5)][f & 31] : 0u;
+            mine += c[k];
+        }
+        uint32_t run = scan_block_excl(mine, s.warp_sums, &excl_total);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int f = tid * 3 + k;
+            if (f < SCAN_BINS * SCAN_NW) s.table[SCAN_BINS - 1 - (f >> 5)][f & 31] = run;
+            run += c[k];
+        }
+    }
+    if (want_order1) {
+        uint32_t c[2], excl_total;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int f = tid * 2 + k;
+            c[k] = (f < 34 * SCAN_NW) ? s.table1[33 - (f >> 5)][f & 31] : 0u;
+            mine += c[k];
+        }
+        uint32_t run = scan_block_excl(mine, s.warp_sums, &excl_total);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int f = tid * 2 + k;
+            if (f < 34 * SCAN_NW) s.table1[33 - (f >> 5)][f & 31] = run;
+            run += c[k];
+        }
+    }
+    __syncthreads();
+    if (tid < 34) {
+        // tiles of class >= b (both kinds) = position at which class b - 1 starts in tile_order... computed from the tile_order2
+        // table: a bin's size = next bin's base - its base
+        const int b = tid;
+        auto bin_size = [&](int bn) {   // tile_order2 bases are in order 67, 66, ..., 0
+            const uint32_t beg = s.table[bn][0];
+            const uint32_t end = bn > 0 ? s.table[bn - 1][0] : (uint32_t)T;
+            return end - beg;
+        };
+        s.bin_total[b] = bin_size(b);
+        s.bin_total[b + 34] = bin_size(b + 34);
+    }
+    __syncthreads();
+    if (tid == 0) {
         const uint32_t total = s.carry;
-        ws.tile_offset[T] = total;
-        ws.hdr->stats.num_rendered = total;
-        ws.hdr->stats.overflow = (total > ws.hdr->cap || ws.hdr->stage_cursor > ws.stage_cap) ? 1u : 0u;
-        ws.hdr->stats.max_tile_instances = s.maxv;
-        // tile order for the per-tile kernels: descending power-of-two size class (longest-processing-time-first)
+        tile_offset[T] = total;
+        hdr->stats.num_rendered = total;
+        hdr->stats.overflow = (total > hdr->cap || hdr->stage_cursor > stage_cap) ? 1u : 0u;
+        hdr->stats.max_tile_instances = s.maxv;
         uint32_t run = 0;
 #pragma unroll 1
-        for (int b = 32; b >= 0; b--) {
-            s.bucket_cnt[b] = s.bucket_cnt2[b] + s.bucket_cnt2[b + 34];
-            s.bucket_base[b] = run; run += s.bucket_cnt[b]; ws.hdr->cum_class[b] = run;
-        }
-        ws.hdr->cum_class[33] = 0;
-        // second order for the lazy blend kernels: blending tiles (kind 1) first, each kind by descending class
-        run = 0;
+        for (int b = 32; b >= 0; b--) { run += s.bin_total[b] + s.bin_total[b + 34]; hdr->cum_class[b] = run; }
+        hdr->cum_class[33] = 0;
+        uint32_t k1 = 0;
 #pragma unroll 1
-        for (int k = 1; k >= 0; k--) {
-            const uint32_t at = run;
-#pragma unroll 1
-            for (int b = 32; b >= 0; b--) { s.bucket_base2[b + 34 * k] = run; run += s.bucket_cnt2[b + 34 * k]; }
-            ws.hdr->lazy_count[k] = run - at;
+        for (int b = 0; b < 34; b++) k1 += s.bin_total[b + 34];
+        hdr->lazy_count[1] = k1;
+        hdr->lazy_count[0] = (uint32_t)T - k1;
+    }
+    // ---- pass B: positions = base of (bin, warp) + rank inside the warp; the row entry is the warp's running cursor ----
+    for (int base = 0; base < T; base += SCAN_NT * SCAN_IT) {
+        const int i0 = base + tid * SCAN_IT;
+        uint32_t v[SCAN_IT];
+        int bin[SCAN_IT];
+        load(i0, v, bin);
+#pragma unroll
+        for (int u = 0; u < SCAN_IT; u++) {
+            const int b = bin[u] >= 0 ? bin[u] : SCAN_BINS + lane;
+            {
+                const unsigned peers = __match_any_sync(0xffffffffu, b);
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (bin[u] >= 0 && lane == leader) { old = s.table[b][wid]; s.table[b][wid] = old + (uint32_t)__popc(peers); }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                if (bin[u] >= 0) tile_order2[old + __popc(peers & lt_mask)] = (uint32_t)(i0 + u);
+            }
+            if (want_order1) {
+                const int b1 = bin[u] >= 0 ? bin[u] % 34 : 34 + lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, b1);
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (bin[u] >= 0 && lane == leader) { old = s.table1[b1][wid]; s.table1[b1][wid] = old + (uint32_t)__popc(peers); }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                if (bin[u] >= 0) tile_order[old + __popc(peers & lt_mask)] = (uint32_t)(i0 + u);
+            }
+            __syncwarp();
         }
     }
-    __syncthreads();
-    for (int base = 0; base < T; base += NT) {
-        const int i = base + threadIdx.x;
-        const uint32_t c = (i < T) ? __ldcg(&ws.tile_count[(size_t)i * CSTRIDE]) : 0u;
-        const int kind = (i < T && ws.tile_blend != nullptr && ws.tile_blend[i]) ? 1 : 0;
-        const int cls = (i < T) ? (c ? 32 - __clz(c) : 0) : 33 + lane;
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, cls);
-            const unsigned lower = peers & ((1u << lane) - 1u);
-            uint32_t pos = 0;
-            if (i < T && lower == 0) pos = atomicAdd(&s.bucket_base[cls], (uint32_t)__popc(peers));
-            pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1) + __popc(lower);
-            if (i < T) ws.tile_order[pos] = (uint32_t)i;
-        }
-        {
-            const int cls2 = (i < T) ? cls + 34 * kind : 68 + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, cls2);
-            const unsigned lower = peers & ((1u << lane) - 1u);
-            uint32_t pos = 0;
-            if (i < T && lower == 0) pos = atomicAdd(&s.bucket_base2[cls2], (uint32_t)__popc(peers));
-            pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1) + __popc(lower);
-            if (i < T) ws.tile_order2[pos] = (uint32_t)i;
-        }
-    }
+}
+
+cudaError_t launch_tile_scan(const Workspace& ws, bool want_order1, cudaStream_t st) {
+    // an ordinary launch (it needs all of k_pre); the colour kernel that follows is its programmatic dependent
+    return launch_chained(false, k_tile_scan, dim3(1), dim3(SCAN_NT), 0, st, ws.hdr, (const uint32_t*)ws.tile_count, ws.tile_offset,
+                          ws.tile_cursor, ws.tile_order, ws.tile_order2, (const uint8_t*)ws.tile_blend, ws.stage_cap,
+                          want_order1 ? 1 : 0);
 }
 
 cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
@@ -1023,7 +1112,9 @@ cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, in
 }
 
 cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {
-    const int grid = num_sms * 6;
+    // 6 CTAs per SM on all SMs but one: k_tile_scan's 1024-thread CTA runs beside this kernel (PDL pair) and fills most of
+    // an SM; with a grid that needs every slot, the CTAs that find theirs taken would run as a second wave after the scan
+    const int grid = max(1, num_sms - 1) * 6;
     // TMA bulk gathers need 16-byte aligned bases (the SH window logic handles the 4-byte aligned per-Gaussian offsets)
     const bool packed = mode == MODE_FOV && in.packed_rows != nullptr && (((uintptr_t)in.packed_rows) & 15) == 0;
     const bool aligned = packed || (((uintptr_t)in.shs | (uintptr_t)in.shs_dcs | (uintptr_t)in.opacities) & 15) == 0;
@@ -1031,20 +1122,20 @@ cudaError_t launch_color(const Workspace& ws, const FrameInputs& in, Mode mode, 
     if (aligned && nsh <= (packed ? 45 : 48) && !g_no_tma) {
         const size_t shs_floats = (size_t)in.P * (size_t)nsh;
         switch (mode) {
-            case MODE_OBB: k_color_tma<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
-            case MODE_SUM: k_color_tma<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
-            case MODE_SMFR: k_color_tma<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
-            case MODE_MMFR: k_color_tma<MODE_MMFR><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
-            default: k_color_tma<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in, shs_floats); break;
+            case MODE_OBB: launch_chained(true, k_color_tma<MODE_OBB>, dim3(grid), dim3(CW * 32), 0, st, ws, in, shs_floats); break;
+            case MODE_SUM: launch_chained(true, k_color_tma<MODE_SUM>, dim3(grid), dim3(CW * 32), 0, st, ws, in, shs_floats); break;
+            case MODE_SMFR: launch_chained(true, k_color_tma<MODE_SMFR>, dim3(grid), dim3(CW * 32), 0, st, ws, in, shs_floats); break;
+            case MODE_MMFR: launch_chained(true, k_color_tma<MODE_MMFR>, dim3(grid), dim3(CW * 32), 0, st, ws, in, shs_floats); break;
+            default: launch_chained(true, k_color_tma<MODE_FOV>, dim3(grid), dim3(CW * 32), 0, st, ws, in, shs_floats); break;
         }
         return cudaGetLastError();
     }
     switch (mode) {
-        case MODE_OBB: k_color<MODE_OBB><<<grid, CW * 32, 0, st>>>(ws, in); break;
-        case MODE_SUM: k_color<MODE_SUM><<<grid, CW * 32, 0, st>>>(ws, in); break;
-        case MODE_SMFR: k_color<MODE_SMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
-        case MODE_MMFR: k_color<MODE_MMFR><<<grid, CW * 32, 0, st>>>(ws, in); break;
-        default: k_color<MODE_FOV><<<grid, CW * 32, 0, st>>>(ws, in); break;
+        case MODE_OBB: launch_chained(true, k_color<MODE_OBB>, dim3(grid), dim3(CW * 32), 0, st, ws, in); break;
+        case MODE_SUM: launch_chained(true, k_color<MODE_SUM>, dim3(grid), dim3(CW * 32), 0, st, ws, in); break;
+        case MODE_SMFR: launch_chained(true, k_color<MODE_SMFR>, dim3(grid), dim3(CW * 32), 0, st, ws, in); break;
+        case MODE_MMFR: launch_chained(true, k_color<MODE_MMFR>, dim3(grid), dim3(CW * 32), 0, st, ws, in); break;
+        default: launch_chained(true, k_color<MODE_FOV>, dim3(grid), dim3(CW * 32), 0, st, ws, in); break;
     }
     return cudaGetLastError();
 }

@@ -196,10 +196,7 @@ struct SetupArgs {
 
 __global__ void k_setup(Workspace ws, SetupArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < a.tiles) {
-        ws.tile_count[(size_t)t * CSTRIDE] = 0;
-        ws.tile_cursor[(size_t)t * CSTRIDE] = 0;
-    }
+    if (t < a.tiles) ws.tile_count[(size_t)t * CSTRIDE] = 0;   // tile_cursor is initialised by the tile scan
     if (blockIdx.x == 0) {
         FrameHeader* h = ws.hdr;
         const int i = threadIdx.x;
@@ -402,10 +399,17 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     const int T = gx * gy;
     const int num_sms = device_sm_count();
     prof_mark(1, st);
-    launch_pre(ws, in, (Mode)MODE, num_sms, st);      // + tile scan, by the last CTA to finish
+    launch_pre(ws, in, (Mode)MODE, num_sms, st);
+    STAGE_CHECK();
+    prof_mark(2, st);
+    // All variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the complete sorted
+    // lists.  The training variant appends the sorted prefix it composites to point_list: exactly what its backward walks.
+    const bool lazy = in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
+    launch_tile_scan(ws, !lazy, st);                  // one CTA; the colour kernel runs beside it (PDL pair)
+    launch_color(ws, in, (Mode)MODE, num_sms, st);
     STAGE_CHECK();
     if (in.early_stats_host != nullptr) {
-        // instance count, overflow flag, visible count are final here: the host can have them a third of the way into the frame
+        // instance count, overflow flag, visible count are final here: the host can have them well before the frame ends
         cudaError_t e_ = cudaMemcpyAsync(in.early_stats_host, ws.hdr, sizeof(fovgs_frame_stats), cudaMemcpyDeviceToHost, st);
         if (e_ != cudaSuccess) return e_;
         if (in.early_stats_event != nullptr) {
@@ -413,15 +417,9 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
             if (e_ != cudaSuccess) return e_;
         }
     }
-    prof_mark(2, st);
-    launch_color(ws, in, (Mode)MODE, num_sms, st);
-    STAGE_CHECK();
     prof_mark(3, st);
     launch_scatter(ws, num_sms, st);
     STAGE_CHECK();
-    // All variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the complete sorted
-    // lists.  The training variant appends the sorted prefix it composites to point_list: exactly what its backward walks.
-    const bool lazy = in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
     prof_mark(4, st);
     if (!lazy) {
         launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);

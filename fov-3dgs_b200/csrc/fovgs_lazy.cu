@@ -1001,10 +1001,10 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
 
 // ---- the kernel: persistent CTAs draw tiles of ONE kind, heaviest first, from a ticket counter ---------------------------
 // A foveated frame launches it twice: BK = 1 (blending tiles) then BK = 0 (plain tiles).  The two launches are independent
-// (disjoint tiles, disjoint pixels), so the second is a programmatic dependent launch: the first calls
-// griddepcontrol.launch_dependents on entry, and the plain-tile CTAs move onto the SMs as the blending-tile CTAs run out
-// of tickets and exit — no idle tail between them.  The second grid's CTAs execute griddepcontrol.wait before THEY exit, so
-// the stream (next stage, next frame) only proceeds once both grids are complete and flushed.
+// (disjoint tiles, disjoint pixels), so they form a programmatic-dependent-launch pair (fovgs_internal.cuh): the first
+// triggers on entry, and the plain-tile CTAs move onto the SMs as the blending-tile CTAs run out of tickets and exit — no
+// idle tail between them.  The second grid's CTAs wait before THEY exit, so the stream (next stage, next frame) only
+// proceeds once both grids are complete and flushed.  `pdl`: 0 single launch, 1 first of a pair, 2 second of a pair.
 #ifndef LAZY_CTAS_BLEND
 #define LAZY_CTAS_BLEND 4      // blending-tile instantiations (A/B: 3 CTAs/SM at 80 registers is 3 % slower)
 #endif
@@ -1012,7 +1012,7 @@ template <int MODE, int STAT = STAT_SUM, int BK = 0>
 __global__ void __launch_bounds__(256, BK ? LAZY_CTAS_BLEND : LAZY_CTAS) k_lazy_blend(Workspace ws, FrameInputs in, int pdl) {
     extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
     LazySmem& sm = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
-    if (pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (pdl == 1) pdl_trigger();
 #if LAZY_STAGE == 2
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar[0], 256);
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(256, BK ? LAZY_CTAS_BLEND : LAZY_CTAS) k_lazy_
         lazy_one_tile<MODE, STAT, BK>(sm, lazy_smem_raw, ws, in, (int)ws.tile_order2[base + t]);
         __syncthreads();      // the tile's shared memory (and sm.ticket) is free again
     }
-    if (pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (pdl == 2) pdl_wait();
 }
 
 template <class K>
@@ -1060,7 +1060,7 @@ static cudaError_t launch_lazy_kernel(K kernel, int grid, size_t smem, cudaStrea
     return cudaLaunchKernelEx(&cfg, kernel, ws, in, pdl);
 }
 
-bool g_no_pdl = false;   // fovgs_set_option(FOVGS_OPT_NO_PDL, 1): the two blend launches of a foveated frame run back to back
+bool g_no_pdl = false;   // fovgs_set_option(FOVGS_OPT_NO_PDL, 1): every kernel of a frame is an ordinary launch (no programmatic dependent launches)
 
 cudaError_t launch_lazy_blend(const Workspace& ws, const FrameInputs& in, int T, Mode mode, cudaStream_t st) {
     static_assert(sizeof(SumSmemExtra) <= sizeof(BlendStage), "SumSmemExtra must fit the second staging buffer");

@@ -30,8 +30,8 @@ _TRAIN_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC)
 _PS1_ABI_MODE = {MODE_OBB: _lib.FOVGS_PS1_OBB, MODE_SUM: _lib.FOVGS_PS1_SUM, MODE_MAX: _lib.FOVGS_PS1_MAX,
                  MODE_LWMC: _lib.FOVGS_PS1_LWMC}
 _DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
-# Blocking (default) mode waits for the statistics the library copies out right after the binning stage (instance count,
-# overflow flag: final a third of the way into the frame) — not for the end of the frame: the call returns with a validated
+# Blocking (default) mode waits for the statistics the library copies out right after the colour stage, which hosts the tile scan (instance count,
+# overflow flag: final under half of the way into the frame) — not for the end of the frame: the call returns with a validated
 # instance count while colour / scatter / blend are still running, and an overflow is repaired (the frame re-runs into the same
 # outputs, stream-ordered) before anybody can have consumed it.  The blend stage's own counters (`blend_consumed`,
 # `blend_block_pairs`) are only final at the end of the frame: FOVGS_FULL_STATS=1 / set_full_stats(True) waits for them.
