@@ -299,6 +299,7 @@ int fovgs_set_option(int32_t option, int32_t value) {
 
 int fovgs_profile_enable(int32_t on) {
     g_prof.enabled = on != 0;
+    g_prof.blend_only = on == 2;
     g_prof.valid = 0;
     g_prof.frames = 0;
     return 0;
@@ -313,6 +314,7 @@ static int profile_read_slot(int slot, float* ms_out_host, int32_t n) {
     cudaError_t e = cudaEventSynchronize(g_prof.ev[slot][StageProfile::N - 1]);
     if (e != cudaSuccess) return fail_cuda(e, "profile_read");
     for (int i = 0; i + 1 < StageProfile::N; i++) {
+        if (g_prof.blend_only && i != StageProfile::N - 2) { ms_out_host[i] = 0.0f; continue; }   // only the blend was bracketed
         e = cudaEventElapsedTime(&ms_out_host[i], g_prof.ev[slot][i], g_prof.ev[slot][i + 1]);
         if (e != cudaSuccess) return fail_cuda(e, "profile_read");
     }

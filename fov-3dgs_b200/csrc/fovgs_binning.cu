@@ -710,6 +710,9 @@ __device__ __forceinline__ void scatter_role(const Workspace& ws, const uint32_t
     }
 }
 
+// Measured and dropped (profiles/README.md, r2): launching this kernel as the programmatic dependent of k_tile_scan and the
+// colour kernel as ITS dependent, so that scatter (L2 atomics, LSU wavefronts) and colour gathers (HBM rows) run side by
+// side — 1.041 ms per frame against 1.021 ms with the colour stage first and the scatter alone after it.
 __global__ void __launch_bounds__(256) k_scatter(Workspace ws) {
     scatter_role(ws, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
@@ -886,7 +889,7 @@ __global__ void __launch_bounds__(CW * 32) k_color_tma(Workspace ws, FrameInputs
 // `match.any` into its own row of a [warp][class] table, one block scan over the table (class-major, warp-minor) turns the
 // rows into bases.  Counters are read with ld.cg: they were only ever touched by L2 atomics.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SCAN_NT = 1024, SCAN_NW = SCAN_NT / 32, SCAN_IT = 8;
+constexpr int SCAN_NT = 512, SCAN_NW = SCAN_NT / 32, SCAN_IT = 8;   // 512 threads x ~54 registers: leaves room for other kernels' CTAs on its SM
 constexpr int SCAN_BINS = 68;      // (kind, class): class = 32 - clz(n) in [0, 32] (0: empty), bin = class + 34 * kind
 struct ScanSmem {
     uint32_t warp_sums[SCAN_NW];
@@ -905,7 +908,7 @@ __device__ __forceinline__ uint32_t scan_block_excl(uint32_t x, uint32_t* warp_s
     __syncthreads();                         // warp_sums may still be read by the previous call
     if (lane == 31) warp_sums[wid] = incl;
     __syncthreads();
-    uint32_t w = warp_sums[lane];            // SCAN_NW == 32: one value per lane
+    uint32_t w = lane < SCAN_NW ? warp_sums[lane] : 0u;
     uint32_t wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) k_tile_scan(FrameHeader* hdr, cons
                                                           uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_order2,
                                                           const uint8_t* __restrict__ tile_blend, uint32_t stage_cap,
                                                           int want_order1) {
-    static_assert(SCAN_NW == 32, "scan_block_excl assumes 32 warps");
+    static_assert(SCAN_NW <= 32, "scan_block_excl scans the warp sums in one warp");
     __shared__ ScanSmem s;
     pdl_trigger();                           // the colour kernel may start now: it shares nothing with this one
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -985,36 +988,38 @@ __global__ void __launch_bounds__(SCAN_NT, 1) k_tile_scan(FrameHeader* hdr, cons
     // ---- bases: exclusive scan over the tables in output order (bins descending — blending kind first —, warps ascending) ----
     {
         // tile_order2: flat entry f = r * 32 + w, r = 0..67 <-> bin 67 - r  (bins 67..34: blending tiles by descending class)
-        uint32_t c[3], excl_total;
+        constexpr int E2 = (SCAN_BINS * SCAN_NW + SCAN_NT - 1) / SCAN_NT;
+        uint32_t c[E2], excl_total;
         uint32_t mine = 0;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int f = tid * 3 + k;
-            c[k] = (f < SCAN_BINS * SCAN_NW) ? s.table[SCAN_BINS - 1 - (f >> 5)][f & 31] : 0u;
+        for (int k = 0; k < E2; k++) {
+            const int f = tid * E2 + k;
+            c[k] = (f < SCAN_BINS * SCAN_NW) ? s.table[SCAN_BINS - 1 - f / SCAN_NW][f % SCAN_NW] : 0u;
             mine += c[k];
         }
         uint32_t run = scan_block_excl(mine, s.warp_sums, &excl_total);
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int f = tid * 3 + k;
-            if (f < SCAN_BINS * SCAN_NW) s.table[SCAN_BINS - 1 - (f >> 5)][f & 31] = run;
+        for (int k = 0; k < E2; k++) {
+            const int f = tid * E2 + k;
+            if (f < SCAN_BINS * SCAN_NW) s.table[SCAN_BINS - 1 - f / SCAN_NW][f % SCAN_NW] = run;
             run += c[k];
         }
     }
     if (want_order1) {
-        uint32_t c[2], excl_total;
+        constexpr int E1 = (34 * SCAN_NW + SCAN_NT - 1) / SCAN_NT;
+        uint32_t c[E1], excl_total;
         uint32_t mine = 0;
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int f = tid * 2 + k;
-            c[k] = (f < 34 * SCAN_NW) ? s.table1[33 - (f >> 5)][f & 31] : 0u;
+        for (int k = 0; k < E1; k++) {
+            const int f = tid * E1 + k;
+            c[k] = (f < 34 * SCAN_NW) ? s.table1[33 - f / SCAN_NW][f % SCAN_NW] : 0u;
             mine += c[k];
         }
         uint32_t run = scan_block_excl(mine, s.warp_sums, &excl_total);
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int f = tid * 2 + k;
-            if (f < 34 * SCAN_NW) s.table1[33 - (f >> 5)][f & 31] = run;
+        for (int k = 0; k < E1; k++) {
+            const int f = tid * E1 + k;
+            if (f < 34 * SCAN_NW) s.table1[33 - f / SCAN_NW][f % SCAN_NW] = run;
             run += c[k];
         }
     }

@@ -345,6 +345,7 @@ static inline void prof_mark(int i, cudaStream_t st) {
         g_prof.created = true;
     }
     if (i == 0) g_prof.frames++;
+    if (g_prof.blend_only && i < StageProfile::N - 2) { g_prof.valid = i + 1; return; }
     cudaEventRecord(g_prof.ev[(g_prof.frames - 1) % StageProfile::SLOTS][i], st);
     g_prof.valid = i + 1;
 }
@@ -405,8 +406,11 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     // All variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the complete sorted
     // lists.  The training variant appends the sorted prefix it composites to point_list: exactly what its backward walks.
     const bool lazy = in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
-    launch_tile_scan(ws, !lazy, st);                  // one CTA; the colour kernel runs beside it (PDL pair)
-    launch_color(ws, in, (Mode)MODE, num_sms, st);
+    launch_tile_scan(ws, !lazy, st);                  // one CTA, an ordinary launch; triggers its dependent on entry
+    launch_color(ws, in, (Mode)MODE, num_sms, st);    // its programmatic dependent: runs beside the scan
+    STAGE_CHECK();
+    prof_mark(3, st);
+    launch_scatter(ws, num_sms, st);
     STAGE_CHECK();
     if (in.early_stats_host != nullptr) {
         // instance count, overflow flag, visible count are final here: the host can have them well before the frame ends
@@ -417,9 +421,6 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
             if (e_ != cudaSuccess) return e_;
         }
     }
-    prof_mark(3, st);
-    launch_scatter(ws, num_sms, st);
-    STAGE_CHECK();
     prof_mark(4, st);
     if (!lazy) {
         launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);

@@ -786,8 +786,10 @@ def geometry(item, mode, P, W, H):
 STAGE_NAMES = ("setup", "preprocess", "color", "scatter", "tile_sort", "blend")
 
 
-def profile_enable(on=True):
-    check(lib().fovgs_profile_enable(1 if on else 0), "fovgs_profile_enable")
+def profile_enable(on=True, blend_only=False):
+    """Stage events on the launch stream.  blend_only: bracket just the blend stage (2 events per frame instead of 7; the
+    other durations read 0) — what bench.py's timed loop uses so the headline carries the dominant kernel's live time."""
+    check(lib().fovgs_profile_enable((2 if blend_only else 1) if on else 0), "fovgs_profile_enable")
 
 
 def profile_read():
