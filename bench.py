@@ -764,6 +764,7 @@ def main():
             line["gather"] = gathered
         if args.impl == "reference":
             line["impl"] = "reference"
+            line["e2e"]["mode"] = "default drop-in call: the reference's own blocking call (it synchronises with the host inside every frame)"
             line["reference_class"] = "gpu: the unmodified reference CUDA extension (oracle/_ref, built by oracle/build_ref.py) on the same B200"
             line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": "reference CUDA rasterizer on the same B200 (reference_class)"}

@@ -63,6 +63,9 @@ __forceinline__ __device__ void tl_ps2level(const float pooling_size, float& lev
 
 __global__ void k_tile_levels(int T, float* __restrict__ tile_levels, const float* __restrict__ gaze_ptr, const int W,
                               const int H, const int tile_width_num, const float alpha) {
+    // second of a programmatic-dependent-launch pair with k_setup (which touches nothing this kernel reads or writes): the
+    // wait below, before exit, keeps the stream's order for k_tile_infos
+    struct ExitWait { __device__ ~ExitWait() { pdl_wait(); } } exit_wait;
     auto idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)T) return;
     const float2 gaze = make_float2(gaze_ptr[0], gaze_ptr[1]);
@@ -195,6 +198,7 @@ struct SetupArgs {
 };
 
 __global__ void k_setup(Workspace ws, SetupArgs a) {
+    pdl_trigger();   // k_tile_levels (foveated frames) may run beside this kernel
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.tiles) ws.tile_count[(size_t)t * CSTRIDE] = 0;   // tile_cursor is initialised by the tile scan
     if (blockIdx.x == 0) {
@@ -366,7 +370,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     prof_mark(0, st);
     k_setup<<<(T + 255) / 256, 256, 0, st>>>(ws, a);
     if (is_foveated(mode)) {
-        k_tile_levels<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, gaze, a.W, a.H, a.gx, alpha);
+        launch_chained(true, k_tile_levels, dim3((T + 255) / 256), dim3(256), 0, st, T, ws.tile_level, gaze, a.W, a.H, a.gx, alpha);
         k_tile_infos<<<(T + 255) / 256, 256, 0, st>>>(T, ws.tile_level, a.gx, a.gy, ws.tile_gy, ws.tile_gx, ws.tile_min,
                                                      ws.tile_blend, ws.hdr, mode == MODE_MMFR ? 1 : 0, cur_level, ws.tile_skip, ws.tile_code);
     }
@@ -409,9 +413,6 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     launch_tile_scan(ws, !lazy, st);                  // one CTA, an ordinary launch; triggers its dependent on entry
     launch_color(ws, in, (Mode)MODE, num_sms, st);    // its programmatic dependent: runs beside the scan
     STAGE_CHECK();
-    prof_mark(3, st);
-    launch_scatter(ws, num_sms, st);
-    STAGE_CHECK();
     if (in.early_stats_host != nullptr) {
         // instance count, overflow flag, visible count are final here: the host can have them well before the frame ends
         cudaError_t e_ = cudaMemcpyAsync(in.early_stats_host, ws.hdr, sizeof(fovgs_frame_stats), cudaMemcpyDeviceToHost, st);
@@ -421,6 +422,9 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
             if (e_ != cudaSuccess) return e_;
         }
     }
+    prof_mark(3, st);
+    launch_scatter(ws, num_sms, st);
+    STAGE_CHECK();
     prof_mark(4, st);
     if (!lazy) {
         launch_tile_sort(ws, T, in.out_ranges, in.out_point_list, st);

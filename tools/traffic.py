@@ -14,7 +14,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGE = {"k_pre": "preprocess", "k_color": "color", "k_scatter": "scatter", "k_lazy_blend": "blend", "k_setup": "setup",
+STAGE = {"k_pre": "preprocess", "k_tile_scan": "color", "k_color": "color", "k_scatter": "scatter", "k_lazy_blend": "blend", "k_setup": "setup",
          "k_tile_levels": "setup", "k_tile_infos": "setup"}
 
 
