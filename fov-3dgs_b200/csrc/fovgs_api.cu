@@ -80,7 +80,7 @@ int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
     if (a->P < 0 || a->P > kMaxP) return fail(FOVGS_ERR_INVALID_ARG, "means3D must have dimensions (num_points, 3), num_points <= 2^30%s");
-    if (!a->out_color || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
+    if ((!a->out_color && !a->out_color_u8) || (a->P > 0 && !a->radii)) return fail(FOVGS_ERR_INVALID_ARG, "null output pointer%s");
     if (a->P == 0) return 0;  // reference: outputs stay at their initial value (rasterize_points.cu:103)
     if (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->shs_dcs || !a->highest_levels || !a->gaze)
         return fail(FOVGS_ERR_INVALID_ARG, "null input pointer (means3D/opacities/scales/rotations/shs_dcs/highest_levels/gaze)%s");
@@ -94,7 +94,7 @@ int fovgs_forward_fov(const fovgs_fov_fwd_args* a, void* stream) {
     in.P = a->P; in.M = a->M_rest;
     in.means3D = a->means3D; in.opacities = a->opacities; in.scales = a->scales; in.rotations = a->rotations;
     in.shs = a->M_rest > 0 ? a->shs_rest : nullptr; in.shs_dcs = a->shs_dcs; in.highest_levels = a->highest_levels;
-    in.radii = a->radii; in.out_color = a->out_color;
+    in.radii = a->radii; in.out_color = a->out_color; in.out_color_u8 = a->out_color_u8;
     in.out_ranges = a->out_ranges; in.out_point_list = a->out_point_list;
     in.early_stats_host = a->early_stats_host; in.early_stats_event = a->early_stats_event;
     in.packed_rows = (a->M_rest <= 15) ? a->packed_color_rows : nullptr;
@@ -179,7 +179,7 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     if (int r = check_cam(a->cam)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = a->cam.image_width, H = a->cam.image_height;
-    if (a->mode < FOVGS_PS1_OBB || a->mode > FOVGS_PS1_LWMC) return fail(FOVGS_ERR_INVALID_ARG, "bad ps1 mode%s");
+    if (a->mode < FOVGS_PS1_OBB || a->mode > FOVGS_PS1_VANILLA) return fail(FOVGS_ERR_INVALID_ARG, "bad ps1 mode%s");
     const Mode mode = a->mode != FOVGS_PS1_OBB ? MODE_SUM : MODE_OBB;
     if (a->mode == FOVGS_PS1_LWMC && !a->loss_map && a->P > 0)
         return fail(FOVGS_ERR_INVALID_ARG, "the loss-weighted variant needs loss_map [H,W]%s");
@@ -196,7 +196,8 @@ int fovgs_forward_ps1(const fovgs_ps1_fwd_args* a, void* stream) {
     if (a->max_instances <= 0 || a->max_instances > 0xffffffffll) return fail(FOVGS_ERR_INVALID_ARG, "max_instances out of range%s");
     Workspace ws = carve_workspace(a->workspace, a->P, W, H, a->max_instances, mode);
     if (!a->workspace || a->workspace_bytes < ws.total_bytes) return fail(FOVGS_ERR_WORKSPACE, "workspace too small%s");
-    cudaError_t e = launch_setup(ws, a->cam, a->P, a->colors_precomp ? 0 : a->M, mode, nullptr, 0.0f, 0.0f, (uint32_t)a->max_instances, st);
+    cudaError_t e = launch_setup(ws, a->cam, a->P, a->colors_precomp ? 0 : a->M, mode, nullptr, 0.0f, 0.0f, (uint32_t)a->max_instances, st,
+                                 a->mode == FOVGS_PS1_VANILLA);
     if (e != cudaSuccess) return fail_cuda(e, "setup");
     FrameInputs in{};
     in.P = a->P; in.M = a->M;

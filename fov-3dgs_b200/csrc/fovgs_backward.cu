@@ -29,11 +29,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Conservative footprint test of one splat against a warp's 8x4 pixel block: false only when no pixel of the block can pass
 // `power >= -4.5 && opacity*exp(power) >= 1/255` (same bound as block_may_touch in fovgs_lazy.cu; margins cover every fp32
 // rounding involved), i.e. when the exact per-pixel code would produce no gradient for any of the 32 pixels.
-__device__ __forceinline__ bool bwd_block_may_touch(const float4 a, const float conz, const float op, const float X0, const float Y0) {
+__device__ __forceinline__ bool bwd_block_may_touch(const float4 a, const float conz, const float op, const float X0, const float Y0,
+                                                    const float tau_cap) {
     const float dx0 = a.x - (X0 + 7.0f), dx1 = a.x - X0, dy0 = a.y - (Y0 + 3.0f), dy1 = a.y - Y0;
     if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
     const float A = a.z, B = a.w, C = conz;
-    const float tau = fminf(4.5f, __logf(255.0f * op));
+    const float tau = fminf(tau_cap, __logf(255.0f * op));
     const float iA = __frcp_rn(A), iC = __frcp_rn(C);
     auto edge_x = [&](float ex) {
         const float t = fminf(fmaxf(-B * ex * iC, dy0), dy1);
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
     const uint32_t pix_id = (uint32_t)W * pyi + pxi;
     const float pixx = (float)pxi, pixy = (float)pyi;
     const uint32_t cap = hdr->cap;
+    const float cut = hdr->cam.falloff_cut;   // the forward's setting lives on in the workspace: -4.5 (SUM/backward.cu:495), -inf for vanilla
     const uint32_t rbeg = min(ws.tile_offset[tile], cap), rend = min(ws.tile_offset[tile + 1], cap);
     if (rend == rbeg) return;
     const size_t HW = (size_t)H * W;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
         for (int jb = 0; jb < lim; jb += 32) {
             const int j = jb + lane;
             bool keep = false;
-            if (j < lim && (total - 1 - (i * 256 + j)) < wmax) keep = bwd_block_may_touch(sA[j], sB[j].x, sB[j].y, blkx, blky);
+            if (j < lim && (total - 1 - (i * 256 + j)) < wmax) keep = bwd_block_may_touch(sA[j], sB[j].x, sB[j].y, blkx, blky, -cut);
             const unsigned mk = __ballot_sync(0xffffffffu, keep);
             if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
             cnt += __popc(mk);
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) k_bwd_render(Workspace ws, const float* _
                 const float4 b = sB[j];
                 const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
                 const float power = gauss_power(a.z, a.w, b.x, dx, dy);
-                if (!(power > 0.0f || power < -4.5f)) {
+                if (!(power > 0.0f || power < cut)) {
                     const float G = expf(power);
                     const float alpha = fminf(0.99f, FM(b.y, G));
                     if (!(alpha < 1.0f / 255.0f)) {

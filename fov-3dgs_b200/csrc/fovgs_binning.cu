@@ -338,7 +338,9 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
         uint32_t okx = 0, oky = 0, okz = 0;
         int rcw = 0, rcx = 0, rcy = 0;
         if (ok) {
-            const bool single0 = ((uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0)) == 1u;
+            // "single" = no OBB test for this splat: one-tile rectangles (the reference's potential_tnum == 1 shortcut) and, in
+            // the vanilla mode of the training family, every splat (its duplicateWithKeys walks the whole rectangle)
+            const bool single0 = ((uint32_t)(s.y1 - s.y0) * (uint32_t)(s.x1 - s.x0)) == 1u || (MODE == MODE_SUM && cam.no_obb);
             int cx0 = s.x0, cy0 = s.y0, cx1 = s.x1, cy1 = s.y1;
             uint32_t hcode = 0;
             if (is_foveated(MODE)) {

@@ -119,9 +119,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                     used = ((float)mm_L1 == hdr->cur_level) ? w1 : FS(1.0f, w1);
                 }
                 const float o0 = FF(bg0, T, C0), o1 = FF(bg1, T, C1), o2 = FF(bg2, T, C2);
-                in.out_color[pix_id] = mm_blend ? FM(o0, used) : o0;
-                in.out_color[HW + pix_id] = mm_blend ? FM(o1, used) : o1;
-                in.out_color[2 * HW + pix_id] = mm_blend ? FM(o2, used) : o2;
+                store_rgb(in, pix_id, HW, mm_blend ? FM(o0, used) : o0, mm_blend ? FM(o1, used) : o1, mm_blend ? FM(o2, used) : o2);
             }
             if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
         } else {
@@ -223,9 +221,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
                 const float nb = FF(x, FM(x, FA(x, x)), m3);            // -(3x^2 - 2x^3)
                 const float w1 = FA(nb, 1.0f);
                 const float w2 = FS(1.0f, w1);
-                in.out_color[pix_id] = FF(A0, w1, FM(B0, w2));
-                in.out_color[HW + pix_id] = FF(A1, w1, FM(B1, w2));
-                in.out_color[2 * HW + pix_id] = FF(A2, w1, FM(B2, w2));
+                store_rgb(in, pix_id, HW, FF(A0, w1, FM(B0, w2)), FF(A1, w1, FM(B1, w2)), FF(A2, w1, FM(B2, w2)));
             }
             if (tid == 0 && batches_done) atomicAdd(&ws.hdr->stats.reserved[0], (uint32_t)min(total, batches_done * 256));
         }
@@ -249,6 +245,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
     // training family: which statistics (fovgs_lazy.cu explains the three reference variants); this full-sort path keeps
     // the reference's per-hit atomics — it serves parity runs (`out_point_list`), the lazy kernel is the fast one
     const int stat = (MODE == MODE_SUM) ? in.stat : STAT_SUM;
+    const float cut = (MODE == MODE_SUM) ? ws.hdr->cam.falloff_cut : -4.5f;   // -inf: FOVGS_PS1_VANILLA
     int max_idx = 0;
     float max_contrib = 0.0f;
     for (int i = 0; i < rounds; i++, toDo -= 256) {
@@ -270,7 +267,7 @@ __global__ void __launch_bounds__(256) k_blend(Workspace ws, FrameInputs in) {
             const float4 b = sB[j];
             const float dx = FS(a.x, pixx), dy = FS(a.y, pixy);
             const float power = gauss_power(a.z, a.w, b.x, dx, dy);
-            if (power > 0.0f || power < -4.5f) continue;
+            if (power > 0.0f || power < cut) continue;
             if (MODE == MODE_SUM && stat == STAT_MAX) atomicAdd(&in.gaussians_count[sId[j]], 1);
             const float alpha = fminf(0.99f, FM(b.y, BLEND_EXP(power)));
             if (alpha < 1.0f / 255.0f) continue;

@@ -193,7 +193,7 @@ struct SetupArgs {
     const float* bg;
     const float* gaze;
     float tanfovx, tanfovy, focal_x, focal_y, scale_modifier, alpha, cur_level;
-    int W, H, gx, gy, sh_degree, M, P, tiles, prefiltered;
+    int W, H, gx, gy, sh_degree, M, P, tiles, prefiltered, vanilla;
     uint32_t cap;
 };
 
@@ -227,6 +227,8 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->cam.sh_degree = a.sh_degree;
             h->cam.M = a.M;
             h->cam.prefiltered = a.prefiltered;
+            h->cam.no_obb = a.vanilla;
+            h->cam.falloff_cut = a.vanilla ? -INFINITY : -4.5f;
             h->alpha = a.alpha;
             h->cur_level = a.cur_level;
             h->P = a.P;
@@ -355,7 +357,7 @@ static inline void prof_mark(int i, cudaStream_t st) {
 }
 
 cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, int M, Mode mode, const float* gaze,
-                         float alpha, float cur_level, uint32_t cap, cudaStream_t st) {
+                         float alpha, float cur_level, uint32_t cap, cudaStream_t st, bool vanilla) {
     SetupArgs a;
     a.view = cam.viewmatrix; a.proj = cam.projmatrix; a.campos = cam.campos; a.bg = cam.bg; a.gaze = gaze;
     a.tanfovx = cam.tanfovx; a.tanfovy = cam.tanfovy;
@@ -365,7 +367,7 @@ cudaError_t launch_setup(const Workspace& ws, const fovgs_camera& cam, int P, in
     a.scale_modifier = cam.scale_modifier; a.alpha = alpha; a.cur_level = cur_level;
     a.W = cam.image_width; a.H = cam.image_height;
     a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
-    a.sh_degree = cam.sh_degree; a.prefiltered = cam.prefiltered; a.M = M; a.P = P; a.tiles = a.gx * a.gy; a.cap = cap;
+    a.sh_degree = cam.sh_degree; a.prefiltered = cam.prefiltered; a.vanilla = vanilla ? 1 : 0; a.M = M; a.P = P; a.tiles = a.gx * a.gy; a.cap = cap;
     const int T = a.tiles;
     prof_mark(0, st);
     k_setup<<<(T + 255) / 256, 256, 0, st>>>(ws, a);

@@ -87,11 +87,12 @@ struct LazySmem {
 // is a clamped 1-D parabola.  The splat is dropped for this warp only when that minimum exceeds the threshold by more
 // than a bound on every fp32 rounding involved (relative 8e-6 of the largest term magnitudes + 2e-3 absolute), so a
 // dropped splat is one the exact per-pixel code below would have skipped for all 32 pixels: images are unchanged.
-__device__ __forceinline__ bool block_may_touch(const float4 a, const float conz, const float op, const float X0, const float Y0) {
+__device__ __forceinline__ bool block_may_touch(const float4 a, const float conz, const float op, const float X0, const float Y0,
+                                                const float tau_cap = 4.5f) {
     const float dx0 = a.x - (X0 + 7.0f), dx1 = a.x - X0, dy0 = a.y - (Y0 + 3.0f), dy1 = a.y - Y0;
     if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
     const float A = a.z, B = a.w, C = conz;
-    const float tau = fminf(4.5f, __logf(255.0f * op));
+    const float tau = fminf(tau_cap, __logf(255.0f * op));   // tau_cap = +inf: the vanilla mode has no falloff cut
     // MUFU.RCP (1 ulp) instead of the IEEE reciprocal (8 instructions each): the clamped parabola minimum moves by second order
     // in the error of t, far inside the slack of the final comparison
     float iA, iC;
@@ -751,6 +752,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
     uint32_t sorted_count = 0, next = 0, kept = 0;   // next = index of the next 256-batch to composite
     bool done = !inside;
     float max_contrib = 0.0f;   // STAT_LWMC
+    const float cut = ws.hdr->cam.falloff_cut;   // -4.5 (SUM/forward.cu:378); -inf for FOVGS_PS1_VANILLA
     uint8_t* __restrict__ wl = sm.widx[warp];
     lazy_for_each_group(sm, ws, tile, [&](const uint64_t* sk, uint32_t m, bool last) {
         for (uint32_t i = tid; i < m; i += 256) plist[sorted_count + i] = (uint32_t)sk[i];
@@ -777,7 +779,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                     const int j = jb + lane;
                     bool keep = false;
                     // MAX counts entries that pass the falloff cut whatever their alpha: opacity 1 leaves only the -4.5 bound
-                    if (j < lim) keep = block_may_touch(sm.bl[0].sA[j], sm.bl[0].sB[j].x, STAT == STAT_MAX ? 1.0f : sm.bl[0].sB[j].y, blkx, blky);
+                    if (j < lim) keep = block_may_touch(sm.bl[0].sA[j], sm.bl[0].sB[j].x, STAT == STAT_MAX ? 1.0f : sm.bl[0].sB[j].y, blkx, blky, -cut);
                     const unsigned mk = __ballot_sync(0xffffffffu, keep);
                     if (keep) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)j;
                     cnt += __popc(mk);
@@ -788,7 +790,7 @@ __device__ __forceinline__ void lazy_tile_sum(LazySmem& sm, SumSmemExtra& sx, co
                 auto composite = [&](const int j, const float power, bool& in_cut) -> float {
                     float w = 0.0f;
                     in_cut = false;
-                    if (!done && !(power > 0.0f || power < -4.5f)) {
+                    if (!done && !(power > 0.0f || power < cut)) {
                         in_cut = true;
                         // the two rarer outcomes (alpha below 1/255, pixel saturated) are selects, not branches
                         const float4 c = sm.bl[0].sC[j];
@@ -943,9 +945,7 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
             lazy_tile<1, R>(sm, ws, tile, px, pixx, pixy, blkx, blky, S1, 0);
             if (inside) {
                 const float bg0 = hdr->bg[0], bg1 = hdr->bg[1], bg2 = hdr->bg[2];
-                in.out_color[pix_id] = FF(bg0, px.T, px.C0);
-                in.out_color[HW + pix_id] = FF(bg1, px.T, px.C1);
-                in.out_color[2 * HW + pix_id] = FF(bg2, px.T, px.C2);
+                store_rgb(in, pix_id, HW, FF(bg0, px.T, px.C0), FF(bg1, px.T, px.C1), FF(bg2, px.T, px.C2));
             }
         } else {
             const int L2 = L1 + 1;
@@ -964,9 +964,7 @@ __device__ __forceinline__ void lazy_one_tile(LazySmem& sm, unsigned char* smem_
                 const float nb = FF(x, FM(x, FA(x, x)), m3);
                 const float w1 = FA(nb, 1.0f);
                 const float w2 = FS(1.0f, w1);
-                in.out_color[pix_id] = FF(A0, w1, FM(B0, w2));
-                in.out_color[HW + pix_id] = FF(A1, w1, FM(B1, w2));
-                in.out_color[2 * HW + pix_id] = FF(A2, w1, FM(B2, w2));
+                store_rgb(in, pix_id, HW, FF(A0, w1, FM(B0, w2)), FF(A1, w1, FM(B1, w2)), FF(A2, w1, FM(B2, w2)));
             }
         }
     } else if (MODE == MODE_SUM) {

@@ -15,6 +15,7 @@ FOVGS_PS1_OBB = 0
 FOVGS_PS1_SUM = 1
 FOVGS_PS1_MAX = 2
 FOVGS_PS1_LWMC = 3
+FOVGS_PS1_VANILLA = 4
 
 FOVGS_VERSION = 201   # include/fovgs.h; every args struct carries it next to its own size (FOVGS_ARGS_HEADER)
 
@@ -84,6 +85,7 @@ class FovFwdArgs(C.Structure):
         ("packed_color_rows", _f),
         ("early_stats_host", _f),
         ("early_stats_event", _f),
+        ("out_color_u8", _f),
     ]
 
 

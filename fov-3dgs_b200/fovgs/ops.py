@@ -26,9 +26,11 @@ MODE_OBB, MODE_SUM, MODE_FOV = 0, 1, 2
 MODE_MAX, MODE_LWMC = 3, 4
 MODE_SMFR = 5   # shared-model foveation baseline (naive_pcheck_obb)
 MODE_MMFR = 6   # multi-model foveation baseline (mmfr_pcheck_obb), one call per level
-_TRAIN_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC)
+MODE_VANILLA = 7   # the stock diff_gaussian_rasterization: SUM's state and backward; no OBB test, no -4.5 cut, no statistics
+_TRAIN_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC, MODE_VANILLA)      # SUM's workspace layout (final_T, n_contrib, cov3D, point_list)
+_STAT_MODES = (MODE_SUM, MODE_MAX, MODE_LWMC)                     # ... that return gaussians_count / contributions
 _PS1_ABI_MODE = {MODE_OBB: _lib.FOVGS_PS1_OBB, MODE_SUM: _lib.FOVGS_PS1_SUM, MODE_MAX: _lib.FOVGS_PS1_MAX,
-                 MODE_LWMC: _lib.FOVGS_PS1_LWMC}
+                 MODE_LWMC: _lib.FOVGS_PS1_LWMC, MODE_VANILLA: _lib.FOVGS_PS1_VANILLA}
 _DEFERRED = os.environ.get("FOVGS_DEFERRED_CHECK", "0") == "1"
 # Blocking (default) mode waits for the statistics the library copies out right after the colour stage, which hosts the tile scan (instance count,
 # overflow flag: final under half of the way into the frame) — not for the end of the frame: the call returns with a validated
@@ -577,8 +579,9 @@ def forward_mmfr(means3D, opacities, scales, rotations, shs, cur_level, gazeArra
 
 def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs, colors_precomp, raster_settings,
                 want_lists=False, loss_map=None):
-    """PS=1 forward (mode = MODE_OBB | MODE_SUM | MODE_MAX | MODE_LWMC; `loss_map` [H,W] for MODE_LWMC).
-    Returns (num_rendered, color, radii, workspace_item[, gaussians_count, contributions][, point_list, ranges])."""
+    """PS=1 forward (mode = MODE_OBB | MODE_SUM | MODE_MAX | MODE_LWMC | MODE_VANILLA; `loss_map` [H,W] for MODE_LWMC).
+    Returns (num_rendered, color, radii, workspace_item[, gaussians_count, contributions][, point_list, ranges]); the
+    statistics pair is returned by SUM / MAX / LWMC only."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     device = means3D.device
@@ -586,11 +589,12 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
     H, W = int(rs.image_height), int(rs.image_width)
     P = means3D.size(0)
     sum_mode = mode in _TRAIN_MODES
+    stat_mode = mode in _STAT_MODES
     if P == 0:
         z = torch.zeros((3, H, W), dtype=torch.float32, device=device)
         r = torch.zeros((0,), dtype=torch.int32, device=device)
         out = [0, z, r, None]
-        if sum_mode:
+        if stat_mode:
             out += [torch.zeros((0,), dtype=torch.int32, device=device), torch.zeros((0,), dtype=torch.float32, device=device)]
         return tuple(out)
     keep = []
@@ -630,7 +634,7 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
         a.colors_precomp = _ptr(colors_precomp)
         a.out_color = color.data_ptr()
         a.radii = radii.data_ptr()
-        if sum_mode:
+        if sum_mode:   # (vanilla: scratch the C-ABI still wants)
             extra["gcount"] = torch.zeros((P,), dtype=torch.int32, device=device)
             extra["contrib"] = torch.zeros((P,), dtype=torch.float32, device=device)
             a.gaussians_count = extra["gcount"].data_ptr()
@@ -650,7 +654,7 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
     item, st = _run_with_capacity(launch, device, mode, P, W, H, fresh_workspace=sum_mode)
     n = st["num_rendered"] if st is not None else -1
     out = [n, color, radii, item]
-    if sum_mode:
+    if stat_mode:
         out += [extra["gcount"], extra["contrib"]]
     if want_lists:
         out += [lists["point_list"][: max(n, 0)], lists["ranges"]]
@@ -659,7 +663,8 @@ def forward_ps1(mode, means3D, opacities, scales, rotations, cov3D_precomp, shs,
 
 def backward_ps1(workspace_item, means3D, radii, scales, rotations, cov3D_precomp, shs, colors_precomp, raster_settings,
                  grad_out_color):
-    """Gradient of the SUM forward.  Returns the reference's 8-tuple
+    """Gradient of the SUM-family forward (SUM / MAX / LWMC / VANILLA: the falloff cut of the matching forward travels in the
+    workspace).  Returns the reference's 8-tuple
     (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
     device = means3D.device
     rs = raster_settings

@@ -306,10 +306,13 @@ def make_mmfr_api():
 # PS=1: inference (pcheck_obb) and training (pcheck_obb_sum)
 # ------------------------------------------------------------------------------------------------------------
 def _make_ps1_function(mode: int):
-    """mode: ops.MODE_OBB (inference) or one of the training family ops.MODE_SUM / MODE_MAX / MODE_LWMC.  The
+    """mode: ops.MODE_OBB (inference), one of the training family ops.MODE_SUM / MODE_MAX / MODE_LWMC, or ops.MODE_VANILLA
+    (the stock diff_gaussian_rasterization: forward + backward, returns (color, radii) like the reference's
+    fov3dgs/submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py:83-99).  The
     loss-weighted variant takes one more argument, `loss_map`, after `raster_settings`
     (.../pcheck_obb_loss_weighted_max_count/diff_gaussian_rasterization_pcheck_obb_loss_weighted_max_count/__init__.py:24-47)."""
-    sum_mode = mode != ops.MODE_OBB
+    sum_mode = mode != ops.MODE_OBB          # keeps the state a backward needs
+    stat_mode = sum_mode and mode != ops.MODE_VANILLA   # returns gaussians_count / contributions as well
     with_loss_map = mode == ops.MODE_LWMC
 
     class _RasterizeGaussians(torch.autograd.Function):
@@ -343,7 +346,7 @@ def _make_ps1_function(mode: int):
             ctx.num_rendered = num_rendered
             ctx.workspace_item = item  # opaque saved state (replaces geomBuffer/binningBuffer/imgBuffer)
             ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh)
-            if sum_mode:
+            if stat_mode:
                 gaussians_count, contributions = out[4], out[5]
                 ctx.mark_non_differentiable(radii, gaussians_count, contributions)
                 return color, radii, gaussians_count, contributions
@@ -462,6 +465,10 @@ def make_max_api():
 
 def make_lwmc_api():
     return _make_ps1_api(ops.MODE_LWMC)
+
+
+def make_vanilla_api():
+    return _make_ps1_api(ops.MODE_VANILLA)
 
 
 def make_unavailable_api(pkg, why):

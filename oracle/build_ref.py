@@ -12,6 +12,7 @@ The resulting modules are the reference's pybind ``_C`` modules:
   ref_sum_C : rasterize_gaussians(19 args) -> 8-tuple, rasterize_gaussians_backward(21 args), mark_visible
   ref_max_C / ref_lwmc_C : as ref_sum_C (lwmc: 20 args, loss_map before debug)
   ref_naive_C / ref_mmfr_C : the SMFR / MMFR foveation baselines (23 args; mmfr takes cur_level instead of highest_levels)
+  ref_vanilla_C : the stock diff-gaussian-rasterization (19 args -> 6-tuple, rasterize_gaussians_backward(19 args), mark_visible)
 
 Nothing in the product path imports these.  Only tests/, bench.py --impl reference and tools/make_golden.py do.
 """
@@ -35,6 +36,8 @@ VARIANTS = {
     "ref_lwmc_C": ("diff-gaussian-rasterization_pcheck_obb_loss_weighted_max_count", True),
     "ref_naive_C": ("diff-gaussian-rasterization_naive_pcheck_obb", False),
     "ref_mmfr_C": ("diff-gaussian-rasterization_mmfr_pcheck_obb", False),
+    # the stock Inria rasterizer the reference vendors (fov3dgs/gaussian_wrapper.py:2 cuda_type="original")
+    "ref_vanilla_C": ("diff-gaussian-rasterization", True),
 }
 
 

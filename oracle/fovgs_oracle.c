@@ -376,6 +376,8 @@ static int inst_cmp(const void* a, const void* b) {
 
 typedef struct {
     int mode;  /* 0 obb, 1 sum, 2 fov, 3 mmfr (tile_skip instead of the level test) */
+    int no_obb; /* vanilla diff-gaussian-rasterization: every tile of the rectangle gets an instance
+                   (diff-gaussian-rasterization/cuda_rasterizer/rasterizer_impl.cu:70-110: duplicateWithKeys walks the whole rect) */
     const uint8_t* tile_skip;
     const orc_camera* cam;
     int P, M;
@@ -438,8 +440,8 @@ static int64_t run_binning(const bin_in_t* in, bin_out_t* o, float fx, float fy,
                     if (in->mode == 3 && in->tile_skip[tile]) continue;
                     const float tcx = (float)x * (float)BLOCK_X + (float)BLOCK_X / 2.0f;
                     const float tcy = (float)y * (float)BLOCK_Y + (float)BLOCK_Y / 2.0f;
-                    const int hit = obb_check(s, &oc, tcx, tcy);
-                    if (g_ambiguity) {
+                    const int hit = in->no_obb ? 1 : obb_check(s, &oc, tcx, tcy);
+                    if (g_ambiguity && !in->no_obb) {
                         /* a perturbation of 2^-21 moves corners / projections by at most (len + |rel|) * 2^-21 pixels */
                         const float reach = (s->len1 + s->len2 + fabsf(tcx - s->px) + fabsf(tcy - s->py) + 16.0f) * 2e-6f + 1e-4f;
                         if (obb_margin(s, &oc, tcx, tcy) <= reach && obb_rsqrt_sensitive(s, tcx, tcy, hit)) amb_push(tile, (uint32_t)i);
@@ -551,6 +553,8 @@ static void blend_tile_ps1(void* vctx, int tile) {
            (pcheck_obb_loss_weighted_max_count/cuda_rasterizer/forward.cu:347-348,403-408) */
         int max_idx[256]; float max_contrib[256];
         const float* loss_map = c->loss_map;
+        /* mode 4 = vanilla: no `power < -4.5f` cut (diff-gaussian-rasterization/cuda_rasterizer/forward.cu:342), no statistics */
+        const float cut = mode == 4 ? -INFINITY : -4.5f;
         int ndone = 0;
         for (int t = 0; t < 256; t++) {
             const int px = tx * 16 + (t & 15), py = ty * 16 + (t >> 4);
@@ -577,7 +581,7 @@ static void blend_tile_ps1(void* vctx, int tile) {
                     contributor[t]++;
                     const float dx = s->px - pxf, dy = s->py - pyf;
                     const float power = gauss_power(s->conx, s->cony, s->conz, dx, dy);
-                    if (power > 0.0f || power < -4.5f) continue;
+                    if (power > 0.0f || power < cut) continue;
                     /* MAX: one count per (pixel, Gaussian) that passes the falloff cut (pcheck_obb_max/forward.cu:381) */
                     if (mode == 2) __atomic_fetch_add(&gaussians_count[id], 1, __ATOMIC_RELAXED);
                     const float alpha = fminf(0.99f, opacity[id] * expf(power));
@@ -588,7 +592,7 @@ static void blend_tile_ps1(void* vctx, int tile) {
                         const float contrib = alpha * Tt[t];
                         if (mode == 1) atomic_add_f32(&contributions[id], contrib);
                         else if (mode == 2) atomic_max_f32(&contributions[id], contrib);   /* pcheck_obb_max/forward.cu:400 */
-                        else if (contrib > max_contrib[t]) { max_contrib[t] = contrib; max_idx[t] = (int)id; }
+                        else if (mode == 3 && contrib > max_contrib[t]) { max_contrib[t] = contrib; max_idx[t] = (int)id; }
                         for (int ch = 0; ch < 3; ch++) C[t][ch] = fmaf(Tt[t], alpha * rgb[3 * id + ch], C[t][ch]);
                     } else {
                         const float w = alpha * Tt[t];
@@ -613,7 +617,9 @@ static void blend_tile_ps1(void* vctx, int tile) {
 
 /* =================================================================================================================
  * PS=1 forward (mode 0 = pcheck_obb, 1 = pcheck_obb_sum, 2 = pcheck_obb_max, 3 = pcheck_obb_loss_weighted_max_count;
- * modes 1-3 share everything but the per-Gaussian statistics of the blend).  All pointers are host memory.  Optional
+ * modes 1-3 share everything but the per-Gaussian statistics of the blend; mode 4 = the vanilla diff-gaussian-rasterization
+ * of fov3dgs/submodules/diff-gaussian-rasterization: SUM's arithmetic without the OBB test, the -4.5 falloff cut and the
+ * statistics — gaussians_count / contributions are not touched).  All pointers are host memory.  Optional
  * outputs may be NULL; `loss_map` [H*W] is read by mode 3 only.
  * ================================================================================================================= */
 int64_t orc_forward_ps1(const orc_camera* cam, int mode, int P, int M, const float* means3D, const float* opacity,
@@ -624,7 +630,7 @@ int64_t orc_forward_ps1(const orc_camera* cam, int mode, int P, int M, const flo
     const int W = cam->W, H = cam->H, gx = (W + 15) / 16, gy = (H + 15) / 16, T = gx * gy;
     const float fy = H / (2.0f * cam->tanfovy), fx = W / (2.0f * cam->tanfovx);
     bin_in_t in; memset(&in, 0, sizeof(in));
-    in.mode = mode >= 1 ? 1 : 0; in.cam = cam; in.P = P; in.M = M; in.means3D = means3D; in.opacity = opacity; in.scales = scales; in.rot = rot; in.shs = shs;
+    in.mode = mode >= 1 ? 1 : 0; in.no_obb = mode == 4; in.cam = cam; in.P = P; in.M = M; in.means3D = means3D; in.opacity = opacity; in.scales = scales; in.rot = rot; in.shs = shs;
     bin_out_t o; memset(&o, 0, sizeof(o));
     o.sp = (splat_t*)calloc((size_t)P + 1, sizeof(splat_t)); o.vis = (uint8_t*)calloc((size_t)P + 1, 1);
     o.radii = radii; o.cov3d = (float*)calloc((size_t)P * 6 + 6, sizeof(float));
@@ -1017,7 +1023,7 @@ static void dnormvdv3(const float* v, const float* dv, float* out) {
     out[2] = (-v[0] * v[2] * dv[0] - v[1] * v[2] * dv[1] + (sum2 - v[2] * v[2]) * dv[2]) * inv;
 }
 
-int orc_backward_ps1(const orc_camera* cam, int P, int M, const float* means3D, const float* scales, const float* rot,
+static int backward_ps1_impl(float cut, const orc_camera* cam, int P, int M, const float* means3D, const float* scales, const float* rot,
                      const float* shs, const float* opacity, const int* radii, const float* means2D, const float* conic,
                      const float* rgb, const uint8_t* clamped, const float* cov3D, const uint32_t* point_list,
                      const uint32_t* ranges, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
@@ -1050,7 +1056,7 @@ int orc_backward_ps1(const orc_camera* cam, int P, int M, const float* means3D, 
                 const float dx = means2D[2 * id] - pxf, dy = means2D[2 * id + 1] - pyf;
                 const float cx = conic[3 * id], cy = conic[3 * id + 1], cz = conic[3 * id + 2], op = opacity[id];
                 const float power = gauss_power(cx, cy, cz, dx, dy);
-                if (power > 0.0f || power < -4.5f) continue;
+                if (power > 0.0f || power < cut) continue;
                 const float G = expf(power);
                 const float alpha = fminf(0.99f, op * G);
                 if (alpha < 1.0f / 255.0f) continue;
@@ -1217,6 +1223,29 @@ int orc_backward_ps1(const orc_camera* cam, int P, int M, const float* means3D, 
         }
     }
     return 0;
+}
+
+/* SUM/cuda_rasterizer/backward.cu (the -4.5 falloff cut of the pcheck variants, :495) */
+int orc_backward_ps1(const orc_camera* cam, int P, int M, const float* means3D, const float* scales, const float* rot,
+                     const float* shs, const float* opacity, const int* radii, const float* means2D, const float* conic,
+                     const float* rgb, const uint8_t* clamped, const float* cov3D, const uint32_t* point_list,
+                     const uint32_t* ranges, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
+                     float* dL_dmeans2D, float* dL_dconic4, float* dL_dopacity, float* dL_dcolors, float* dL_dmeans3D,
+                     float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drot) {
+    return backward_ps1_impl(-4.5f, cam, P, M, means3D, scales, rot, shs, opacity, radii, means2D, conic, rgb, clamped, cov3D,
+                             point_list, ranges, final_T, n_contrib, dL_dpix, dL_dmeans2D, dL_dconic4, dL_dopacity, dL_dcolors,
+                             dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot);
+}
+/* vanilla diff-gaussian-rasterization/cuda_rasterizer/backward.cu:495: only `power > 0` is skipped */
+int orc_backward_vanilla(const orc_camera* cam, int P, int M, const float* means3D, const float* scales, const float* rot,
+                         const float* shs, const float* opacity, const int* radii, const float* means2D, const float* conic,
+                         const float* rgb, const uint8_t* clamped, const float* cov3D, const uint32_t* point_list,
+                         const uint32_t* ranges, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
+                         float* dL_dmeans2D, float* dL_dconic4, float* dL_dopacity, float* dL_dcolors, float* dL_dmeans3D,
+                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drot) {
+    return backward_ps1_impl(-INFINITY, cam, P, M, means3D, scales, rot, shs, opacity, radii, means2D, conic, rgb, clamped, cov3D,
+                             point_list, ranges, final_T, n_contrib, dL_dpix, dL_dmeans2D, dL_dconic4, dL_dopacity, dL_dcolors,
+                             dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot);
 }
 
 void orc_mark_visible(const orc_camera* cam, int P, const float* means3D, uint8_t* present) {

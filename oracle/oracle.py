@@ -86,11 +86,12 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-PS1_MODES = {"obb": 0, "sum": 1, "max": 2, "lwmc": 3}
+PS1_MODES = {"obb": 0, "sum": 1, "max": 2, "lwmc": 3, "vanilla": 4}
 
 
 def forward_ps1(scene, cam, mode="obb", bg=(0.0, 0.0, 0.0), list_cap=None, loss_map=None):
-    """mode: 'obb' | 'sum' | 'max' | 'lwmc' (loss_map [H,W] required).  Returns dict with color, radii, num_rendered,
+    """mode: 'obb' | 'sum' | 'max' | 'lwmc' (loss_map [H,W] required) | 'vanilla' (the stock diff-gaussian-rasterization:
+    no OBB test, no -4.5 cut, no statistics).  Returns dict with color, radii, num_rendered,
     point_list, ranges, means2D, depths, conic, cov3D, rgb, clamped (+ gaussians_count, contributions, final_T,
     n_contrib for the training-family modes)."""
     L = lib()
@@ -191,8 +192,9 @@ def forward_mmfr(scene, cam, cur_level, gaze, alpha=0.05, bg=(0.0, 0.0, 0.0), li
     return o
 
 
-def backward_ps1(scene, cam, fwd, dL_dpix, bg=(0.0, 0.0, 0.0)):
-    """fwd: result of forward_ps1(mode='sum').  Returns dict of the 8 gradients (+ dL_dconic scratch)."""
+def backward_ps1(scene, cam, fwd, dL_dpix, bg=(0.0, 0.0, 0.0), vanilla=False):
+    """fwd: result of forward_ps1(mode='sum') — or mode='vanilla' with vanilla=True.  Returns dict of the 8 gradients
+    (+ dL_dconic scratch)."""
     L = lib()
     P = scene["means3D"].shape[0]
     M = scene["shs"].shape[1]
@@ -206,7 +208,7 @@ def backward_ps1(scene, cam, fwd, dL_dpix, bg=(0.0, 0.0, 0.0)):
     }
     ins = [_f32(scene["means3D"]), _f32(scene["scales"]), _f32(scene["rotations"]), _f32(scene["shs"]), _f32(scene["opacity"])]
     pl = np.ascontiguousarray(fwd["point_list"], np.uint32)
-    L.orc_backward_ps1(C.byref(c), P, M, *[_p(a) for a in ins], _p(np.ascontiguousarray(fwd["radii"], np.int32)),
+    (L.orc_backward_vanilla if vanilla else L.orc_backward_ps1)(C.byref(c), P, M, *[_p(a) for a in ins], _p(np.ascontiguousarray(fwd["radii"], np.int32)),
                        _p(_f32(fwd["means2D"])), _p(_f32(fwd["conic"])), _p(_f32(fwd["rgb"])),
                        _p(np.ascontiguousarray(fwd["clamped"], np.uint8)), _p(_f32(fwd["cov3D"])), _p(pl),
                        _p(np.ascontiguousarray(fwd["ranges"], np.uint32)), _p(_f32(fwd["final_T"])),

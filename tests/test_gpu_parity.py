@@ -96,6 +96,65 @@ def test_sum_forward_and_backward_match_reference_golden(scene_small, golden_dir
         assert np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30) <= 1e-4, nm
 
 
+def test_vanilla_forward_and_backward_match_reference_golden(scene_small, golden_dir):
+    """diff_gaussian_rasterization (the stock rasterizer, cuda_type="original"): whole-rectangle lists, no -4.5 cut — against
+    the unmodified reference binary (oracle/_ref/ref_vanilla_C), full-sort path and lazy path."""
+    g = _g(golden_dir, "vanilla_small_c0.npz")
+    gb = _g(golden_dir, "vanilla_small_c0_bwd.npz")
+    s, c = scene_small
+    (n, color, radii, item, pl, rg), sc, rs = _run_ps1(ops.MODE_VANILLA, s, c)
+    assert n == int(g["num_rendered"])
+    assert np.array_equal(radii.cpu().numpy(), g["radii"])
+    assert np.array_equal(pl.cpu().numpy(), g["point_list"])
+    assert np.array_equal(rg.cpu().numpy(), g["ranges"])
+    assert np.abs(color.cpu().numpy() - g["color"]).max() <= IMG_TOL
+    (n2, color2, radii2, item2), _, _ = _run_ps1(ops.MODE_VANILLA, s, c, want_lists=False)      # lazy sort + blend
+    assert n2 == n and torch.equal(color2, color) and torch.equal(radii2, radii)
+    H, W = c["image_height"], c["image_width"]
+    grad_out = torch.from_numpy(np.random.default_rng(int(gb["grad_seed"])).standard_normal((3, H, W)).astype(np.float32)).cuda()
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+    for it, rd in ((item, radii), (item2, radii2)):
+        grads = ops.backward_ps1(it, sc["means3D"], rd, sc["scales"], sc["rotations"], None, sc["shs"], None, rs, grad_out)
+        for nm, t in zip(names, grads):
+            a, b = t.cpu().numpy().ravel(), gb[nm].ravel()
+            assert np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30) <= 1e-4, nm
+
+
+def test_vanilla_vs_oracle_and_drop_in_package():
+    """Fresh inputs against the CPU oracle (lists bit-exact, image within tolerance, gradients rel-L2), then the package the
+    reference imports (fov3dgs/gaussian_wrapper.py:2): returns (color, radii), differentiable."""
+    import oracle
+    import diff_gaussian_rasterization as mv
+    s = synth.make_scene_cube(3000, 41)
+    c = _small_cam(176, 112)
+    o = oracle.forward_ps1(s, c, "vanilla")
+    (n, color, radii, item, pl, rg), sc, rs = _run_ps1(ops.MODE_VANILLA, s, c)
+    assert n == o["num_rendered"] and n > oracle.forward_ps1(s, c, "sum")["num_rendered"]
+    assert np.array_equal(radii.cpu().numpy(), o["radii"])
+    assert np.array_equal(pl.cpu().numpy().astype(np.uint32), o["point_list"])
+    assert np.array_equal(rg.cpu().numpy().astype(np.uint32), o["ranges"])
+    assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
+    grad_out = np.random.default_rng(2).standard_normal((3, 112, 176)).astype(np.float32)
+    go = oracle.backward_ps1(s, c, o, grad_out, vanilla=True)
+    g = ops.backward_ps1(item, sc["means3D"], radii, sc["scales"], sc["rotations"], None, sc["shs"], None, rs,
+                         torch.from_numpy(grad_out).cuda())
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+    for nm, t in zip(names, g):
+        a, b = t.cpu().numpy().ravel(), go[nm].ravel()
+        assert np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30) <= 1e-4, nm
+    r = mv.GaussianRasterizer(raster_settings=_settings(mv, c, 3))
+    means = sc["means3D"].clone().requires_grad_(True)
+    out = r(means3D=means, means2D=torch.zeros_like(means), opacities=sc["opacity"], shs=sc["shs"], scales=sc["scales"],
+            rotations=sc["rotations"])
+    assert len(out) == 2 and torch.equal(out[0], color) and torch.equal(out[1], radii)
+    (out[0] * torch.from_numpy(grad_out).cuda()).sum().backward()
+    assert np.linalg.norm(means.grad.cpu().numpy().ravel() - go["dL_dmeans3D"].ravel()) <= 1e-4 * np.linalg.norm(go["dL_dmeans3D"].ravel())
+    # a SUM frame on the same pooled workspace afterwards must get its -4.5 cut back (the cut travels in the frame header)
+    os_ = oracle.forward_ps1(s, c, "sum")
+    (ns, cs, *_), _, _ = _run_ps1(ops.MODE_SUM, s, c)
+    assert ns == os_["num_rendered"] and np.abs(cs.cpu().numpy() - os_["color"]).max() <= IMG_TOL
+
+
 @pytest.mark.parametrize("variant", ["max", "lwmc"])
 def test_pruning_variants_match_reference_golden(scene_small, golden_dir, variant):
     g = _g(golden_dir, f"{variant}_small_c0.npz")

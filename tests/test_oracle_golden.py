@@ -88,6 +88,56 @@ def test_sum_backward_matches_reference_gradients(scene_small, sum_out, golden_d
         assert rel <= 1e-4, (nm, rel)
 
 
+def test_vanilla_matches_reference(scene_small, golden_dir):
+    """The stock diff-gaussian-rasterization the reference vendors (fov3dgs/gaussian_wrapper.py:2 cuda_type="original"):
+    whole-rectangle tile lists, no -4.5 falloff cut."""
+    g = _g(golden_dir, "vanilla_small_c0.npz")
+    s, c = scene_small
+    o = oracle.forward_ps1(s, c, "vanilla")
+    assert o["num_rendered"] == int(g["num_rendered"])
+    assert np.array_equal(o["radii"], g["radii"])
+    assert np.array_equal(o["point_list"], g["point_list"].astype(np.uint32))
+    assert np.array_equal(o["ranges"], g["ranges"].astype(np.uint32))
+    assert np.array_equal(o["n_contrib"], g["n_contrib"].astype(np.uint32))
+    assert np.abs(o["final_T"] - g["final_T"]).max() <= 1e-6
+    assert np.abs(o["color"] - g["color"]).max() <= IMG_TOL
+    gb = _g(golden_dir, "vanilla_small_c0_bwd.npz")
+    H, W = c["image_height"], c["image_width"]
+    grad_out = np.random.default_rng(int(gb["grad_seed"])).standard_normal((3, H, W)).astype(np.float32)
+    grads = oracle.backward_ps1(s, c, o, grad_out, vanilla=True)
+    for nm in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"):
+        a, b = grads[nm].ravel(), gb[nm].ravel()
+        rel = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+        assert rel <= 1e-4, (nm, rel)
+
+
+def test_property_vanilla_lists_are_the_whole_rectangles_and_contain_the_obb_lists():
+    """Without the OBB test every visible Gaussian lands in every tile of its rectangle: num_rendered = sum of rectangle
+    areas (recomputed here from means2D / radii with the reference's getRect, auxiliary.h:46-57); the pcheck lists are a
+    subset; the projections and radii of Gaussians both keep are the same bits."""
+    s = synth.make_scene_cube(3000, 17)
+    c = synth.look_at_camera(176, 112, 70.0, (0.3, 0.2, -3.5))
+    v = oracle.forward_ps1(s, c, "vanilla")
+    o = oracle.forward_ps1(s, c, "sum")
+    gx, gy = (176 + 15) // 16, (112 + 15) // 16
+    r = v["radii"]
+    vis = r > 0
+    x, y = v["means2D"][vis, 0], v["means2D"][vis, 1]
+    rr = r[vis].astype(np.float32)
+    x0 = np.clip(((x - rr) / 16).astype(np.int32), 0, gx); x1 = np.clip(((x + rr + 15) / 16).astype(np.int32), 0, gx)
+    y0 = np.clip(((y - rr) / 16).astype(np.int32), 0, gy); y1 = np.clip(((y + rr + 15) / 16).astype(np.int32), 0, gy)
+    assert v["num_rendered"] == int(((x1 - x0) * (y1 - y0)).sum())
+    assert v["num_rendered"] >= o["num_rendered"]
+    kv = set(map(int, oracle.instance_keys(v["point_list"], v["ranges"])))
+    ko = set(map(int, oracle.instance_keys(o["point_list"], o["ranges"])))
+    assert ko <= kv
+    both = (o["radii"] > 0)
+    assert np.array_equal(v["radii"][both], o["radii"][both])
+    assert np.array_equal(_bits(v["means2D"])[both], _bits(o["means2D"])[both])
+    # the statistics outputs are not touched by the vanilla mode
+    assert not v["gaussians_count"].any() and not v["contributions"].any()
+
+
 @pytest.mark.parametrize("gi", [0, 1])
 def test_fov_matches_reference(scene_small, golden_dir, gi):
     g = _g(golden_dir, f"fov_small_c0_g{gi}.npz")

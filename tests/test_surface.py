@@ -102,10 +102,16 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=x, rotations=torch.zeros(4, 4))
 
 
-def test_non_hot_path_variants_explain_themselves():
+def test_vanilla_package_is_a_real_rasterizer():
+    """fov3dgs/gaussian_wrapper.py:2,11: cuda_type="original" constructs diff_gaussian_rasterization.GaussianRasterizer — same
+    surface as the reference's stock package (forward signature, CPU tensors rejected: no fallback)."""
     m = importlib.import_module("diff_gaussian_rasterization")
-    with pytest.raises(NotImplementedError):
-        m.GaussianRasterizer(raster_settings=None)
+    r = m.GaussianRasterizer(raster_settings=_settings(m))
+    assert list(inspect.signature(r.forward).parameters) == ["means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                                             "rotations", "cov3D_precomp"]
+    x = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=x, rotations=torch.zeros(4, 4))
 
 
 def test_gaussian_wrapper_import_line_works():

@@ -242,11 +242,12 @@ def run_mmfr(scn, cam, gazes, rep_list, do_time, golden_dir, tag):
 
 
 PS1_VARIANTS = {"obb": ("ref_obb_C", ops.MODE_OBB), "sum": ("ref_sum_C", ops.MODE_SUM), "max": ("ref_max_C", ops.MODE_MAX),
-                "lwmc": ("ref_lwmc_C", ops.MODE_LWMC)}
+                "lwmc": ("ref_lwmc_C", ops.MODE_LWMC), "vanilla": ("ref_vanilla_C", ops.MODE_VANILLA)}
 
 
 def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
-    sum_mode = variant != "obb"          # the training family: sum / max / lwmc
+    sum_mode = variant != "obb"          # the training family: sum / max / lwmc / vanilla (forward state + backward)
+    stat_mode = sum_mode and variant != "vanilla"   # ... of which all but the stock rasterizer return per-Gaussian statistics
     mod = ref_api.ref_module(PS1_VARIANTS[variant][0])
     sc = to_cuda(scn)
     c = to_cuda(cam)
@@ -283,10 +284,6 @@ def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
         vis = (rad_r > 0)
         rep["rgb_max_abs"] = float(((gr["rgb"] - go["rgb"]).abs() * vis.unsqueeze(-1)).max().item())
         if sum_mode:
-            gc_r, ct_r = res[6], res[7]
-            gc_o, ct_o = out[4], out[5]
-            rep["gaussians_count_mismatch"] = int((gc_r != gc_o).sum().item())
-            rep["contrib_max_rel"] = float(((ct_r - ct_o).abs() / (ct_r.abs() + 1e-6)).max().item())
             rep["cov3D_bit_mismatch"] = mism(gr["cov3D"], go["cov3D"], vis)
             rep["n_contrib_mismatch"] = None
             # the lazy (consumption-driven) training kernel: same statistics, same image, same saved state
@@ -294,10 +291,15 @@ def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
                                  loss_map=loss_map)
             torch.cuda.synchronize()
             rep["lazy_img_max_abs"] = float((lz[1] - col_r).abs().max().item())
-            rep["lazy_gaussians_count_mismatch"] = int((gc_r != lz[4]).sum().item())
-            rep["lazy_contrib_max_rel"] = float(((ct_r - lz[5]).abs() / (ct_r.abs() + 1e-6)).max().item())
-            rep["lazy_contrib_bit_mismatch"] = mism(ct_r, lz[5])
-            rep["contrib_bit_mismatch"] = mism(ct_r, ct_o)
+            if stat_mode:
+                gc_r, ct_r = res[6], res[7]
+                gc_o, ct_o = out[4], out[5]
+                rep["gaussians_count_mismatch"] = int((gc_r != gc_o).sum().item())
+                rep["contrib_max_rel"] = float(((ct_r - ct_o).abs() / (ct_r.abs() + 1e-6)).max().item())
+                rep["lazy_gaussians_count_mismatch"] = int((gc_r != lz[4]).sum().item())
+                rep["lazy_contrib_max_rel"] = float(((ct_r - lz[5]).abs() / (ct_r.abs() + 1e-6)).max().item())
+                rep["lazy_contrib_bit_mismatch"] = mism(ct_r, lz[5])
+                rep["contrib_bit_mismatch"] = mism(ct_r, ct_o)
             # backward
             grad_out = torch.from_numpy(np.random.default_rng(3).standard_normal((3, H, W)).astype(np.float32)).cuda()
             g_ref = ref_api.ps1_backward(mod, sc, c, rad_r, grad_out, geom, n_r, binning, img)
@@ -321,8 +323,9 @@ def run_ps1(variant, scn, cam, rep_list, do_time, golden_dir, tag):
         if golden_dir:
             extra = {}
             if sum_mode:
-                extra = {"gaussians_count": res[6].cpu().numpy(), "contributions": res[7].cpu().numpy(),
-                         "final_T": ir["accum_alpha"].cpu().numpy(), "n_contrib": ir["n_contrib"].cpu().numpy()}
+                extra = {"final_T": ir["accum_alpha"].cpu().numpy(), "n_contrib": ir["n_contrib"].cpu().numpy()}
+                if stat_mode:
+                    extra.update({"gaussians_count": res[6].cpu().numpy(), "contributions": res[7].cpu().numpy()})
                 if loss_map is not None:
                     extra["loss_map_seed"] = np.int64(17)
             np.savez_compressed(os.path.join(golden_dir, f"{variant}_{tag}.npz"), color=col_r.cpu().numpy(), radii=rad_r.cpu().numpy(),
