@@ -56,8 +56,8 @@ class Readback:
     renders (two host buffers).  Both bench arms use the same protocol.  `drain()` waits for the last copies, so all
     images of the timed frames are on the host when the clock stops."""
 
-    def __init__(self, dev, shape, depth=4):
-        self.host = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+    def __init__(self, dev, shape, depth=4, dtype=torch.float32):
+        self.host = [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(depth)]
         self.done = [None] * depth
         self.stream = torch.cuda.Stream(dev)
         self.n = 0
@@ -349,6 +349,23 @@ def run_ours(args, wl, rank, world, dev):
         finally:
             ops.set_deferred_check(False)
         del readback
+        # extra: the same end-to-end loop (default blocking mode) with the opt-in 8-bit image of the blend epilogue — what the
+        # reference's scripts store (torchvision.utils.save_image) — 6.2 MB per frame back to the host instead of 24.9 MB
+        readback = Readback(dev, (3, wl.H, wl.W), dtype=torch.uint8)
+
+        def render_u8(rs, gaze):
+            r = fovpkg.GaussianRasterizer(raster_settings=rs)
+            r.output_uint8 = True
+            return r(means3D=sc["means3D"], means2D=None, opacities=sc["opacities4"], shs_rest=sc["shs_rest"], scales=sc["scales"],
+                     rotations=sc["rotations"], shs_dcs=sc["shs_dcs"], highest_levels=sc["highest_levels"], gazeArray=gaze,
+                     alpha=0.05, blending=True)
+
+        render_f32, render = render, render_u8
+        try:
+            e2e_u8_s = e2e_loop()
+        finally:
+            render = render_f32
+        del readback
 
     extra = extra_ours(args, wl, sc, cams_dev, bg, frames, dev) if not args.no_extra else None
     # kernels per frame: k_setup, k_tile_levels, k_tile_infos, k_pre, k_tile_scan, k_color_tma, k_scatter, k_lazy_blend x 2
@@ -361,7 +378,7 @@ def run_ours(args, wl, rank, world, dev):
             return render(rs_dev[f % 30], gazes_dev[f % 9])[0]
 
     return {"last_image": last_image, "last_frame": frames[-1], "render_frame": render_frame, "n_frames": args.steps,
-            "ms": ms, "ms_staged": ms_staged, "blend_live": blend_live, "ms_uncached": ms_uncached, "stage_uncached": stage_uncached, "e2e_s": e2e_sync_s, "e2e_pipelined_s": e2e_s, "stages": stage_frames, "stats": stats,
+            "ms": ms, "ms_staged": ms_staged, "blend_live": blend_live, "ms_uncached": ms_uncached, "stage_uncached": stage_uncached, "e2e_s": e2e_sync_s, "e2e_pipelined_s": e2e_s, "e2e_u8_s": e2e_u8_s, "stages": stage_frames, "stats": stats,
             "clocks": clocks_summary(clk), "h2d": h2d, "d2h": d2h, "launches_per_frame": FOV_LAUNCHES_PER_FRAME, "extra": extra}
 
 
@@ -738,10 +755,11 @@ def main():
         res = run_ours(args, wl, rank, world, dev)
 
     # max over ranks (device time and wall time)
-    t = torch.tensor([res["ms"], res["e2e_s"], res.get("e2e_pipelined_s", 0.0), res.get("ms_uncached", 0.0)], dtype=torch.float64, device=dev)
+    t = torch.tensor([res["ms"], res["e2e_s"], res.get("e2e_pipelined_s", 0.0), res.get("ms_uncached", 0.0), res.get("e2e_u8_s", 0.0)],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_max, e2e_piped_max, ms_unc_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_max, e2e_max, e2e_piped_max, ms_unc_max, e2e_u8_max = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     total_frames = args.steps * world
     value = total_frames / (ms_max * 1e-3)
     e2e_v = total_frames / e2e_max
@@ -772,6 +790,10 @@ def main():
         else:
             line["gpu_launches"] = res["launches_per_frame"] * args.steps
             line["e2e"]["pipelined_value"] = total_frames / e2e_piped_max      # opt-in serving mode, not the headline
+            if e2e_u8_max > 0:                                                  # opt-in 8-bit image (extra, not the headline)
+                line["e2e"]["uint8_output"] = {"value": total_frames / e2e_u8_max, "d2h_bytes_per_step": res["d2h"] // 4,
+                                               "note": "rasterizer.output_uint8 = True: the blend epilogue writes the image the "
+                                                       "reference's scripts store (torchvision save_image quantisation)"}
             line["value_uncached"] = total_frames / (ms_unc_max * 1e-3)       # FOVGS_MODEL_CACHE=0
             line["stage_ms_uncached"] = res["stage_uncached"]
             line["roofline"] = roofline(res, wl, args.steps)

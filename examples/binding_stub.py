@@ -20,13 +20,13 @@ class fovgs_fov_fwd_args(C.Structure):                 # include/fovgs.h: fovgs_
                 ("alpha", C.c_float), ("blending", C.c_int32), ("out_color", C.c_void_p), ("radii", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("max_instances", C.c_int64),
                 ("out_point_list", C.c_void_p), ("out_ranges", C.c_void_p), ("packed_color_rows", C.c_void_p),
-                ("early_stats_host", C.c_void_p), ("early_stats_event", C.c_void_p)]
+                ("early_stats_host", C.c_void_p), ("early_stats_event", C.c_void_p), ("out_color_u8", C.c_void_p)]
 
 lib.fovgs_workspace_bytes.restype = C.c_size_t
 lib.fovgs_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
 lib.fovgs_last_error.restype = C.c_char_p
 lib.fovgs_struct_size.restype = C.c_size_t
-FOVGS_VERSION = 201                                     # include/fovgs.h
+FOVGS_VERSION = 202                                     # include/fovgs.h
 assert lib.fovgs_version() == FOVGS_VERSION
 assert lib.fovgs_struct_size(0) == C.sizeof(fovgs_camera) and lib.fovgs_struct_size(2) == C.sizeof(fovgs_fov_fwd_args)
 

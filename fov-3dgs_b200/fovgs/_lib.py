@@ -17,7 +17,7 @@ FOVGS_PS1_MAX = 2
 FOVGS_PS1_LWMC = 3
 FOVGS_PS1_VANILLA = 4
 
-FOVGS_VERSION = 201   # include/fovgs.h; every args struct carries it next to its own size (FOVGS_ARGS_HEADER)
+FOVGS_VERSION = 202   # include/fovgs.h; every args struct carries it next to its own size (FOVGS_ARGS_HEADER)
 
 _f = C.c_void_p  # all device pointers travel as void*
 _HEADER = [("struct_size", C.c_uint32), ("abi_version", C.c_uint32)]

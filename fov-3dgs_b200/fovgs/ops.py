@@ -444,7 +444,8 @@ _FOV_KINDS = {
 }
 
 
-def _forward_foveated(kind, fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists, keep):
+def _forward_foveated(kind, fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists, keep,
+                      out_uint8=False):
     """The marshalling the three foveated forwards share: camera block, outputs, workspace, optional sorted lists, launch through
     the capacity protocol.  `fields`: the variant's own struct fields (name -> int / float / device pointer)."""
     entry, Args, mode = _FOV_KINDS[kind]
@@ -454,7 +455,9 @@ def _forward_foveated(kind, fields, means3D, scales, rotations, gazeArray, alpha
     P = means3D.size(0)
     gaze = _gaze_tensor(gazeArray, device)
     cam = _camera(rs, device, keep)
-    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    # out_uint8 (foveated rasterizer only): the blend epilogue writes the 8-bit image the reference's scripts store
+    # (torchvision.utils.save_image's quantisation) INSTEAD of the fp32 one: 6.2 MB per 1080p frame instead of 24.9 MB
+    color = torch.empty((3, H, W), dtype=torch.uint8 if out_uint8 else torch.float32, device=device)
     radii = torch.empty((P,), dtype=torch.int32, device=device)
     T = ((W + 15) // 16) * ((H + 15) // 16)
     lists = {}
@@ -468,7 +471,10 @@ def _forward_foveated(kind, fields, means3D, scales, rotations, gazeArray, alpha
     a.gaze = gaze.data_ptr()
     a.alpha = float(alpha) if alpha is not None else 0.0
     a.blending = int(bool(blending))
-    a.out_color = color.data_ptr()
+    if out_uint8:
+        a.out_color, a.out_color_u8 = None, color.data_ptr()
+    else:
+        a.out_color = color.data_ptr()
     a.radii = radii.data_ptr()
     for k, v in fields.items():
         setattr(a, k, v)
@@ -500,14 +506,17 @@ def _empty_frame(means3D, raster_settings):
 
 
 def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highest_levels, gazeArray, alpha, blending,
-                raster_settings, want_lists=False):
-    """Foveated forward.  Returns (num_rendered, color[3,H,W], radii[P]) (+ point_list, ranges when want_lists)."""
+                raster_settings, want_lists=False, out_uint8=False):
+    """Foveated forward.  Returns (num_rendered, color[3,H,W], radii[P]) (+ point_list, ranges when want_lists).
+    out_uint8: `color` is the uint8 image clamp(v * 255 + 0.5, 0, 255) (what torchvision.utils.save_image would store of the
+    fp32 image, fov3dgs/render.py:52), written by the blend epilogue in place of the fp32 image."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     device = means3D.device
     P = means3D.size(0)
     if P == 0:
-        return _empty_frame(means3D, raster_settings)
+        n0, c0, r0 = _empty_frame(means3D, raster_settings)
+        return (n0, c0.to(torch.uint8), r0) if out_uint8 else (n0, c0, r0)
     user_model = (means3D, shs_rest if (shs_rest is not None and shs_rest.numel()) else None, shs_dcs, opacities)
     means3D = _prep(means3D, "means3D", device)
     opacities = _prep(opacities, "opacities", device)
@@ -525,7 +534,7 @@ def forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highes
     fields = {"M_rest": M_rest, "opacities": opacities.data_ptr(), "shs_rest": _ptr(shs_rest), "shs_dcs": shs_dcs.data_ptr(),
               "highest_levels": highest_levels.data_ptr(), "packed_color_rows": None if packed is None else packed.data_ptr()}
     return _forward_foveated("fov", fields, means3D, scales, rotations, gazeArray, alpha, blending, raster_settings, want_lists,
-                             [opacities, shs_rest, shs_dcs, highest_levels, packed])
+                             [opacities, shs_rest, shs_dcs, highest_levels, packed], out_uint8=out_uint8)
 
 
 def forward_smfr(means3D, opacities, scales, rotations, shs, highest_levels, gazeArray, alpha, blending, raster_settings,

@@ -132,9 +132,20 @@ class _FovGaussianRasterizer(nn.Module):
     def markVisible(self, positions):
         return _mark_visible(self.raster_settings, positions)
 
+    # Extension (not in the reference): `rasterizer.output_uint8 = True` makes forward() return the uint8 image the reference's
+    # scripts store (torchvision.utils.save_image's quantisation of the fp32 render, fov3dgs/render.py:52), written by the blend
+    # epilogue in place of the fp32 image — 6.2 MB instead of 24.9 MB per 1080p frame on its way to the host.  Inference only.
+    output_uint8 = False
+
     def forward(self, means3D, means2D, opacities, shs_rest=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None, shs_dcs=None, highest_levels=None, gazeArray=None, alpha=None, blending=None):
         _check_inputs(shs_rest, colors_precomp, scales, rotations, cov3D_precomp)
+        if self.output_uint8:
+            if colors_precomp is not None or cov3D_precomp is not None:
+                raise RuntimeError("the foveated rasterizer renders from SH coefficients and scales/rotations")
+            _, color, radii = ops.forward_fov(means3D, opacities, scales, rotations, shs_rest, shs_dcs, highest_levels, gazeArray,
+                                              alpha, blending, self.raster_settings, out_uint8=True)
+            return color, radii
         return _fov_rasterize_gaussians(means3D, means2D, _empty_if_none(shs_rest), _empty_if_none(colors_precomp),
                                         opacities, _empty_if_none(scales), _empty_if_none(rotations),
                                         _empty_if_none(cov3D_precomp), self.raster_settings, shs_dcs, highest_levels,

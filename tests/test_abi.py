@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in _header_symbols():
         assert hasattr(L, s), f"libfovgs.so does not export {s}"
     assert sorted(_lib.EXPORTS) == _header_symbols()
-    assert L.fovgs_version() == _lib.FOVGS_VERSION == 201
+    assert L.fovgs_version() == _lib.FOVGS_VERSION == 202
 
 
 def test_workspace_bytes_is_monotone_and_mode_dependent():

@@ -272,6 +272,35 @@ def test_fov_vs_oracle(gaze):
     assert np.abs(color.cpu().numpy() - o["color"]).max() <= IMG_TOL
 
 
+@pytest.mark.parametrize("want_lists", [False, True])
+def test_uint8_output_is_the_quantised_fp32_image(want_lists):
+    """The optional 8-bit image of the foveated blend epilogue (lazy and full-sort paths) is, byte for byte, what the reference's
+    scripts would store of the fp32 image: torchvision.utils.save_image = mul(255).add_(0.5).clamp_(0, 255).to(uint8)
+    (fov3dgs/render.py:52).  A bright background exercises the upper clamp."""
+    import diff_gaussian_rasterization_fov_pcheck_obb as m
+    s = synth.add_foveation(synth.make_scene_cube(5000, 23))
+    c = _small_cam(400, 240)
+    sc = _cuda(s)
+    bg = torch.tensor([1.3, 0.4, -0.2], device="cuda")
+    rs = _settings(m, c, s["sh_degree"], bg=bg)
+    g = torch.tensor([0.4, 0.6], device="cuda")
+    args = (sc["means3D"], sc["opacities4"], sc["scales"], sc["rotations"], sc["shs_rest"], sc["shs_dcs"], sc["highest_levels"], g,
+            0.05, True, rs)
+    ref = ops.forward_fov(*args, want_lists=want_lists)
+    u8 = ops.forward_fov(*args, want_lists=want_lists, out_uint8=True)
+    assert u8[1].dtype == torch.uint8 and u8[0] == ref[0] and torch.equal(u8[2], ref[2])
+    expect = ref[1].clone().mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)
+    assert torch.equal(u8[1], expect)
+    assert int(expect.max()) == 255 and int(expect.min()) == 0
+    if not want_lists:
+        r = m.GaussianRasterizer(raster_settings=rs)
+        r.output_uint8 = True
+        color, radii = r(means3D=sc["means3D"], means2D=None, opacities=sc["opacities4"], shs_rest=sc["shs_rest"], scales=sc["scales"],
+                         rotations=sc["rotations"], shs_dcs=sc["shs_dcs"], highest_levels=sc["highest_levels"], gazeArray=g,
+                         alpha=0.05, blending=True)
+        assert torch.equal(color, expect) and torch.equal(radii, ref[2])
+
+
 @pytest.mark.parametrize("gaze", [(0.5, 0.5), (0.2, 0.8)])
 def test_smfr_baseline_vs_oracle_full_and_lazy(gaze):
     """SMFR baseline (naive_pcheck_obb, SURVEY §8f rank 2): lists exact, image within tolerance, lazy == full-sort bits;
