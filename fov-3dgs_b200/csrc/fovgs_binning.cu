@@ -248,6 +248,19 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                     sx = in.scales[3 * (size_t)idx0]; sy = in.scales[3 * (size_t)idx0 + 1]; sz = in.scales[3 * (size_t)idx0 + 2];
                     q = *reinterpret_cast<const float4*>(in.rotations + 4 * (size_t)idx0);
                 }
+                // Foveated modes: a Gaussian only lands in tiles of its level's region {tile_min < highest_level + 1}, so the
+                // "tile grid" it is culled against is that region's tile bounding box, not the screen: three in five Gaussians
+                // carry highest level 0, whose region is the foveal disc — outside it they used to survive this cull, pay the
+                // exact projection (~450 instructions) and only then lose their whole rectangle to the same box in phase A.
+                float lo_x = 0.0f, hi_x = scr_w, lo_y = 0.0f, hi_y = scr_h;
+                if (is_foveated(MODE)) {
+                    const float hl0 = has_level_mask(MODE) ? in.highest_levels[idx0] : 0.0f;   // MMFR: box 0 = this level's tiles
+                    const int li = (int)hl0;
+                    if (hl0 >= 0.0f && hl0 <= (float)(FOV_LEVELS - 1) && (float)li == hl0) {   // same condition as phase A's clip
+                        lo_x = 16.0f * (float)sm.bbox[li][0]; lo_y = 16.0f * (float)sm.bbox[li][1];
+                        hi_x = 16.0f * (float)sm.bbox[li][2]; hi_y = 16.0f * (float)sm.bbox[li][3];
+                    }
+                }
                 const float tz = xform_row(cam.view, 2, mx, my, mz);
                 if (!(tz <= 0.2f)) {                  // same expression, same bits as the exact near-plane test (NaN passes)
                     float lam3;                       // bound on the largest eigenvalue of Sigma3D
@@ -276,7 +289,8 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                     const float py = ((FM(hy, pw) + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
                     const float ex = rb + 1.0f + 1e-5f * fabsf(px), ey = rb + 1.0f + 1e-5f * fabsf(py);
                     // exact rect: x1 = clamp(trunc((px + r + 15)/16)), x0 = clamp(trunc((px - r)/16)); empty iff x1 <= x0 or y1 <= y0
-                    const bool out = (px + ex + 16.0f < 0.0f) || (px - ex > scr_w + 1.0f) || (py + ey + 16.0f < 0.0f) || (py - ey > scr_h + 1.0f);
+                    // (against tile columns [bx0, bx1): x1 <= bx0 or x0 >= bx1; the screen is the box [0, grid))
+                    const bool out = (px + ex + 16.0f < lo_x) || (px - ex > hi_x + 1.0f) || (py + ey + 16.0f < lo_y) || (py - ey > hi_y + 1.0f);
                     keep = !out;                      // NaN anywhere: comparisons are false -> keep
                 }
                 if (!keep) in.radii[idx0] = 0;
@@ -298,6 +312,10 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                 const size_t g0 = (size_t)cur * PRE_CHUNK;
                 const char* pm = (const char*)(in.means3D + 3 * g0) + 128 * lane;
                 if (lane < PRE_CHUNK * 12 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
+                if (has_level_mask(MODE)) {
+                    const char* pl = (const char*)(in.highest_levels + g0) + 128 * lane;
+                    if (lane < PRE_CHUNK * 4 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+                }
                 if (in.cov3D_precomp == nullptr) {
                     const char* ps = (const char*)(in.scales + 3 * g0) + 128 * lane;
                     const char* pr = (const char*)(in.rotations + 4 * g0) + 128 * lane;
