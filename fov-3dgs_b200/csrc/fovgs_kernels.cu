@@ -235,7 +235,6 @@ __global__ void k_setup(Workspace ws, SetupArgs a) {
             h->tiles = a.tiles;
             h->cap = a.cap;
             h->stage_cursor = 0;
-            h->pre_done = 0;
             h->pre_chunk = 0;
             h->vis_cursor = 0;
             h->exp_consts[0] = __uint_as_float(0x3bbb989du);

@@ -480,22 +480,3 @@ def make_lwmc_api():
 
 def make_vanilla_api():
     return _make_ps1_api(ops.MODE_VANILLA)
-
-
-def make_unavailable_api(pkg, why):
-    """Import-only stand-in for reference packages outside the hot path (gaussian_wrapper.py:2-7
-    imports them at module import time).  Using them raises with an explanation."""
-
-    class GaussianRasterizer(nn.Module):
-        def __init__(self, raster_settings=None):
-            super().__init__()
-            raise NotImplementedError(f"{pkg} is not provided by fovgs-b200: {why}")
-
-    def rasterize_gaussians(*a, **k):
-        raise NotImplementedError(f"{pkg} is not provided by fovgs-b200: {why}")
-
-    return {
-        "GaussianRasterizationSettings": GaussianRasterizationSettings,
-        "GaussianRasterizer": GaussianRasterizer,
-        "rasterize_gaussians": rasterize_gaussians,
-    }
