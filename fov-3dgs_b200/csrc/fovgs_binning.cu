@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) k_tile_scan(FrameHeader* hdr, cons
                                                           uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ tile_cursor,
                                                           uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_order2,
                                                           const uint8_t* __restrict__ tile_blend, uint32_t stage_cap,
-                                                          int want_order1) {
+                                                          int want_order1, uint32_t* stats_host) {
     static_assert(SCAN_NW <= 32, "scan_block_excl scans the warp sums in one warp");
     __shared__ ScanSmem s;
     pdl_trigger();                           // the colour kernel may start now: it shares nothing with this one
@@ -1073,6 +1073,13 @@ __global__ void __launch_bounds__(SCAN_NT, 1) k_tile_scan(FrameHeader* hdr, cons
         hdr->lazy_count[1] = k1;
         hdr->lazy_count[0] = (uint32_t)T - k1;
     }
+    if (stats_host != nullptr) {
+        // the frame statistics the host waits for (instance count, overflow flag, visible count, ...) go straight into its pinned,
+        // device-mapped buffer: no 64-byte device->host copy sits in the stream between two kernels of the frame
+        __syncthreads();
+        if (tid < (int)(sizeof(fovgs_frame_stats) / 4)) stats_host[tid] = reinterpret_cast<const volatile uint32_t*>(&hdr->stats)[tid];
+        __threadfence_system();
+    }
     // ---- pass B: positions = base of (bin, warp) + rank inside the warp; the row entry is the warp's running cursor ----
     for (int base = 0; base < T; base += SCAN_NT * SCAN_IT) {
         const int i0 = base + tid * SCAN_IT;
@@ -1104,11 +1111,11 @@ __global__ void __launch_bounds__(SCAN_NT, 1) k_tile_scan(FrameHeader* hdr, cons
     }
 }
 
-cudaError_t launch_tile_scan(const Workspace& ws, bool want_order1, cudaStream_t st) {
+cudaError_t launch_tile_scan(const Workspace& ws, bool want_order1, uint32_t* stats_host, cudaStream_t st) {
     // an ordinary launch (it needs all of k_pre); the colour kernel that follows is its programmatic dependent
     return launch_chained(false, k_tile_scan, dim3(1), dim3(SCAN_NT), 0, st, ws.hdr, (const uint32_t*)ws.tile_count, ws.tile_offset,
                           ws.tile_cursor, ws.tile_order, ws.tile_order2, (const uint8_t*)ws.tile_blend, ws.stage_cap,
-                          want_order1 ? 1 : 0);
+                          want_order1 ? 1 : 0, stats_host);
 }
 
 cudaError_t launch_pre(const Workspace& ws, const FrameInputs& in, Mode mode, int num_sms, cudaStream_t st) {

@@ -411,15 +411,25 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     // All variants sort lazily inside the blend kernel (fovgs_lazy.cu) unless the caller asked for the complete sorted
     // lists.  The training variant appends the sorted prefix it composites to point_list: exactly what its backward walks.
     const bool lazy = in.out_point_list == nullptr && in.out_ranges == nullptr && !g_force_full_sort;
-    launch_tile_scan(ws, !lazy, st);                  // one CTA, an ordinary launch; triggers its dependent on entry
+    // early statistics: written by the scan kernel straight into the caller's pinned buffer when that is device-accessible
+    // (cudaHostAlloc / torch pin_memory under unified addressing), else copied out behind the colour stage
+    uint32_t* stats_host_dev = nullptr;
+    if (in.early_stats_host != nullptr) {
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, in.early_stats_host, 0) == cudaSuccess) stats_host_dev = (uint32_t*)d;
+        else (void)cudaGetLastError();
+    }
+    launch_tile_scan(ws, !lazy, stats_host_dev, st);  // one CTA, an ordinary launch; triggers its dependent on entry
     launch_color(ws, in, (Mode)MODE, num_sms, st);    // its programmatic dependent: runs beside the scan
     STAGE_CHECK();
     if (in.early_stats_host != nullptr) {
         // instance count, overflow flag, visible count are final here: the host can have them well before the frame ends
-        cudaError_t e_ = cudaMemcpyAsync(in.early_stats_host, ws.hdr, sizeof(fovgs_frame_stats), cudaMemcpyDeviceToHost, st);
-        if (e_ != cudaSuccess) return e_;
+        if (stats_host_dev == nullptr) {
+            cudaError_t e_ = cudaMemcpyAsync(in.early_stats_host, ws.hdr, sizeof(fovgs_frame_stats), cudaMemcpyDeviceToHost, st);
+            if (e_ != cudaSuccess) return e_;
+        }
         if (in.early_stats_event != nullptr) {
-            e_ = cudaEventRecord((cudaEvent_t)in.early_stats_event, st);
+            cudaError_t e_ = cudaEventRecord((cudaEvent_t)in.early_stats_event, st);
             if (e_ != cudaSuccess) return e_;
         }
     }

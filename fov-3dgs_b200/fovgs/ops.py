@@ -201,6 +201,15 @@ def _early_event(item, stream_obj):
     return ev
 
 
+def _ring_event_handle(item, slot, stream_obj):
+    """cudaEvent_t of ring slot `slot` (the library records it; torch creates the underlying event at its first record)."""
+    if item["ring_events"][slot] is None:
+        ev = item["ring_events"][slot] = torch.cuda.Event()
+        ev.record(stream_obj)
+        item.setdefault("ring_handles", {})[slot] = int(ev.cuda_event)
+    return item["ring_handles"][slot]
+
+
 _pool = _Pool()
 
 
@@ -293,13 +302,10 @@ def _run_with_capacity_impl(launch, device, mode, P, W, H, fresh_workspace):
                 _drain_ring(item, key, block=True, only_slot=slot)     # the host ran _RING frames ahead: wait for the oldest
             if item is not _pool.items.get(key) or item["cap"] < _pool.min_caps.get(key, 0):
                 continue                                                # an overflow was learnt: take the grown workspace
-            item["early"] = None
+            # the library writes this frame's statistics into ring slot `slot` (the scan kernel stores them straight into the
+            # pinned buffer) and records the slot's event behind the colour stage: no copy operation enters the stream
+            item["early"] = (item["stats_ptr"] + 64 * slot, _ring_event_handle(item, slot, cur_stream))
             launch(item, stream)
-            _read_stats(item, stream, slot)
-            ev = item["ring_events"][slot]
-            if ev is None:
-                ev = item["ring_events"][slot] = torch.cuda.Event()
-            ev.record(cur_stream)
             item["ring_pending"][slot] = True
             item["ring_pos"] = (slot + 1) % _RING
             return item, None

@@ -19,12 +19,13 @@ class _Stream:
 
 
 class _Event:
-    """Stand-in for torch.cuda.Event: `landed` says whether the 64-byte statistics copy behind it has completed."""
+    """Stand-in for torch.cuda.Event: `landed` says whether the frame statistics guarded by it have reached the host buffer."""
     auto_land = True
     waits = 0
 
     def __init__(self):
         self.landed = False
+        self.cuda_event = id(self)      # the handle the library gets (it records the event behind the colour stage)
 
     def record(self, stream=None):
         self.landed = _Event.auto_land
@@ -35,6 +36,12 @@ class _Event:
     def synchronize(self):
         _Event.waits += 1
         self.landed = True
+
+
+def _library_records_slot_event(item):
+    """What libfovgs does in a deferred frame: the scan kernel writes the statistics into the ring slot it was handed
+    (item["early"][0]) and the library records that slot's event on the stream behind the colour stage."""
+    item["ring_events"][item["ring_pos"]].record()
 
 
 @pytest.fixture
@@ -140,6 +147,8 @@ def test_prefiltered_violation_and_deferred_overflow_raise(stubbed):
             item["stats_np"][slot] = 0
             item["stats_np"][slot, 0] = 30_000_000
             item["stats_np"][slot, 1] = 1 if item["cap"] < 30_000_000 else 0
+            assert item["early"][0] == item["stats_ptr"] + 64 * slot        # the library is told to write THIS slot
+            _library_records_slot_event(item)
 
         item, st = stubbed._run_with_capacity(overflowing, dev, ops.MODE_FOV, 20, 32, 32, fresh_workspace=False)
         assert st is None and item["ring_pending"][0]                       # not inspected yet
@@ -155,8 +164,8 @@ def test_prefiltered_violation_and_deferred_overflow_raise(stubbed):
 
 
 def test_deferred_statistics_are_only_read_after_their_copy_landed(stubbed, monkeypatch):
-    """the host may run ahead of the GPU.  A frame's slot is inspected only once the event behind its 64-byte copy
-    says it has landed, every frame has its own slot (a ring), and an overflow in ANY frame is seen — not only the last one."""
+    """the host may run ahead of the GPU.  A frame's slot is inspected only once the event the library records
+    behind its statistics says they have landed, every frame has its own slot (a ring), and an overflow in ANY frame is seen — not only the last one."""
     dev = torch.device("cpu")
     frame = [0]
 
@@ -166,6 +175,7 @@ def test_deferred_statistics_are_only_read_after_their_copy_landed(stubbed, monk
         item["stats_np"][slot, 0] = 30_000_000 if frame[0] == 2 else 1000
         item["stats_np"][slot, 1] = 1 if (frame[0] == 2 and item["cap"] < 30_000_000) else 0
         frame[0] += 1
+        _library_records_slot_event(item)
 
     stubbed.set_deferred_check(True)
     try:
