@@ -229,6 +229,9 @@ def run_ours(args, wl, rank, world, dev):
                  rotations=sc["rotations"], shs_dcs=sc["shs_dcs"], highest_levels=sc["highest_levels"], gazeArray=gaze,
                  alpha=0.05, blending=True)
 
+    if os.environ.get("FOVGS_NO_DIRECT_STATS", "0") == "1":      # A/B switch (tools): statistics by cudaMemcpyAsync
+        from fovgs._lib import lib as _rawlib
+        assert _rawlib().fovgs_set_option(4, 1) == 0
     frames = [rank + i * world for i in range(args.steps + args.warmup)]
     with torch.no_grad():
         # ---------------- value: device-resident inputs, pipelined ----------------

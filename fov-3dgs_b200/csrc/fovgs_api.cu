@@ -294,6 +294,7 @@ int fovgs_set_option(int32_t option, int32_t value) {
         case FOVGS_OPT_FULL_SORT: g_force_full_sort = value != 0; return 0;
         case FOVGS_OPT_NO_TMA: g_no_tma = value != 0; return 0;
         case FOVGS_OPT_NO_PDL: g_no_pdl = value != 0; return 0;
+        case FOVGS_OPT_NO_DIRECT_STATS: g_no_direct_stats = value != 0; return 0;
         default: return fail(FOVGS_ERR_INVALID_ARG, "unknown option%s");
     }
 }

@@ -341,6 +341,7 @@ Workspace carve_workspace(void* base, int P, int W, int H, int64_t cap, Mode mod
 
 // ---- optional stage timing (bench.py roofline): CUDA events between the stages of a frame ----
 StageProfile g_prof;
+bool g_no_direct_stats = false;   // fovgs_set_option(FOVGS_OPT_NO_DIRECT_STATS, 1): early statistics by cudaMemcpyAsync (A/B)
 bool g_force_full_sort = false;   // fovgs_set_option(FOVGS_OPT_FULL_SORT, 1): always run the complete per-tile sort
 static inline void prof_mark(int i, cudaStream_t st) {
     if (!g_prof.enabled) return;
@@ -416,7 +417,8 @@ static cudaError_t forward_impl(const Workspace& ws, const FrameInputs& in, int 
     uint32_t* stats_host_dev = nullptr;
     if (in.early_stats_host != nullptr) {
         void* d = nullptr;
-        if (cudaHostGetDevicePointer(&d, in.early_stats_host, 0) == cudaSuccess) stats_host_dev = (uint32_t*)d;
+        if (g_no_direct_stats) d = nullptr;
+        else if (cudaHostGetDevicePointer(&d, in.early_stats_host, 0) == cudaSuccess) stats_host_dev = (uint32_t*)d;
         else (void)cudaGetLastError();
     }
     launch_tile_scan(ws, !lazy, stats_host_dev, st);  // one CTA, an ordinary launch; triggers its dependent on entry
