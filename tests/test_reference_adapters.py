@@ -155,7 +155,8 @@ def test_mmfr_adapter_calls_one_level_at_a_time(env):
     assert [c["means3D"] for c in calls] == [m.get_xyz.data_ptr() for m in models]
 
 
-@pytest.mark.parametrize("cuda_type,mode,n_out", [("pcheck_obb", 0, 4), ("pcheck_obb_sum", 1, 6), ("pcheck_obb_max", 2, 6)])
+@pytest.mark.parametrize("cuda_type,mode,n_out", [("pcheck_obb", 0, 4), ("pcheck_obb_sum", 1, 6), ("pcheck_obb_max", 2, 6),
+                                                  ("original", 4, 4)])   # gaussian_wrapper.py:11: the stock rasterizer
 def test_ps1_adapter_and_wrapper_run_unchanged(env, cuda_type, mode, n_out):
     mod = importlib.import_module("gaussian_renderer")
     pc = _model()
