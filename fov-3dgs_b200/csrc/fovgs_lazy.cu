@@ -46,6 +46,9 @@ constexpr int LCAP = LAZY_LCAP;
 #define LAZY_PREFETCH 0
 #endif
 constexpr int NSTAGE = LAZY_STAGE ? 2 : 1;
+#ifndef LAZY_RANK_MAX
+#define LAZY_RANK_MAX 256u
+#endif
 #ifndef LAZY_FIRST_GROUP
 #define LAZY_FIRST_GROUP 512u   // first sorted group of a partitioned tile; doubles up to LCAP
 #endif
@@ -260,7 +263,7 @@ struct PixSmfrBlend {
 // ---- shared-memory sort of the m keys in keys[0][0..m); returns the buffer index that holds the sorted keys ----------
 __device__ __forceinline__ int lazy_sort_group(LazySmem& sm, const uint32_t m) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (m <= 256) {
+    if (m <= LAZY_RANK_MAX) {   // rank sort: m comparisons per key; above this the radix passes below are cheaper
         uint64_t k = 0;
         uint32_t r = 0;
         if ((uint32_t)tid < m) {
