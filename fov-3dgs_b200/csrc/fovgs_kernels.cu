@@ -1,9 +1,9 @@
 // fovgs_kernels.cu — frame setup (header, tile-level tables), workspace carving and the forward launch sequence:
-//   k_setup, k_tile_levels, k_tile_infos -> k_pre (+ tile scan) -> k_color_tma -> k_scatter -> k_lazy_blend
-//   (with out_point_list / FOVGS_OPT_FULL_SORT: ... -> k_tile_sort_* -> k_blend)
+//   k_setup || k_tile_levels, k_tile_infos -> k_pre -> k_tile_scan || k_color_tma -> k_scatter -> k_lazy_blend (x2, overlapped)
+//   (with out_point_list / FOVGS_OPT_FULL_SORT: ... -> k_tile_sort_* -> k_blend);  || = programmatic-dependent-launch pair
 //
 // Design: binning is a two-level sort.  Level 1 is a counting sort by tile (histogram in k_pre, scan by
-// its last CTA, cursor scatter) which yields the reference's `ranges` for free; level 2 orders each tile's segment by
+// the one-CTA k_tile_scan beside the colour kernel, cursor scatter) which yields the reference's `ranges` for free; level 2 orders each tile's segment by
 // depth bits, ties by Gaussian id — lazily inside the blend kernel (fovgs_lazy.cu) or completely (fovgs_sort.cu) — which
 // reproduces exactly the order of the reference's stable 45-bit global radix sort
 // (FOV/cuda_rasterizer/rasterizer_impl.cu:843-854).  No host synchronisation anywhere.
