@@ -408,7 +408,17 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                 for (int k = 0; k < 6; k++) ws.cov3D[6 * (size_t)idx + k] = c3[k];
             }
             okx = __float_as_uint(1.0f / (float)max(cw, 1));
-            oky = hcode | (single0 ? 256u : 0u);
+            // The two tile-axis separations of the OBB test (below, per candidate) are monotone in the tile index — fl(a - t) is
+            // non-increasing in t — so when they hold at the candidate rectangle's two extreme columns and rows, evaluated with
+            // the very same operations, they hold for every tile in it: flag 512 lets phase B skip them (and their 16-byte
+            // shared load) for this splat.  The rectangle was clipped to a slightly widened band, so nearly every splat qualifies.
+            bool band_ok = false;
+            if (!single0 && cw > 0 && ch > 0) {
+                const float tcx_lo = FF((float)cx0, 16.0f, 8.0f), tcx_hi = FF((float)(cx1 - 1), 16.0f, 8.0f);
+                const float tcy_lo = FF((float)cy0, 16.0f, 8.0f), tcy_hi = FF((float)(cy1 - 1), 16.0f, 8.0f);
+                band_ok = !(FS(e_mxx, tcx_hi) < -8.0f) && !(FS(e_mnx, tcx_lo) > 8.0f) && !(FS(e_mxy, tcy_hi) < -8.0f) && !(FS(e_mny, tcy_lo) > 8.0f);
+            }
+            oky = hcode | (single0 ? 256u : 0u) | (band_ok ? 512u : 0u);
             okz = __float_as_uint(s.depth);
             rcw = cw; rcx = cx0; rcy = cy0;
         }
@@ -467,9 +477,13 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                     // arithmetic, so every decision is the reference's decision, bit for bit.
                     const float4 pc = wm.oc[owner];
                     const float4 pe = wm.oe[owner];
-                    const float4 px4 = wm.ox[owner];
                     const float tcx = FF((float)tx, 16.0f, 8.0f), tcy = FF((float)ty, 16.0f, 8.0f);
-                    if (FS(px4.y, tcx) < -8.0f || FS(px4.x, tcx) > 8.0f || FS(px4.w, tcy) < -8.0f || FS(px4.z, tcy) > 8.0f) {
+                    bool band_fail = false;
+                    if (!(ko.y & 512u)) {   // (rare: the splat's rectangle reaches past the exact band, see phase A)
+                        const float4 b4 = wm.ox[owner];
+                        band_fail = FS(b4.y, tcx) < -8.0f || FS(b4.x, tcx) > 8.0f || FS(b4.w, tcy) < -8.0f || FS(b4.z, tcy) > 8.0f;
+                    }
+                    if (band_fail) {
                         pass = false;
                     } else {
                         const float dx = tcx - pc.x, dy = tcy - pc.y;
@@ -477,9 +491,11 @@ __global__ void __launch_bounds__(PB, PRE_CTAS) k_pre(Workspace ws, FrameInputs 
                         const float t2 = fabsf(fmaf(pe.x, dx, pe.y * dy)) - pe.w;
                         const float eps = 4e-6f * (fabsf(dx) + fabsf(dy) + 16.0f);
                         if (t1 > eps || t2 > eps) pass = false;                        // separated along an eigen-axis, surely
-                        else if (!(t1 < -eps && t2 < -eps))                            // inside the rounding band (or NaN): exact
+                        else if (!(t1 < -eps && t2 < -eps)) {                          // inside the rounding band (or NaN): exact
+                            const float4 px4 = wm.ox[owner];
                             pass = obb_hits_tile_ext(px4.x, px4.y, px4.z, px4.w, pc.x, pc.y, pc.z, pc.w, pe.x, pe.y, wm.l1[owner],
                                                      wm.l2[owner], tcx, tcy);
+                        }
                     }
                 }
                 // RED (no return value).  Measured alternative: taking the returned rank here so that the scatter needs no
