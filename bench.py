@@ -776,8 +776,8 @@ def main():
             "config": config_of(wl, args),
             "clocks": res["clocks"],
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
-                    "mode": "default drop-in call: every call returns with its validated instance count (host waits for the "
-                            "statistics the library copies out after the tile scan)"},
+                    "mode": "default drop-in call: every call returns with its validated instance count (host waits for the event behind "
+                            "the colour stage; the tile-scan kernel has stored the statistics in its pinned buffer by then)"},
         }
         if res.get("extra") is not None:
             line["extra"] = res["extra"]
