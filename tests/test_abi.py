@@ -30,6 +30,24 @@ def test_library_exports_every_declared_symbol():
     assert L.fovgs_version() == _lib.FOVGS_VERSION == 202
 
 
+def test_python_constants_mirror_the_header():
+    """Enumerators and option numbers of include/fovgs.h against their mirrors in fovgs/_lib.py (a drifted constant would
+    select another variant silently: the PS=1 mode picks OBB test / falloff cut / statistics)."""
+    import re
+    from fovgs import _lib
+    text = open(os.path.join(ROOT, "include", "fovgs.h")).read()
+    enums = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\b(FOVGS_PS1_[A-Z]+)\s*=\s*(\d+)", text))
+    assert enums == {"FOVGS_PS1_OBB": 0, "FOVGS_PS1_SUM": 1, "FOVGS_PS1_MAX": 2, "FOVGS_PS1_LWMC": 3, "FOVGS_PS1_VANILLA": 4}
+    for name, value in enums.items():
+        assert getattr(_lib, name) == value, name
+    opts = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"#define\s+(FOVGS_OPT_[A-Z_]+)\s+(\d+)", text))
+    assert opts == {"FOVGS_OPT_FULL_SORT": 1, "FOVGS_OPT_NO_TMA": 2, "FOVGS_OPT_NO_PDL": 3, "FOVGS_OPT_NO_DIRECT_STATS": 4}
+    assert int(re.search(r"#define\s+FOVGS_VERSION\s+(\d+)", text).group(1)) == _lib.FOVGS_VERSION
+    # unknown modes / options are rejected before any CUDA call
+    L = _lib.lib()
+    assert L.fovgs_set_option(99, 1) != 0 and b"unknown option" in L.fovgs_last_error()
+
+
 def test_workspace_bytes_is_monotone_and_mode_dependent():
     from fovgs import _lib
     L = _lib.lib()
